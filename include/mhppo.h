@@ -1,0 +1,127 @@
+/* mhppo.h -- C ABI of libmhppo_b200.so: the B200 (sm_100a) drop-in for MH-PPO's hot path.
+ *
+ * The reference (BrunoudA/MH-PPO) has no FFI: its seam is the gym-0.26 `Env` Python API of the six
+ * `Environments/Env_hybrid_multi_*.py` classes plus the torch calls of `Env_rollout` / `Algo_PPO`
+ * in `Coop-MH-PPO-scalable.py`.  Each entry point below names the reference interface it replaces
+ * (file:line, abbreviations: SC = Environments/Env_hybrid_multi_coop_scalable.py, CO = .._coop.py,
+ * ST = .._stop.py, NA = .._naif.py, C4 = .._coop_4cars.py, C42 = .._coop_4cars2.py,
+ * PY = Coop-MH-PPO-scalable.py).  INTEGRATION.md shows the ctypes binding a maintainer would add.
+ *
+ * Conventions
+ *  - plain C types only; `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *  - every pointer named *_dev is device memory owned by the caller (e.g. torch tensor.data_ptr());
+ *    the library never frees or retains it past the call; *_host pointers are host memory;
+ *  - every call returns 0 on success or a negative MHPPO_E* code; mhppo_last_error() gives the text
+ *    for the calling thread; nothing throws, nothing allocates after *_create;
+ *  - all work is enqueued on `stream`, no hidden synchronisation (except the *_host entry points,
+ *    which synchronise `stream` before returning because they fill host buffers);
+ *  - one handle = one GPU = one host thread at a time.
+ *  - there is NO CPU fallback: without a CUDA device every call fails with MHPPO_ENODEV.
+ */
+#ifndef MHPPO_H
+#define MHPPO_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MHPPO_ABI_VERSION 1
+
+enum { MHPPO_OK = 0, MHPPO_EINVAL = -1, MHPPO_ENODEV = -2, MHPPO_ECUDA = -3, MHPPO_ENOMEM = -4,
+       MHPPO_EUNSUPPORTED = -5 };
+
+/* env classes of the reference, Environments/__init__.py:3-41 */
+enum { MHPPO_ENV_STOP = 0, MHPPO_ENV_NAIF = 1, MHPPO_ENV_COOP = 2, MHPPO_ENV_COOP_4CARS = 3,
+       MHPPO_ENV_COOP_4CARS2 = 4, MHPPO_ENV_COOP_SCALABLE = 5 };
+
+/* Constructor arguments of the env classes (SC:680: car_b, ped_b, cross_b, nb_car, nb_ped, nb_lines,
+ * dt, max_episode, simulation) plus what a vectorised env needs (n_envs, RNG stream, device). */
+typedef struct mhppo_env_cfg {
+    int32_t variant;      /* MHPPO_ENV_* */
+    int32_t nb_car, nb_ped, nb_lines;
+    int32_t max_episode;  /* 80 in the drivers (PY:1026) */
+    int32_t sin_model;    /* simulation == "sin" */
+    int32_t device;       /* CUDA device ordinal */
+    int32_t reserved;
+    double dt;            /* 0.3 */
+    double car_b[4];      /* row-major 2x2 */
+    double ped_b[8];      /* row-major 2x4 */
+    double cross_b[2];
+    uint64_t seed;        /* Philox key (RNG contract: DESIGN.md "RNG") */
+    int64_t n_envs;       /* envs held by this handle */
+    int64_t env_id0;      /* global id of env 0: rank r of R passes r*n_envs so shards are disjoint streams */
+} mhppo_env_cfg;
+
+typedef struct mhppo_env_dims {
+    int32_t n_slots;      /* car slots in state: nb_car | 2*nb_car (4cars*) | 2*nb_lines (scalable) */
+    int32_t n_lead;       /* cars with a reward / reward_light entry */
+    int32_t n_action;     /* action vector length, [acc.., light..] as in SC:798-802 / C42:809-811 */
+    int32_t n_obs;        /* flat observation: keys in gym-0.26 Dict order car,(car_follow),env,ped */
+    int32_t n_ped;
+    int32_t done_step;    /* step index whose step() returns done (79 for dt=.3, max_episode=80) */
+    int32_t reserved[2];
+} mhppo_env_dims;
+
+/* A 2-D fp32 view [n_envs, width] with element strides, so callers may keep either the gym layout
+ * (env_stride = width, comp_stride = 1) or the coalesced device layout (env_stride = 1,
+ * comp_stride = n_envs).  ptr == NULL means "not wanted" for outputs. */
+typedef struct mhppo_view {
+    float *ptr;
+    int64_t env_stride;
+    int64_t comp_stride;
+} mhppo_view;
+
+int mhppo_abi_version(void);
+const char *mhppo_last_error(void);
+int mhppo_device_count(void);
+
+/* gym.make(id, **cfg) / Crosswalk_hybrid_multi_*.__init__  (SC:680-736, REG:3-41) */
+int mhppo_env_create(const mhppo_env_cfg *cfg, void **handle);
+int mhppo_env_destroy(void *handle);
+int mhppo_env_get_dims(void *handle, mhppo_env_dims *dims);
+
+/* Crosswalk_hybrid_multi_*.reset  (SC:884-946, CO:838-892, ST:847, NA:829, C4:850-911, C42:866-927).
+ * mask_dev: uint8[n_envs] or NULL (= all). obs receives the first observation of reset envs only. */
+int mhppo_env_reset(void *handle, const uint8_t *mask_dev, mhppo_view obs_dev, void *stream);
+
+/* Crosswalk_hybrid_multi_*.step  (SC:789-878, CO:745-832, ST:754, NA:736, C4:783-844, C42:799-860).
+ * actions [n_envs,n_action]; obs [n_envs,n_obs]; rewards, reward_light (= env.reward_light, SC:846)
+ * [n_envs,n_lead]; done uint8[n_envs].  autoreset != 0: a done env is re-initialised inside the same
+ * kernel (gym vector convention): obs = first observation of the new episode, term_obs (optional) =
+ * terminal observation. */
+int mhppo_env_step(void *handle, mhppo_view actions_dev, mhppo_view obs_dev, mhppo_view rewards_dev,
+                   mhppo_view reward_light_dev, uint8_t *done_dev, int autoreset, mhppo_view term_obs_dev,
+                   void *stream);
+
+/* Same call for HOST buffers in the reference's own layout (row-major [n_envs, width], what
+ * env.step(np.ndarray) takes and returns): copies actions host->device, steps, copies the results
+ * back and synchronises `stream`.  Pinned staging lives in the handle. */
+int mhppo_env_step_host(void *handle, const float *actions_host, float *obs_host, float *rewards_host,
+                        float *reward_light_host, uint8_t *done_host, int autoreset, void *stream);
+int mhppo_env_reset_host(void *handle, float *obs_host, void *stream);
+
+/* get_state()/reset_pedestrian()/reset_cars() of the reference read/poke Python attributes
+ * (SC:948-969).  The vectorised equivalent moves the whole state as the canonical dump
+ *   car_f [N,C,7] Ac,Vc,Sc,light,possible_accident,error_scenario,Ts      car_i [N,C,2] line,exist
+ *   ped_f [N,P,9] Vp_x,Vp_y,Sp_x,Sp_y,v0x,v0y,cross_stop,delta,worst_dl
+ *   ped_i [N,P,9] t0/dt,waiting_time/dt,crossing_time/dt,time_stop,line_pos,direction,gender,age,flags
+ *   env_f [N,1]   cross (fp64)                env_i [N,4] step_idx,ped_traffic,car_traffic,rng_ctr
+ * flags bits: 0 exist,1 is_crossing,2 decision,3 at_crossing,4 ped_left,5 ped_in_cross,
+ * 6 ped_not_waiting,7 accident,8 worst_scenario_accident,9 follow_rule,10 stop,11 need_to_stop.
+ * All pointers are device memory. */
+int mhppo_env_export_state(void *handle, float *car_f_dev, int32_t *car_i_dev, float *ped_f_dev,
+                           int32_t *ped_i_dev, double *env_f_dev, int64_t *env_i_dev, void *stream);
+int mhppo_env_import_state(void *handle, const float *car_f_dev, const int32_t *car_i_dev,
+                           const float *ped_f_dev, const int32_t *ped_i_dev, const double *env_f_dev,
+                           const int64_t *env_i_dev, void *stream);
+
+/* bytes of HBM the handle holds per env (state arena), for the roofline accounting */
+int64_t mhppo_env_state_bytes_per_env(void *handle);
+/* number of kernel launches this library has issued in this process (bench.py "gpu_launches") */
+int64_t mhppo_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,78 @@
+"""ctypes binding of libmhppo_b200.so (the C ABI of include/mhppo.h).  Fails loudly if the library
+has not been built (`python mh-ppo_b200/build.py`) -- there is no fallback path."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmhppo_b200.so")
+
+
+class LibraryMissing(RuntimeError):
+    pass
+
+
+class MhppoError(RuntimeError):
+    pass
+
+
+class EnvCfg(C.Structure):
+    _fields_ = [("variant", C.c_int32), ("nb_car", C.c_int32), ("nb_ped", C.c_int32), ("nb_lines", C.c_int32),
+                ("max_episode", C.c_int32), ("sin_model", C.c_int32), ("device", C.c_int32), ("reserved", C.c_int32),
+                ("dt", C.c_double), ("car_b", C.c_double * 4), ("ped_b", C.c_double * 8), ("cross_b", C.c_double * 2),
+                ("seed", C.c_uint64), ("n_envs", C.c_int64), ("env_id0", C.c_int64)]
+
+
+class EnvDims(C.Structure):
+    _fields_ = [("n_slots", C.c_int32), ("n_lead", C.c_int32), ("n_action", C.c_int32), ("n_obs", C.c_int32),
+                ("n_ped", C.c_int32), ("done_step", C.c_int32), ("reserved", C.c_int32 * 2)]
+
+
+class View(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("env_stride", C.c_int64), ("comp_stride", C.c_int64)]
+
+
+# every symbol include/mhppo.h declares (tests/test_abi.py checks the list against the header)
+SYMBOLS = {
+    "mhppo_abi_version": (C.c_int, []),
+    "mhppo_last_error": (C.c_char_p, []),
+    "mhppo_device_count": (C.c_int, []),
+    "mhppo_env_create": (C.c_int, [C.POINTER(EnvCfg), C.POINTER(C.c_void_p)]),
+    "mhppo_env_destroy": (C.c_int, [C.c_void_p]),
+    "mhppo_env_get_dims": (C.c_int, [C.c_void_p, C.POINTER(EnvDims)]),
+    "mhppo_env_reset": (C.c_int, [C.c_void_p, C.c_void_p, View, C.c_void_p]),
+    "mhppo_env_step": (C.c_int, [C.c_void_p, View, View, View, View, C.c_void_p, C.c_int, View, C.c_void_p]),
+    "mhppo_env_step_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_int, C.c_void_p]),
+    "mhppo_env_reset_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mhppo_env_export_state": (C.c_int, [C.c_void_p] * 8),
+    "mhppo_env_import_state": (C.c_int, [C.c_void_p] * 8),
+    "mhppo_env_state_bytes_per_env": (C.c_int64, [C.c_void_p]),
+    "mhppo_launch_count": (C.c_int64, []),
+}
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise LibraryMissing("%s not built: run `python mh-ppo_b200/build.py` (nvcc, sm_100a). "
+                                 "mhppo_b200 has no CPU fallback." % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, args
+        if L.mhppo_abi_version() != 1:
+            raise MhppoError("ABI version mismatch")
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise MhppoError("mhppo error %d: %s" % (rc, lib().mhppo_last_error().decode()))
+
+
+def launch_count():
+    return int(lib().mhppo_launch_count())

@@ -1,0 +1,665 @@
+// env_core.cuh -- one crosswalk env advanced by one thread, state held in registers.
+//
+// This is the device-side semantics of `Crosswalk_hybrid_multi_{stop,naif,coop,coop_4cars,
+// coop_4cars2,coop_scalable}.step/reset` (reference: Environments/Env_hybrid_multi_*.py; citation
+// abbreviations SC/CO/ST/NA/C4/C42 as in include/mhppo.h).  One templated body covers the six
+// classes; the behavioural deltas between the files are compile-time switches (`VT<V>`).
+//
+// Design (B200-first, not a translation of the Python object graph):
+//  * thread = env, lane = env inside a warp; car/ped slots are fully unrolled register arrays, so
+//    the reference's filtered Python lists become bit masks over slots (order preserved);
+//  * persisted state is fp32 / packed integers in HBM (env_state.cuh), arithmetic is fp64 in the
+//    reference's operation order (compile with -fmad=false) so threshold flags are bit-exact and
+//    values differ from the fp64 reference only by the final fp32 rounding;
+//  * time, t0, waiting_time and crossing_time are integer multiples of dt;
+//  * the data-dependent RNG consumption of the reference is reproduced with a per-env Philox
+//    cursor (philox.cuh); throw-away draws (SC:153) just advance the counter;
+//  * auto-reset runs inside the step kernel through a non-inlined reset on a scratch copy.
+//
+// The file is also compilable as plain C++ (tests/hostsim) so the kernel logic can be unit-tested
+// against the golden fixtures on a machine without a GPU; the product never runs that build.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#include "philox.cuh"
+
+#ifdef __CUDACC__
+#define MH_NOINLINE __host__ __device__ __noinline__
+#else
+#define MH_NOINLINE __attribute__((noinline))
+#endif
+
+namespace mhppo {
+
+enum { V_STOP = 0, V_NAIF = 1, V_COOP = 2, V_4CARS = 3, V_4CARS2 = 4, V_SCAL = 5 };
+
+// pedestrian flag bits: positions are those of the canonical state dump (include/mhppo.h)
+enum : uint32_t {
+    PF_EXIST = 1u << 0, PF_CROSSING = 1u << 1, PF_DECISION = 1u << 2, PF_AT_CROSSING = 1u << 3,
+    PF_LEFT = 1u << 4, PF_IN_CROSS = 1u << 5, PF_NOT_WAITING = 1u << 6, PF_ACCIDENT = 1u << 7,
+    PF_WORST_ACC = 1u << 8, PF_FOLLOW = 1u << 9, PF_STOP = 1u << 10, PF_NEED_STOP = 1u << 11
+};
+
+// compile-time behaviour table of the six env files ("Behavioural deltas")
+template <int V>
+struct VT {
+    static constexpr bool scal = (V == V_SCAL);
+    static constexpr bool four = (V == V_4CARS || V == V_4CARS2);
+    static constexpr bool naif = (V == V_NAIF);
+    static constexpr bool stop = (V == V_STOP);
+    static constexpr bool burn_shuffle = (V == V_STOP || V == V_COOP || V == V_SCAL);  // SC:153 ST:152 CO:152
+    static constexpr bool has_need_to_stop = (V == V_STOP || V == V_4CARS2 || V == V_SCAL);  // SC:371 ST:366 C42:448
+    static constexpr bool draws_need_to_stop = has_need_to_stop;                     // SC:91
+    static constexpr bool draws_cross_stop = (V == V_STOP || V == V_COOP || V == V_4CARS2 || V == V_SCAL);  // SC:92 CO:91
+    static constexpr bool placeholder_keeps_x = (V == V_COOP || V == V_SCAL);        // CO:68 vs ST:68
+    static constexpr int nts_lo = stop ? 2 : 5, nts_hi = stop ? 15 : 35;             // ST:367, SC:372
+    static constexpr int rs_lo = (V == V_4CARS2) ? 5 : 2;                            // C42:480
+    static constexpr int rs_hi = stop ? 15 : ((V == V_4CARS2) ? 35 : 5);             // ST:402, SC:406
+    static constexpr double far = scal ? 100.0 : 0.0;                                // SC:191,509,525 vs CO:190,493,509
+    static constexpr bool neg_dl = (V == V_STOP || V == V_NAIF);                     // ST:197 NA:200: -dl-1
+    static constexpr int danger_sign = (V == V_STOP || V == V_COOP || V == V_4CARS2) ? +1
+                                       : ((V == V_4CARS || V == V_SCAL) ? -1 : 0);   // SC:258 CO:256 C4:345 NA:252
+    static constexpr double wait_thr = stop ? 0.01 : 0.05;                           // ST:478 / SC:482
+    static constexpr double Ts0 = scal ? 0.0 : -10.0;                                // SC:555 / CO:539
+    static constexpr int car_w = scal ? 7 : 6;                                       // SC:655 / CO:612
+};
+
+struct CarR {
+    double Vc, Sc, light, Ac, pa, es, Ts;
+    int line, exist;
+};
+struct PedR {
+    double Spx, Spy, Vpx, Vpy, v0x, v0y, cstop, delta, wdl;
+    int t0c, waitc, crossc, tstop, lpos, dir, gender, age;
+    uint32_t fl;
+};
+template <int MC, int MP>
+struct EnvR {
+    double cross;
+    int step, ped_traffic, car_traffic;
+    Rng rng;
+    CarR car[MC];
+    PedR ped[MP];
+};
+
+// runtime configuration shared by every env of a handle (kernel argument, by value)
+struct EnvConst {
+    int nC, nP, L, nb_car, nlead, nA, nobs, done_idx, sin_model;
+    double dt, acc_lo, acc_hi;       // car_b[0,0], car_b[1,0]
+    double pb[8];                    // ped_b row-major
+    double cross_lo, cross_hi;       // cross_b
+};
+
+struct Geo {
+    double cross, W, Hn, Hp, Lf;     // Hn = -W/2, Hp = W/2
+};
+MH_HD Geo make_geo(double cross, int L) {
+    Geo g; g.cross = cross; g.Lf = (double)L; g.W = g.Lf * cross; g.Hn = (-g.W) / 2.0; g.Hp = g.W / 2.0;
+    return g;
+}
+
+MH_HD double dmin(double a, double b) { return b < a ? b : a; }   // Python min(a, b)
+MH_HD double dmax(double a, double b) { return b > a ? b : a; }   // Python max(a, b)
+
+// pedestrian.is_in_front, SC:463-468
+MH_HD bool in_front(const Geo &g, const PedR &p, int line, double nl) {
+    if (p.dir == -1) return p.Spy >= (g.Hp - g.cross * ((g.Lf - 0.5 * nl) - (double)line)) - 0.001;
+    return p.Spy <= (g.Hn + g.cross * (((double)line - 0.5 * nl) + 1.0)) + 0.001;
+}
+// pedestrian.is_crossing_in_front, SC:470-476
+MH_HD bool crossing_in_front(const Geo &g, const PedR &p, int line, double pl) {
+    if (p.dir == -1) return p.Spy < g.Hp - g.cross * (((g.Lf - (double)line) - 1.0) - pl);
+    return p.Spy > g.Hn + g.cross * ((double)line - pl);
+}
+
+// pedestrian.CG_score, SC:419-428 -- one normal draw, only for crossing pedestrians
+MH_HD double cg_score(const PedR &p, double size, Rng &rng) {
+    if (!(p.fl & PF_CROSSING)) return 0.0;
+    double lv = 0.09 + log10(size / fabs(p.v0y + 10e-3));
+    lv = lv + 0.0369 * (double)(p.gender == 1);
+    lv = lv + -0.0355 * (double)(p.age == 0);
+    lv = lv + -0.0221 * (double)(p.age == 1);
+    lv = lv + -0.1810 * (double)(p.age == 2);
+    lv = lv + rng.normal(0.0, 0.09);
+    return pow(10.0, lv);
+}
+
+// pedestrian.choix_pedestrian, SC:139-174 / NA:138-177.  `seen` = slots handed to pedestrian.step
+// (existing cars in scalable SC:803-806, leaders+followers in 4cars C4:796-799, all otherwise).
+template <int V, int MC>
+MH_HD bool choix(const Geo &g, const PedR &p, const CarR (&car)[MC], uint32_t seen, int nseen, Rng &rng) {
+    typedef VT<V> T;
+    if (p.fl & PF_FOLLOW) {
+        if (T::naif) {
+            // NA:151 really permutes the visiting order (every naif car exists: slot == list index)
+            uint64_t ord = 0xFEDCBA9876543210ull;
+            if (nseen > 1)
+                for (int i = nseen - 1; i > 0; --i) {
+                    int j = (int)floor(rng.random() * (double)(i + 1));
+                    if (j > i) j = i;
+                    const uint64_t a = (ord >> (4 * i)) & 15u, b = (ord >> (4 * j)) & 15u;
+                    ord &= ~((15ull << (4 * i)) | (15ull << (4 * j)));
+                    ord |= (b << (4 * i)) | (a << (4 * j));
+                }
+            for (int k = 0; k < nseen; ++k) {                      // NA:153-155
+                const int i = (int)((ord >> (4 * k)) & 15u);
+                bool hit = false;
+#pragma unroll
+                for (int s = 0; s < MC; ++s)
+                    if (s == i)
+                        hit = crossing_in_front(g, p, car[s].line, 0.5) && in_front(g, p, car[s].line, 1.0) &&
+                              (car[s].Sc < 4.0 + p.Spx) && (car[s].Sc > p.Spx);
+                if (hit) return false;
+            }
+            for (int k = 0; k < nseen; ++k) {                      // NA:156-158
+                const int i = (int)((ord >> (4 * k)) & 15u);
+                bool hit = false;
+#pragma unroll
+                for (int s = 0; s < MC; ++s)
+                    if (s == i) hit = (car[s].Sc < p.Spx) && (car[s].light < 0.0);
+                if (hit) return false;
+            }
+        } else {
+            if (T::burn_shuffle && nseen > 1) rng.skip(nseen - 1);  // SC:152-153: shuffles a temporary
+#pragma unroll
+            for (int i = 0; i < MC; ++i)                            // SC:154-158
+                if ((seen >> i) & 1u)
+                    if (crossing_in_front(g, p, car[i].line, 0.5) && in_front(g, p, car[i].line, 1.0))
+                        if ((car[i].Sc < 4.0 + p.Spx) && (car[i].Sc > p.Spx)) return false;
+#pragma unroll
+            for (int i = 0; i < MC; ++i)                            // SC:159-161
+                if ((seen >> i) & 1u)
+                    if (car[i].Sc < p.Spx && car[i].light != 0.0) return car[i].light > 0.0;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < MC; ++i) {                                  // SC:162-173
+        if (!((seen >> i) & 1u)) continue;
+        if (in_front(g, p, car[i].line, 1.0)) {
+            if ((car[i].Sc < 4.0 + p.Spx) && (car[i].Sc > p.Spx)) return false;
+            if (car[i].Sc < p.Spx) {
+                const double car_time = fabs((car[i].Sc - p.Spx) / (car[i].Vc + 10e-3));
+                const double CG = cg_score(p, fabs((double)(p.lpos - car[i].line)) * g.cross, rng);
+                if (car_time + car[i].light < CG) return false;
+            }
+        }
+    }
+    return true;
+}
+
+// pedestrian.function_step: sin profile SC:436-443 (parameters SC:94-102) or uniform SC:433-434
+MH_HD void walk_model(const EnvConst &c, const Geo &g, const PedR &p, int step, double &pos, double &spd) {
+    if (c.sin_model && (p.fl & PF_CROSSING)) {
+        const double PI_ = 3.141592653589793, Vm = 2.5;
+        const double av = fabs(p.v0y);
+        const double T = g.W / (av + 10e-3);
+        const bool check = ((av * PI_) / 2.0 <= Vm);
+        const double A = check ? (PI_ * av / 2.0 + 0.0) : (0.0 + (Vm - av) / (1.0 - (2.0 / PI_)));
+        const double B = check ? 0.0 : (Vm - A);
+        const double w = PI_ / T;
+        const double t = (double)step * c.dt + c.dt, t0 = (double)p.t0c * c.dt;
+        const double ph = w * (t - t0);
+        double sn, cs;
+        sincos(ph, &sn, &cs);
+        const double speed_p = A * sn + B;
+        const double pos_p = g.Hn + (A * (-cs + 1.0) / w);
+        if (!(pos_p >= 0.0 && speed_p < av)) {
+            pos = (double)p.dir * pos_p; spd = (double)p.dir * speed_p;
+            return;
+        }
+    }
+    pos = p.Spy + p.v0y * c.dt; spd = p.v0y;
+}
+
+// pedestrian.step, SC:297-417
+template <int V, int MC>
+MH_HD void ped_step(const EnvConst &c, const Geo &g, PedR &p, const CarR (&car)[MC], uint32_t seen, int nseen,
+                    int step, Rng &rng) {
+    typedef VT<V> T;
+    const double dt = c.dt;
+    const double pp_y = p.Spy + p.v0y * dt;                                          // SC:298
+    const double dy = (double)p.dir * p.Spy;                                         // boolean_ped_position SC:266-275
+    p.fl &= ~(PF_LEFT | PF_IN_CROSS);
+    if (dy >= g.Hp) p.fl |= PF_LEFT;
+    else if (dy > g.Hn) p.fl |= PF_IN_CROSS;
+    if (!(p.fl & PF_CROSSING)) return;                                               // SC:308
+    bool choose = true;
+    if (!(p.fl & PF_DECISION) && (p.fl & PF_AT_CROSSING)) {                          // SC:311-318
+        choose = choix<V, MC>(g, p, car, seen, nseen, rng);
+        if (choose) { p.lpos = (p.dir < 0) ? (c.L - 1) : 0; p.fl &= ~PF_AT_CROSSING; }
+        p.fl |= PF_DECISION;
+        p.t0c = step;
+    }
+    if ((dy < g.Hn) && (pp_y * (double)p.dir > g.Hn) && !(p.fl & PF_DECISION)) {     // SC:320-328
+        const double px = (p.Vpx * dt) * (fabs(g.Hn - dy) / fabs(p.Vpy * dt + 10e-3));
+        p.Vpx = px / dt;
+        p.Spx = p.Spx + px;
+        p.Vpy = (double)p.dir * fabs(-dy - g.Hp) / dt;
+        p.Spy = (double)(-p.dir) * g.W / 2.0;
+        p.tstop = 0;
+        p.fl |= PF_AT_CROSSING;
+    } else if ((fabs(p.Spy) <= g.Hp) || (p.fl & PF_DECISION)) {                      // SC:331
+        if (p.tstop != 0) {                                                          // SC:335-339
+            p.Vpx = 0.0; p.Vpy = 0.0; p.tstop -= 1; p.t0c += 1;
+        } else {
+            const double u = rng.random();                                           // SC:346: always drawn
+            if ((u < 0.98) && choose) {
+                p.fl &= ~PF_DECISION;
+                double ny, nv;
+                walk_model(c, g, p, step, ny, nv);                                   // SC:348
+                bool change_line = false;                                            // will_change_line SC:281-286
+                if (fabs(ny) < g.Hp) {
+                    const double nl = floor((ny + g.Hp) / g.cross);
+                    if (nl != (double)p.lpos && fabs(p.Spy) < g.Hp) change_line = true;
+                }
+                double dtc = ((double)(c.L - p.lpos - 1) * g.cross) * (double)(p.dir > 0);   // SC:350-351
+                dtc += ((double)p.lpos * g.cross) * (double)(p.dir < 0);
+                bool new_choice = false;
+                if (change_line && (dtc > 0.0 && dtc < g.W)) {                       // SC:353-357
+                    new_choice = choix<V, MC>(g, p, car, seen, nseen, rng);
+                    if (new_choice) p.fl &= ~PF_STOP;
+                }
+                if (p.fl & PF_STOP) {                                                // SC:363-369
+                    p.Vpx = 0.0; p.Vpy = 0.0; p.t0c += 1;
+                    if (change_line) p.waitc += 1;
+                } else if (T::has_need_to_stop && (p.fl & PF_NEED_STOP) && p.Spy < p.cstop && pp_y > p.cstop) {
+                    p.tstop = rng.randint(T::nts_lo, T::nts_hi);                     // SC:371-380
+                    p.fl &= ~PF_NEED_STOP;
+                    p.Vpx = 0.0; p.Vpy = 0.0; p.t0c += 1;
+                } else if (!change_line || new_choice) {                             // SC:382-387
+                    const double ratio = p.v0x / p.v0y;                              // SC:73
+                    p.Spy = ny; p.Vpy = nv;
+                    p.Spx = p.Spx + p.Vpy * ratio * dt;
+                    p.Vpx = p.Vpy * ratio;
+                    p.crossc += 1;
+                    if (change_line) {                                               // apply_change_line SC:288-294
+                        if (fabs(ny) >= g.Hp) p.lpos = (p.dir < 0) ? c.L : ((p.dir > 0) ? -1 : 0);
+                        else p.lpos = (int)floor((ny + g.Hp) / g.cross);
+                    }
+                } else {                                                             // SC:389-397
+                    p.fl |= PF_STOP;
+                    const double d = fabs(((double)p.dir * (g.W - dtc) - (double)p.dir * g.W / 2.0) - p.Spy);
+                    const double px = p.Vpx * d / fabs(p.Vpy + 10e-3);
+                    p.Vpx = px / dt;
+                    p.Spx = p.Spx + px;
+                    p.Vpy = (double)p.dir * d / dt;
+                    p.Spy = (double)p.dir * ((g.W - dtc) - g.W / 2.0);
+                }
+            } else {                                                                 // SC:405-413
+                p.tstop = rng.randint(T::rs_lo, T::rs_hi);
+                if (!choose) { p.fl &= ~PF_DECISION; p.tstop = 0; p.waitc += 1; }
+                p.Vpx = 0.0; p.Vpy = 0.0; p.t0c += 1;
+            }
+        }
+    } else {                                                                         // SC:415-417
+        p.Spx = p.Spx + p.v0x * dt; p.Vpx = p.v0x;
+        p.Spy = p.Spy + p.v0y * dt; p.Vpy = p.v0y;
+    }
+}
+
+// pedestrian.worst_delta_l, SC:522-527
+template <int V>
+MH_HD double worst_delta_l(const EnvConst &c, const Geo &g, const PedR &p, const CarR &k) {
+    if (k.Sc > p.Spx || (p.fl & PF_LEFT) || !in_front(g, p, k.line, 0.0)) return VT<V>::far;
+    return fabs(k.Sc - p.Spx) - (k.Vc * k.Vc / (-2.0 * c.acc_lo));
+}
+
+// pedestrian.detection, SC:176-264; `res` is accumulated into reward_light by the caller (SC:841-846)
+template <int V, int MC>
+MH_HD void detection(const EnvConst &c, const Geo &g, PedR &p, CarR (&car)[MC], const double (&prevSc)[MC],
+                     double (&res)[MC]) {
+    typedef VT<V> T;
+    const double time_braking = -(10.0 / (2.0 * c.acc_lo)) + 1.0;                    // SC:580 (Vc = 10 at construction)
+    const double wait_t = (double)p.waitc * c.dt, cross_t = (double)p.crossc * c.dt;
+#pragma unroll
+    for (int i = 0; i < MC; ++i) {
+        if (i >= c.nlead) continue;                                                  // C4:815: leaders only
+        CarR &k = car[i];
+        if (!in_front(g, p, k.line, 0.0)) continue;                                  // SC:180
+        if (T::scal && !k.exist) continue;
+        const bool cif = crossing_in_front(g, p, k.line, 0.0);
+        const double wdl = worst_delta_l<V>(c, g, p, k);
+        bool ped_accident;
+        if (T::naif) {                                                               // NA:181-185: new flag first
+            p.fl = (wdl < 0.0) ? (p.fl | PF_WORST_ACC) : (p.fl & ~PF_WORST_ACC);
+            ped_accident = !(p.fl & PF_ACCIDENT) && (p.fl & PF_WORST_ACC);
+        } else {                                                                     // SC:181-182
+            ped_accident = !(p.fl & PF_ACCIDENT) && (p.fl & PF_WORST_ACC);
+            p.fl = (wdl < 0.0) ? (p.fl | PF_WORST_ACC) : (p.fl & ~PF_WORST_ACC);
+        }
+        if (ped_accident && cif && (prevSc[i] < p.Spx) && (k.Sc > p.Spx)) p.fl |= PF_ACCIDENT;   // SC:184-185
+        if (cif) {                                                                   // SC:187-201
+            const double dl = (k.Vc < 0.05) ? T::far : wdl / k.Vc;
+            double pa;
+            if (dl > 0.0) pa = -1.0 * exp(-4.0 * dl);
+            else pa = T::neg_dl ? (-1.0 * dl - 1.0) : (1.0 * dl - 1.0);
+            k.pa = dmin(k.pa, pa);
+        }
+        if (k.Sc < p.Spx) {                                                          // SC:206-208 / NA:207-208
+            double ts;
+            if (T::naif) ts = ((wait_t + 10.0 * cross_t) - time_braking) + 1.0;
+            else {
+                double nwait = 0.0;
+#pragma unroll
+                for (int q = 0; q < MC; ++q)
+                    if (q < c.nlead && car[q].light > 0.0 && car[q].Sc < p.Spx && (!T::scal || car[q].exist)) nwait += 1.0;
+                ts = (((1.0 + nwait) * wait_t + 2.0 * cross_t) - time_braking) + 1.0;
+            }
+            k.Ts = dmax(ts, k.Ts);
+        }
+        if (k.light < 0.0) {                                                         // SC:216-228
+            const double ne = (k.Ts < 0.0) ? (-1.0 * exp(4.0 * k.Ts)) : (-1.0 * (1.0 + k.Ts));
+            if (!T::naif && cif && (k.Sc < p.Spx)) p.fl |= PF_NOT_WAITING;
+            k.es = dmin(ne, k.es);
+        }
+        if (k.light > 0.0) {                                                         // SC:230-237
+            const double gap = p.Spx - k.Sc;
+            const double ne = (gap > 0.0) ? (-1.0 * exp(-4.0 * gap)) : (-1.0 * ((1.0 + k.Sc) - p.Spx));
+            k.es = dmin(ne, k.es);
+        }
+    }
+    double green = 0.0;                                                              // SC:246
+#pragma unroll
+    for (int q = 0; q < MC; ++q)
+        if (q < c.nlead && car[q].light > 0.0 && (!T::scal || car[q].exist)) green += 1.0;
+#pragma unroll
+    for (int i = 0; i < MC; ++i) {                                                   // SC:250-263
+        double r = car[i].pa + car[i].es;
+        if (T::danger_sign != 0) {
+            const double extra = (0.5 * green * (double)(car[i].light < 0.0)) * (double)(car[i].Ts > 0.0);
+            r = (T::danger_sign > 0) ? (r + extra) : (r - extra);
+        }
+        if (T::scal && !car[i].exist) r = 0.0;
+        res[i] = r;
+    }
+}
+
+// pedestrian.new_reward_wait_safety, SC:478-506 (+ delta_l SC:516-520)
+template <int V>
+MH_HD double wait_safety(const EnvConst &c, const Geo &g, PedR &p, const CarR &k) {
+    if (!(p.fl & PF_LEFT) && (p.fl & PF_CROSSING) && (k.Sc < p.Spx) && in_front(g, p, k.line, 0.0)) {
+        double e;
+        if (k.Vc < VT<V>::wait_thr) e = 0.0;
+        else {
+            const double d = (fabs(k.Sc - p.Spx) - (k.Vc * k.Vc / (-2.0 * c.acc_lo))) - 1.0 * k.Vc;
+            const double dl = d / k.Vc;
+            if (dl >= -1.0) e = dmax(-20.0 * exp(-4.0 * dl - 4.0), -20.0);
+            else e = 20.0 * dl;
+        }
+        e = e - ((p.fl & PF_ACCIDENT) ? 20.0 : 0.0);
+        if (e < p.wdl) p.wdl = e;
+    }
+    return p.wdl;
+}
+
+// car.sigma SC:592-602
+MH_HD double sigma_lim(double Vc, double a, double dt) {
+    if (Vc == 0.0) return (a > 0.0) ? 1.0 : 0.0;       // max(0, a/|a|); a == 0 -> 0
+    if (a > 0.0) return 1.0;
+    return dmax(dmin(-Vc / (dt * a), 1.0), 0.0);
+}
+// car.follow_action SC:604-624 (IDM; car_follower.follow_action C4:109-129)
+MH_HD double idm(const EnvConst &c, const CarR &k, double leadSc, double leadVc) {
+    const double dd = leadSc - k.Sc;
+    const double dv = k.Vc - leadVc;
+    const double s = (2.0 + (k.Vc * 2.0)) + (k.Vc * dv) / (2.0 * sqrt(-c.acc_lo * c.acc_hi));
+    const double r4 = k.Vc / 10.0, r2 = s / dd;
+    return c.acc_hi * ((1.0 - (r4 * r4) * (r4 * r4)) - r2 * r2);
+}
+// car.step SC:627-650 (ST:599-618 adds the clamp; car_follower.transform C4:79-93)
+template <int V>
+MH_HD void car_move(const EnvConst &c, CarR &k, double action, double light) {
+    double a = dmin(dmax(action, c.acc_lo), c.acc_hi);                               // acceleration() SC:589-590
+    const double sg = sigma_lim(k.Vc, a, c.dt);
+    if (VT<V>::stop && sg > 0.0) a = dmax(a, -k.Vc / (c.dt * sg));                   // ST:604-605
+    const double fa = a * sg;                                                        // discount [1,0,0] is the identity
+    const double v = k.Vc + c.dt * fa;
+    const double s = ((fa * (c.dt * c.dt)) / 2.0 + (k.Vc * c.dt)) + k.Sc;
+    k.Ac = fa; k.Vc = v; k.Sc = s; k.light = light;
+}
+
+// ---------------------------------------------------------------------------------------------
+// observation writer: car.get_data SC:652-655, env row SC:871, pedestrian.get_data SC:449-460 with
+// delta_l_all SC:508-514.  Out(k, value) stores component k of this env's flat observation
+// (key order car,(car_follow),env,ped).  Mutates the running-min `delta` exactly like get_data.
+template <int V, int MC, int MP, class Out>
+MH_HD void write_obs(const EnvConst &c, EnvR<MC, MP> &e, bool at_reset, Out &out) {
+    typedef VT<V> T;
+    const Geo g = make_geo(e.cross, c.L);
+    int o = 0;
+#pragma unroll
+    for (int i = 0; i < MC; ++i) {
+        if (i >= c.nC) continue;
+        const CarR &k = e.car[i];
+        if (T::scal && !k.exist) {
+            out(o + 0, 0.f); out(o + 1, 0.f); out(o + 2, 10.f); out(o + 3, -1000.f); out(o + 4, 0.f);
+            out(o + 5, (float)k.line); out(o + 6, 0.f);
+        } else {
+            out(o + 0, (float)k.Ac); out(o + 1, (float)k.Vc); out(o + 2, (float)(10.0 - k.Vc)); out(o + 3, (float)k.Sc);
+            out(o + 4, (float)k.light); out(o + 5, (float)k.line);
+            if (T::scal) out(o + 6, 1.f);
+        }
+        o += T::car_w;
+    }
+    out(o++, (float)(e.cross * (double)c.L / 2.0));
+    out(o++, (float)e.ped_traffic);
+    if (T::scal) out(o++, (float)e.car_traffic);
+    out(o++, (float)c.L);
+    // cars handed to get_data: every slot of self.cars at reset (SC:922-929; leaders only C4:886-893);
+    // existing cars in step (SC:803-806), leaders + followers in 4cars (C4:796-799)
+    const int upto = at_reset ? c.nlead : c.nC;
+#pragma unroll
+    for (int j = 0; j < MP; ++j) {
+        if (j >= c.nP) continue;
+        PedR &p = e.ped[j];
+        if (!(p.fl & PF_EXIST)) {
+#pragma unroll
+            for (int q = 0; q < 9; ++q) out(o + q, 0.f);
+        } else {
+            double dl = T::far;
+            const bool left = (p.fl & PF_LEFT) != 0;
+#pragma unroll
+            for (int i = 0; i < MC; ++i) {
+                if (i >= upto) continue;
+                const CarR &k = e.car[i];
+                if (T::scal && !at_reset && !k.exist) continue;
+                if ((k.Sc <= p.Spx) && in_front(g, p, k.line, 0.0) && !left && (k.light >= 0.0)) {
+                    const double nd = (fabs(k.Sc - p.Spx) - (k.Vc * k.Vc / (-2.0 * c.acc_lo))) - 1.0 * k.Vc;
+                    dl = dmin(dl, nd);
+                }
+            }
+            const double gate = ((p.fl & PF_CROSSING) && !left) ? 1.0 : 0.0;
+            p.delta = dmin(dl * gate, p.delta);
+            out(o + 0, (float)p.Vpx); out(o + 1, (float)p.Vpy); out(o + 2, (float)p.Spx); out(o + 3, (float)p.Spy);
+            out(o + 4, (float)p.delta); out(o + 5, left ? 1.f : 0.f); out(o + 6, (p.fl & PF_IN_CROSS) ? 1.f : 0.f);
+            out(o + 7, 1.f); out(o + 8, (float)p.dir);
+        }
+        o += 9;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// reset: SC:884-946 (CO:838-892, C4:850-911, C42:866-927); pedestrian.__init__ SC:15-104 and
+// car.__init__ SC:531-581 consume the stream in the reference's order.
+template <int V>
+MH_HD void ped_init(const EnvConst &c, double W, double cross, PedR &p, bool real, Rng &rng) {
+    typedef VT<V> T;
+    p.fl = real ? (PF_EXIST | PF_CROSSING) : 0u;
+    (void)rng.randint(0, 20);                                                        // time_to_remove SC:43 (dead)
+    const int fr = rng.randint(0, 9);
+    if (T::naif ? (fr < 10) : (fr < 3)) p.fl |= PF_FOLLOW;                           // SC:48 / NA:46
+    p.dir = 2 * rng.randint(0, 1) - 1;                                               // SC:54
+    p.lpos = (p.dir < 0) ? c.L : -1;                                                 // SC:55
+    p.v0x = rng.uniform(c.pb[0], c.pb[4]);                                           // SC:56
+    p.v0y = rng.uniform(c.pb[1], c.pb[5]) * (double)p.dir;                           // SC:57
+    p.Spx = rng.uniform(c.pb[2], c.pb[6]);                                           // SC:61
+    p.Spy = (rng.uniform(c.pb[3], c.pb[7]) - W / 2.0) * (double)p.dir;               // SC:62
+    if (!real) {                                                                     // SC:66-68
+        p.v0x = 0.0; p.v0y = 0.0;
+        p.Spy = c.pb[3] * (double)p.dir;
+        if (!T::placeholder_keeps_x) p.Spx = c.pb[2];
+    }
+    p.Vpx = p.v0x; p.Vpy = p.v0y;
+    p.gender = rng.randint(0, 1);                                                    // SC:84
+    p.age = rng.randint(0, 2);                                                       // SC:85
+    if (real) rng.skip(1);                                                           // SC:86: CG normal draw, value dead
+    p.delta = 0.0; p.wdl = 0.0; p.cstop = 0.0;
+    p.t0c = 0; p.waitc = 0; p.crossc = 0; p.tstop = 0;
+    if (T::draws_need_to_stop) { if (rng.uniform(0.0, 1.0) < 0.5) p.fl |= PF_NEED_STOP; }   // SC:91
+    else if (V == V_COOP) p.fl |= PF_NEED_STOP;                                      // CO:90
+    if (T::draws_cross_stop) p.cstop = rng.uniform(-W / 2.0 + 0.2, W / 2.0 - 0.2);   // SC:92
+    (void)cross;
+}
+
+template <int V>
+MH_HD void car_init(const EnvConst &c, double W, CarR &k, int arg, int exist, Rng &rng) {
+    typedef VT<V> T;
+    const double v0 = 10.0;
+    const double mean_speed_ped = c.pb[1] + c.pb[5] / 2.0;                           // SC:565
+    const double fct = (W * v0) / mean_speed_ped;                                    // SC:570
+    const double lo = (c.pb[3] * v0) / c.pb[1], hi = (c.pb[7] * v0) / c.pb[5];       // SC:573-574
+    const double u = rng.uniform(lo - fct, hi);                                      // SC:576
+    k.line = T::scal ? arg / 2 : arg;                                                // SC:537
+    k.Sc = T::scal ? (u - 20.0 * (double)(arg % 2)) : u;
+    k.Vc = v0; k.Ac = 0.0; k.light = 0.0; k.pa = 0.0; k.es = 0.0; k.Ts = T::Ts0; k.exist = exist;
+}
+
+template <int V, int MC, int MP>
+MH_NOINLINE void reset_env(const EnvConst &c, EnvR<MC, MP> &e) {
+    typedef VT<V> T;
+    Rng &rng = e.rng;
+    e.cross = rng.uniform(c.cross_lo, c.cross_hi);                                   // SC:890 (kept fp64 in HBM)
+    const double W = (double)c.L * e.cross;
+    for (int j = 0; j < c.nP; ++j) ped_init<V>(c, W, e.cross, e.ped[j], false, rng); // SC:897-899
+    if (T::scal) {
+        for (int i = 0; i < c.nC; ++i) car_init<V>(c, W, e.car[i], i / 2, 0, rng);   // SC:900-901
+        e.car_traffic = rng.randint(1, c.nb_car);                                    // SC:902
+        uint64_t pool = 0xFEDCBA9876543210ull;                                       // random.sample SC:903
+        const int n = c.nC;
+        for (int i = 0; i < e.car_traffic; ++i) {
+            int j = i + (int)floor(rng.random() * (double)(n - i));
+            if (j > n - 1) j = n - 1;
+            const uint64_t a = (pool >> (4 * i)) & 15u, b = (pool >> (4 * j)) & 15u;
+            pool &= ~((15ull << (4 * i)) | (15ull << (4 * j)));
+            pool |= (b << (4 * i)) | (a << (4 * j));
+        }
+        for (int q = 0; q < e.car_traffic; ++q) {                                    // SC:904-906
+            const int s = (int)((pool >> (4 * q)) & 15u);
+            car_init<V>(c, W, e.car[s], s / 2, 1, rng);
+        }
+    } else {
+        for (int i = 0; i < c.nb_car; ++i) car_init<V>(c, W, e.car[i], i % c.L, 1, rng);   // CO:852-853
+        e.car_traffic = c.nb_car;
+        if (T::four)
+            for (int i = 0; i < c.nb_car; ++i) car_init<V>(c, W, e.car[c.nb_car + i], e.car[i].line, 1, rng);  // C4:868
+    }
+    e.ped_traffic = rng.randint(1, c.nP);                                            // SC:912
+    for (int j = 0; j < e.ped_traffic; ++j) ped_init<V>(c, W, e.cross, e.ped[j], true, rng);   // SC:913-915
+    if (T::four)
+        for (int i = 0; i < c.nb_car; ++i) {                                         // C4:878-879 / C42:894-895
+            CarR &f = e.car[c.nb_car + i];
+            const double gap = (V == V_4CARS2) ? rng.uniform(10.0, 30.0) : 15.0;
+            f.Vc = 10.0; f.Sc = e.car[i].Sc - gap; f.light = 0.0; f.line = e.car[i].line;
+        }
+    e.step = 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Action vector of one env split per car slot: acc[s] = actions[s], light[s] = actions[nA/2 + s]
+// (SC:798-802 [acc x 2L, light x 2L]; CO:754-755; C42:809-811 [acc_l, acc_f, light_l, light_f] with
+// follower slot s = nb_car + i).
+template <int MC>
+struct ActR { float acc[MC], light[MC]; };
+
+// one env.step: SC:789-878.  Returns done.  rewards / reward_light are written through
+// RewOut(i, reward, reward_light).
+template <int V, int MC, int MP, class RewOut>
+MH_HD bool step_env(const EnvConst &c, EnvR<MC, MP> &e, const ActR<MC> &act, RewOut &rew_out) {
+    typedef VT<V> T;
+    const Geo g = make_geo(e.cross, c.L);
+    double prevSc[MC];
+#pragma unroll
+    for (int i = 0; i < MC; ++i) prevSc[i] = e.car[i].Sc;                            // SC:797
+    // ---- cars (SC:798-802 / C4:792-795 / C42:808-811 / CO:754-755)
+    if (T::scal) {
+#pragma unroll
+        for (int i = 0; i < MC; ++i) {
+            if (i >= c.nC) continue;
+            double a = (double)act.acc[i];
+            if ((i & 1) && e.car[i > 0 ? i - 1 : 0].exist && e.car[i].exist)
+                a = dmin(idm(c, e.car[i], e.car[i > 0 ? i - 1 : 0].Sc, e.car[i > 0 ? i - 1 : 0].Vc), a);
+            else a = dmin(2.0, a);
+            car_move<V>(c, e.car[i], a, (double)act.light[i]);
+        }
+    } else if (T::four) {
+        const int n = c.nb_car;
+#pragma unroll
+        for (int i = 0; i < MC / 2; ++i) {
+            if (i >= n) continue;
+            car_move<V>(c, e.car[i], (double)act.acc[i], (double)act.light[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < MC / 2; ++i) {
+            if (i >= n) continue;
+            // follower slot n+i; static register index needs the compile-time bound MC/2 == n
+            CarR &f = e.car[MC / 2 + i];
+            const double a_idm = idm(c, f, e.car[i].Sc, e.car[i].Vc);
+            if (V == V_4CARS2) car_move<V>(c, f, dmin(a_idm, (double)act.acc[MC / 2 + i]), (double)act.light[MC / 2 + i]);
+            else car_move<V>(c, f, a_idm, e.car[i].light);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < MC; ++i) {
+            if (i >= c.nC) continue;
+            car_move<V>(c, e.car[i], (double)act.acc[i], (double)act.light[i]);
+        }
+    }
+    // ---- pedestrians (SC:803-809)
+    uint32_t seen = 0; int nseen = 0;
+#pragma unroll
+    for (int i = 0; i < MC; ++i)
+        if (i < c.nC && (!T::scal || e.car[i].exist)) { seen |= 1u << i; ++nseen; }
+#pragma unroll
+    for (int j = 0; j < MP; ++j)
+        if (j < c.nP) ped_step<V, MC>(c, g, e.ped[j], e.car, seen, nseen, e.step, e.rng);
+    // ---- danger detection (SC:841-846)
+    double rl[MC];
+#pragma unroll
+    for (int i = 0; i < MC; ++i) rl[i] = 0.0;
+#pragma unroll
+    for (int j = 0; j < MP; ++j) {
+        if (j >= c.nP) continue;
+        double res[MC];
+        detection<V, MC>(c, g, e.ped[j], e.car, prevSc, res);
+        const bool add = (e.ped[j].fl & PF_CROSSING) && (!T::scal || (e.ped[j].fl & PF_EXIST));
+        if (add) {
+#pragma unroll
+            for (int i = 0; i < MC; ++i) rl[i] += res[i];
+        }
+    }
+    // ---- rewards (SC:849-858)
+#pragma unroll
+    for (int i = 0; i < MC; ++i) {
+        if (i >= c.nlead) continue;
+        const CarR &k = e.car[i];
+        const double d = k.Vc - 10.0;
+        double r = (-10.0 * (d * d)) / 100.0;                                        // SC:657-665
+        if (!(k.light <= 0.0)) {
+            bool any = false; double m = 0.0;
+#pragma unroll
+            for (int j = 0; j < MP; ++j) {
+                if (j >= c.nP || !(e.ped[j].fl & PF_EXIST)) continue;
+                const double w = wait_safety<V>(c, g, e.ped[j], k);
+                if (!any || w < m) { m = w; any = true; }
+            }
+            if (any) r += m;
+        }
+        rew_out(i, r, rl[i]);
+    }
+    const bool done = (e.step >= c.done_idx) || (e.ped_traffic <= 0);                // SC:874
+    e.step += 1;                                                                     // SC:875
+    return done;
+}
+
+}  // namespace mhppo

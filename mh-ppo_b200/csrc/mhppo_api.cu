@@ -1,0 +1,270 @@
+// mhppo_api.cu -- host side of the C ABI declared in include/mhppo.h (env part).
+//
+// Owns the HBM state arena of a vectorised env, picks the kernel instantiation for the requested
+// (variant, car slots, pedestrians) and enqueues the kernels on the caller's stream.  No torch
+// types, no allocation after create, no hidden synchronisation (except the *_host entry points).
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "env_kernels.cuh"
+
+namespace mhppo {
+
+static thread_local std::string g_err;
+static std::atomic<int64_t> g_launches{0};
+
+static int fail(int code, const std::string &msg) { g_err = msg; return code; }
+static int cuda_fail(cudaError_t e, const char *what) {
+    g_err = std::string(what) + ": " + cudaGetErrorString(e);
+    return MHPPO_ECUDA;
+}
+#define CK(call)                                                   \
+    do {                                                           \
+        cudaError_t e_ = (call);                                   \
+        if (e_ != cudaSuccess) return cuda_fail(e_, #call);        \
+    } while (0)
+
+struct EnvHandle {
+    mhppo_env_cfg cfg;
+    EnvConst c;
+    EnvArena a;
+    RngKey key;
+    const EnvKernelEntry *k;
+    void *arena_base;
+    size_t arena_bytes;
+    // staging for the *_host entry points (row-major, reference layout)
+    float *d_act, *d_obs, *d_rew, *d_rl; uint8_t *d_done;
+};
+
+__global__ void __launch_bounds__(kEnvBlock) k_env_export(EnvArena a, EnvConst c, DumpPtrs d) {
+    const int64_t n = (int64_t)blockIdx.x * kEnvBlock + threadIdx.x;
+    if (n < a.N) export_one(a, c, n, d);
+}
+__global__ void __launch_bounds__(kEnvBlock) k_env_import(EnvArena a, EnvConst c, DumpPtrs d) {
+    const int64_t n = (int64_t)blockIdx.x * kEnvBlock + threadIdx.x;
+    if (n < a.N) import_one(a, c, n, d);
+}
+
+static const EnvKernelEntry *find_kernel(int variant, int C, int P) {
+    int n = 0;
+    const EnvKernelEntry *t = nullptr;
+    switch (variant) {
+        case V_STOP: t = env_table_stop(&n); break;
+        case V_NAIF: t = env_table_naif(&n); break;
+        case V_COOP: t = env_table_coop(&n); break;
+        case V_4CARS: t = env_table_4cars(&n); break;
+        case V_4CARS2: t = env_table_4cars2(&n); break;
+        case V_SCAL: t = env_table_scalable(&n); break;
+        default: return nullptr;
+    }
+    const bool exact_c = (variant == V_4CARS || variant == V_4CARS2);  // follower registers sit at MC/2
+    const EnvKernelEntry *best = nullptr;
+    for (int i = 0; i < n; ++i) {
+        const EnvKernelEntry &e = t[i];
+        if (e.mp < P) continue;
+        if (exact_c ? (e.mc != C) : (e.mc < C)) continue;
+        if (!best || e.mc * 16 + e.mp < best->mc * 16 + best->mp) best = &e;
+    }
+    return best;
+}
+
+static unsigned grid_for(int64_t n) { return (unsigned)((n + kEnvBlock - 1) / kEnvBlock); }
+
+}  // namespace mhppo
+
+using namespace mhppo;
+
+extern "C" {
+
+int mhppo_abi_version(void) { return MHPPO_ABI_VERSION; }
+const char *mhppo_last_error(void) { return g_err.c_str(); }
+int64_t mhppo_launch_count(void) { return g_launches.load(); }
+
+int mhppo_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int mhppo_env_create(const mhppo_env_cfg *cfg, void **handle) {
+    if (!cfg || !handle) return fail(MHPPO_EINVAL, "null argument");
+    *handle = nullptr;
+    if (cfg->variant < 0 || cfg->variant > 5) return fail(MHPPO_EINVAL, "unknown env variant");
+    if (cfg->nb_car < 1 || cfg->nb_ped < 1 || cfg->nb_lines < 1 || cfg->n_envs < 1)
+        return fail(MHPPO_EINVAL, "nb_car, nb_ped, nb_lines and n_envs must be >= 1");
+    if (cfg->nb_lines > 29) return fail(MHPPO_EINVAL, "nb_lines > 29 does not fit the packed line_pos field");
+    if (cfg->max_episode < 1 || cfg->max_episode > 250)
+        return fail(MHPPO_EINVAL, "max_episode must be in [1, 250] (8-bit dt counters)");
+    if (!(cfg->dt > 0.0)) return fail(MHPPO_EINVAL, "dt must be > 0");
+    const int v = cfg->variant;
+    const bool four = (v == V_4CARS || v == V_4CARS2);
+    const int C = (v == V_SCAL) ? 2 * cfg->nb_lines : (four ? 2 * cfg->nb_car : cfg->nb_car);
+    if (v == V_SCAL && cfg->nb_car > C) return fail(MHPPO_EINVAL, "scalable env needs nb_car <= 2*nb_lines (random.sample, SC:903)");
+    const EnvKernelEntry *k = find_kernel(v, C, cfg->nb_ped);
+    if (!k) {
+        char b[160];
+        snprintf(b, sizeof b, "no sm_100a kernel instantiation for variant %d with %d car slots and %d pedestrians", v, C, cfg->nb_ped);
+        return fail(MHPPO_EUNSUPPORTED, b);
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(MHPPO_ENODEV, "no CUDA device: mhppo_b200 has no CPU fallback");
+    }
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(MHPPO_EINVAL, "device ordinal out of range");
+    CK(cudaSetDevice(cfg->device));
+
+    EnvHandle *h = new (std::nothrow) EnvHandle();
+    if (!h) return fail(MHPPO_ENOMEM, "host allocation failed");
+    memset(h, 0, sizeof(*h));
+    h->cfg = *cfg; h->k = k;
+    EnvConst &c = h->c;
+    c.nC = C; c.nP = cfg->nb_ped; c.L = cfg->nb_lines; c.nb_car = cfg->nb_car;
+    c.nlead = four ? cfg->nb_car : C;
+    c.nA = (v == V_SCAL) ? 4 * cfg->nb_lines : ((v == V_4CARS2) ? 4 * cfg->nb_car : 2 * cfg->nb_car);
+    c.nobs = ((v == V_SCAL) ? 7 : 6) * C + ((v == V_SCAL) ? 4 : 3) + 9 * cfg->nb_ped;
+    {   // done = time >= (max_episode-1)*dt with time the fp64 running sum of dt (SC:874-875, 945)
+        double t = 0.0; const double lim = (cfg->max_episode - 1) * cfg->dt; int kk = 0;
+        while (!(t >= lim) && kk < 100000) { t = t + cfg->dt; ++kk; }
+        c.done_idx = kk;
+    }
+    c.sin_model = cfg->sin_model; c.dt = cfg->dt; c.acc_lo = cfg->car_b[0]; c.acc_hi = cfg->car_b[2];
+    for (int i = 0; i < 8; ++i) c.pb[i] = cfg->ped_b[i];
+    c.cross_lo = cfg->cross_b[0]; c.cross_hi = cfg->cross_b[1];
+    h->key.k0 = (uint32_t)cfg->seed; h->key.k1 = (uint32_t)(cfg->seed >> 32); h->key.env_id0 = cfg->env_id0;
+
+    const int64_t N = cfg->n_envs;
+    const size_t per_env = (size_t)(2 * C + 3 * cfg->nb_ped + 1) * sizeof(float4);
+    h->arena_bytes = per_env * (size_t)N;
+    cudaError_t e = cudaMalloc(&h->arena_base, h->arena_bytes);
+    if (e != cudaSuccess) { delete h; return cuda_fail(e, "cudaMalloc(state arena)"); }
+    e = cudaMemset(h->arena_base, 0, h->arena_bytes);
+    if (e != cudaSuccess) { cudaFree(h->arena_base); delete h; return cuda_fail(e, "cudaMemset(state arena)"); }
+    float4 *p = (float4 *)h->arena_base;
+    h->a.N = N;
+    h->a.car_a = p; p += (size_t)C * N;
+    h->a.car_b = p; p += (size_t)C * N;
+    h->a.ped_a = p; p += (size_t)cfg->nb_ped * N;
+    h->a.ped_b = p; p += (size_t)cfg->nb_ped * N;
+    h->a.ped_c = p; p += (size_t)cfg->nb_ped * N;
+    h->a.env_e = p;
+    // device staging for the host-buffer entry points
+    const size_t nb = (size_t)N * sizeof(float);
+    e = cudaMalloc(&h->d_act, nb * c.nA);
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_obs, nb * c.nobs);
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_rew, nb * c.nlead);
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_rl, nb * c.nlead);
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_done, (size_t)N);
+    if (e != cudaSuccess) { mhppo_env_destroy(h); return cuda_fail(e, "cudaMalloc(host-API staging)"); }
+    *handle = h;
+    return MHPPO_OK;
+}
+
+int mhppo_env_destroy(void *handle) {
+    EnvHandle *h = (EnvHandle *)handle;
+    if (!h) return MHPPO_OK;
+    cudaFree(h->arena_base); cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_rew); cudaFree(h->d_rl);
+    cudaFree(h->d_done);
+    delete h;
+    return MHPPO_OK;
+}
+
+int mhppo_env_get_dims(void *handle, mhppo_env_dims *d) {
+    EnvHandle *h = (EnvHandle *)handle;
+    if (!h || !d) return fail(MHPPO_EINVAL, "null argument");
+    memset(d, 0, sizeof(*d));
+    d->n_slots = h->c.nC; d->n_lead = h->c.nlead; d->n_action = h->c.nA; d->n_obs = h->c.nobs;
+    d->n_ped = h->c.nP; d->done_step = h->c.done_idx;
+    return MHPPO_OK;
+}
+
+int64_t mhppo_env_state_bytes_per_env(void *handle) {
+    EnvHandle *h = (EnvHandle *)handle;
+    return h ? (int64_t)(h->arena_bytes / (size_t)h->a.N) : 0;
+}
+
+int mhppo_env_reset(void *handle, const uint8_t *mask_dev, mhppo_view obs_dev, void *stream) {
+    EnvHandle *h = (EnvHandle *)handle;
+    if (!h) return fail(MHPPO_EINVAL, "null handle");
+    auto fn = h->k->reset;
+    fn<<<grid_for(h->a.N), kEnvBlock, 0, (cudaStream_t)stream>>>(h->a, h->c, h->key, mask_dev, obs_dev);
+    g_launches.fetch_add(1);
+    CK(cudaGetLastError());
+    return MHPPO_OK;
+}
+
+int mhppo_env_step(void *handle, mhppo_view actions_dev, mhppo_view obs_dev, mhppo_view rewards_dev,
+                   mhppo_view reward_light_dev, uint8_t *done_dev, int autoreset, mhppo_view term_obs_dev,
+                   void *stream) {
+    EnvHandle *h = (EnvHandle *)handle;
+    if (!h) return fail(MHPPO_EINVAL, "null handle");
+    if (!actions_dev.ptr) return fail(MHPPO_EINVAL, "actions are required");
+    StepIO io;
+    io.actions = actions_dev; io.obs = obs_dev; io.rewards = rewards_dev; io.reward_light = reward_light_dev;
+    io.term_obs = term_obs_dev; io.done = done_dev; io.autoreset = autoreset;
+    auto fn = h->k->step;
+    fn<<<grid_for(h->a.N), kEnvBlock, 0, (cudaStream_t)stream>>>(h->a, h->c, h->key, io);
+    g_launches.fetch_add(1);
+    CK(cudaGetLastError());
+    return MHPPO_OK;
+}
+
+int mhppo_env_reset_host(void *handle, float *obs_host, void *stream) {
+    EnvHandle *h = (EnvHandle *)handle;
+    if (!h) return fail(MHPPO_EINVAL, "null handle");
+    cudaStream_t s = (cudaStream_t)stream;
+    mhppo_view obs = { h->d_obs, h->c.nobs, 1 };
+    int rc = mhppo_env_reset(handle, nullptr, obs, stream);
+    if (rc) return rc;
+    if (obs_host) CK(cudaMemcpyAsync(obs_host, h->d_obs, sizeof(float) * h->c.nobs * h->a.N, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return MHPPO_OK;
+}
+
+int mhppo_env_step_host(void *handle, const float *actions_host, float *obs_host, float *rewards_host,
+                        float *reward_light_host, uint8_t *done_host, int autoreset, void *stream) {
+    EnvHandle *h = (EnvHandle *)handle;
+    if (!h || !actions_host) return fail(MHPPO_EINVAL, "null argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t N = h->a.N; const EnvConst &c = h->c;
+    CK(cudaMemcpyAsync(h->d_act, actions_host, sizeof(float) * c.nA * N, cudaMemcpyHostToDevice, s));
+    mhppo_view act = { h->d_act, c.nA, 1 }, none = { nullptr, 0, 0 };
+    mhppo_view obs = obs_host ? mhppo_view{ h->d_obs, c.nobs, 1 } : none;
+    mhppo_view rew = rewards_host ? mhppo_view{ h->d_rew, c.nlead, 1 } : none;
+    mhppo_view rl = reward_light_host ? mhppo_view{ h->d_rl, c.nlead, 1 } : none;
+    int rc = mhppo_env_step(handle, act, obs, rew, rl, done_host ? h->d_done : nullptr, autoreset, none, stream);
+    if (rc) return rc;
+    if (obs_host) CK(cudaMemcpyAsync(obs_host, h->d_obs, sizeof(float) * c.nobs * N, cudaMemcpyDeviceToHost, s));
+    if (rewards_host) CK(cudaMemcpyAsync(rewards_host, h->d_rew, sizeof(float) * c.nlead * N, cudaMemcpyDeviceToHost, s));
+    if (reward_light_host) CK(cudaMemcpyAsync(reward_light_host, h->d_rl, sizeof(float) * c.nlead * N, cudaMemcpyDeviceToHost, s));
+    if (done_host) CK(cudaMemcpyAsync(done_host, h->d_done, (size_t)N, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return MHPPO_OK;
+}
+
+int mhppo_env_export_state(void *handle, float *car_f, int32_t *car_i, float *ped_f, int32_t *ped_i, double *env_f,
+                           int64_t *env_i, void *stream) {
+    EnvHandle *h = (EnvHandle *)handle;
+    if (!h || !car_f || !car_i || !ped_f || !ped_i || !env_f || !env_i) return fail(MHPPO_EINVAL, "null argument");
+    DumpPtrs d{car_f, car_i, ped_f, ped_i, env_f, env_i};
+    k_env_export<<<grid_for(h->a.N), kEnvBlock, 0, (cudaStream_t)stream>>>(h->a, h->c, d);
+    g_launches.fetch_add(1);
+    CK(cudaGetLastError());
+    return MHPPO_OK;
+}
+
+int mhppo_env_import_state(void *handle, const float *car_f, const int32_t *car_i, const float *ped_f,
+                           const int32_t *ped_i, const double *env_f, const int64_t *env_i, void *stream) {
+    EnvHandle *h = (EnvHandle *)handle;
+    if (!h || !car_f || !car_i || !ped_f || !ped_i || !env_f || !env_i) return fail(MHPPO_EINVAL, "null argument");
+    DumpPtrs d{(float *)car_f, (int32_t *)car_i, (float *)ped_f, (int32_t *)ped_i, (double *)env_f, (int64_t *)env_i};
+    k_env_import<<<grid_for(h->a.N), kEnvBlock, 0, (cudaStream_t)stream>>>(h->a, h->c, d);
+    g_launches.fetch_add(1);
+    CK(cudaGetLastError());
+    return MHPPO_OK;
+}
+
+}  // extern "C"

@@ -583,8 +583,7 @@ static void car_init(Ctx *x, OCar *c, int arg, int exist) {
 }
 
 static void store_round(const OHandle *h, OEnv *e) {
-    if (!h->c.store_f32) return;
-    e->cross = f32r(e->cross);
+    if (!h->c.store_f32) return;   /* cross stays fp64 in HBM (env_state.cuh) */
     for (int i = 0; i < h->C; ++i) {
         OCar *c = &e->car[i];
         c->Ac = f32r(c->Ac); c->Vc = f32r(c->Vc); c->Sc = f32r(c->Sc); c->light = f32r(c->light);
@@ -592,7 +591,18 @@ static void store_round(const OHandle *h, OEnv *e) {
     }
     for (int j = 0; j < h->c.nb_ped; ++j) {
         OPed *p = &e->ped[j];
-        p->Vpx = f32r(p->Vpx); p->Vpy = f32r(p->Vpy); p->Spx = f32r(p->Spx); p->Spy = f32r(p->Spy);
+        /* HBM format rule "symbolic positions" (mh-ppo_b200/csrc/env_state.cuh): an Sp_y whose fp32
+         * rounding equals that of the kerb snap (SC:326) or of the lane-edge snap (SC:392-397, dtc
+         * SC:350-351) is kept as that exact fp64 value; anything else is rounded to fp32. */
+        const double L = h->c.nb_lines, W = L * e->cross;
+        const double kerb = -p->dir * W / 2.;
+        double dtc = (L - p->line_pos - 1) * e->cross * (p->dir > 0);
+        dtc += (p->line_pos) * e->cross * (p->dir < 0);
+        const double lane = p->dir * ((W - dtc) - W / 2.);
+        if ((float)p->Spy == (float)kerb) p->Spy = kerb;
+        else if ((float)p->Spy == (float)lane) p->Spy = lane;
+        else p->Spy = f32r(p->Spy);
+        p->Vpx = f32r(p->Vpx); p->Vpy = f32r(p->Vpy); p->Spx = f32r(p->Spx);
         p->v0x = f32r(p->v0x); p->v0y = f32r(p->v0y); p->cross_stop = f32r(p->cross_stop);
         p->delta = f32r(p->delta); p->worst_dl = f32r(p->worst_dl);
     }
@@ -603,7 +613,6 @@ static void env_reset(const OHandle *h, OEnv *e, float *obs) {
     Ctx x = { h, e };
     const mho_cfg *c = &h->c; const int v = c->variant, P = c->nb_ped, L = c->nb_lines;
     e->cross = rng_uniform(&x, c->cross_b[0], c->cross_b[1]);              /* SC:890 */
-    if (c->store_f32) e->cross = f32r(e->cross);  /* HBM semantics: everything derives from the stored cross */
     for (int j = 0; j < P; ++j) ped_init(&x, &e->ped[j], 0, 0);            /* SC:897-899 */
     if (v == MHO_SCALABLE) {
         for (int i = 0; i < 2 * L; ++i) car_init(&x, &e->car[i], i / 2, 0); /* SC:900-901 */

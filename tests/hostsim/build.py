@@ -1,0 +1,20 @@
+"""Build the TEST-ONLY host compilation of the kernel logic (see hostsim.cpp)."""
+import os
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(HERE, "libhostsim.so")
+CSRC = os.path.join(HERE, "..", "..", "mh-ppo_b200", "csrc")
+
+
+def build(force=False):
+    srcs = [os.path.join(HERE, "hostsim.cpp")] + [os.path.join(CSRC, f) for f in ("env_core.cuh", "env_state.cuh", "philox.cuh")]
+    if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= max(os.path.getmtime(s) for s in srcs):
+        return LIB
+    subprocess.run(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-D_GNU_SOURCE",
+                    "-o", LIB, srcs[0], "-lm"], check=True, capture_output=True)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force=True))

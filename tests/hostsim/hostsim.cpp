@@ -1,0 +1,127 @@
+// hostsim.cpp -- TEST-ONLY host build of the kernel's per-env logic (mh-ppo_b200/csrc/env_core.cuh,
+// env_state.cuh) so the CUDA code path can be unit-tested against the golden fixtures and the oracle on a
+// machine without a GPU.  It is built by tests/hostsim/build.py into tests/hostsim/, is never
+// loaded by the product package, and is NOT a CPU fallback: mh-ppo_b200 fails loudly without CUDA.
+#include <stdint.h>
+#include <string.h>
+#include <stdlib.h>
+#include <math.h>
+#define _GNU_SOURCE 1
+#include "../../mh-ppo_b200/csrc/env_state.cuh"
+
+using namespace mhppo;
+
+struct View { float *ptr; int64_t env_stride, comp_stride; };
+struct HostOut { float *p; int64_t cs; void operator()(int k, float v) const { p[(int64_t)k * cs] = v; } };
+struct NullOutH { void operator()(int, float) const {} };
+
+struct Sim {
+    int variant, mc, mp;
+    EnvConst c; EnvArena a; uint32_t k0, k1; int64_t env_id0;
+};
+
+template <int V, int MC, int MP>
+static void sim_reset(Sim *s, const uint8_t *mask, View obs) {
+    for (int64_t n = 0; n < s->a.N; ++n) {
+        if (mask && !mask[n]) continue;
+        EnvR<MC, MP> e; memset(&e, 0, sizeof(e));
+        const uint64_t gid = (uint64_t)(s->env_id0 + n);
+        e.rng.env_lo = (uint32_t)gid; e.rng.env_hi = (uint32_t)(gid >> 32); e.rng.k0 = s->k0; e.rng.k1 = s->k1;
+        e.rng.ctr = f2u(s->a.env_e[n].w);
+        reset_env<V, MC, MP>(s->c, e);
+        if (obs.ptr) { HostOut out{obs.ptr + n * obs.env_stride, obs.comp_stride}; write_obs<V, MC, MP>(s->c, e, true, out); }
+        else { NullOutH nul; write_obs<V, MC, MP>(s->c, e, true, nul); }
+        store_env<MC, MP>(s->a, s->c, n, e);
+    }
+}
+
+template <int V, int MC, int MP>
+static void sim_step(Sim *s, View actions, View obs, View rewards, View reward_light, uint8_t *done, int autoreset,
+                     View term_obs) {
+    const EnvConst &c = s->c;
+    for (int64_t n = 0; n < s->a.N; ++n) {
+        EnvR<MC, MP> e; memset(&e, 0, sizeof(e));
+        const uint64_t gid = (uint64_t)(s->env_id0 + n);
+        e.rng.env_lo = (uint32_t)gid; e.rng.env_hi = (uint32_t)(gid >> 32); e.rng.k0 = s->k0; e.rng.k1 = s->k1;
+        load_env<MC, MP>(s->a, c, n, e);
+        ActR<MC> act;
+        const float *ap = actions.ptr + n * actions.env_stride;
+        const int half = c.nA / 2;
+        for (int q = 0; q < MC; ++q) {
+            act.acc[q] = (q < half) ? ap[(int64_t)q * actions.comp_stride] : 0.f;
+            act.light[q] = (q < half) ? ap[(int64_t)(half + q) * actions.comp_stride] : 0.f;
+        }
+        float *rp = rewards.ptr ? rewards.ptr + n * rewards.env_stride : nullptr;
+        float *lp = reward_light.ptr ? reward_light.ptr + n * reward_light.env_stride : nullptr;
+        auto rew_out = [&](int i, double r, double rl) {
+            if (rp) rp[(int64_t)i * rewards.comp_stride] = (float)r;
+            if (lp) lp[(int64_t)i * reward_light.comp_stride] = (float)rl;
+        };
+        const bool d = step_env<V, MC, MP>(c, e, act, rew_out);
+        if (done) done[n] = d ? 1 : 0;
+        const bool do_reset = d && autoreset;
+        for (int pass = 0; pass < 2; ++pass) {
+            const bool last = !do_reset || pass == 1;
+            const View &v = last ? obs : term_obs;
+            if (v.ptr) { HostOut out{v.ptr + n * v.env_stride, v.comp_stride}; write_obs<V, MC, MP>(c, e, pass == 1, out); }
+            if (last) break;
+            EnvR<MC, MP> fresh; memset(&fresh, 0, sizeof(fresh));
+            fresh.rng = e.rng;
+            reset_env<V, MC, MP>(c, fresh);
+            e = fresh;
+        }
+        store_env<MC, MP>(s->a, c, n, e);
+    }
+}
+
+#define DISPATCH(FN, ...)                                                                          \
+    do {                                                                                           \
+        const int key = s->variant * 10000 + s->mc * 100 + s->mp;                                  \
+        switch (key) {                                                                             \
+            case 50403: FN<V_SCAL, 4, 3>(__VA_ARGS__); break;                                      \
+            case 50201: FN<V_SCAL, 2, 1>(__VA_ARGS__); break;                                      \
+            case 50804: FN<V_SCAL, 8, 4>(__VA_ARGS__); break;                                      \
+            case 20804: FN<V_COOP, 8, 4>(__VA_ARGS__); break;                                      \
+            case 20201: FN<V_COOP, 2, 1>(__VA_ARGS__); break;                                      \
+            case 804: FN<V_STOP, 8, 4>(__VA_ARGS__); break;                                        \
+            case 10804: FN<V_NAIF, 8, 4>(__VA_ARGS__); break;                                      \
+            case 30202: FN<V_4CARS, 2, 2>(__VA_ARGS__); break;                                     \
+            case 30402: FN<V_4CARS, 4, 2>(__VA_ARGS__); break;                                     \
+            case 30604: FN<V_4CARS, 6, 4>(__VA_ARGS__); break;                                     \
+            case 40202: FN<V_4CARS2, 2, 2>(__VA_ARGS__); break;                                    \
+            case 40402: FN<V_4CARS2, 4, 2>(__VA_ARGS__); break;                                    \
+            case 40604: FN<V_4CARS2, 6, 4>(__VA_ARGS__); break;                                    \
+            default: return -5;                                                                    \
+        }                                                                                          \
+    } while (0)
+
+extern "C" {
+
+int hs_create(int variant, int mc, int mp, const EnvConst *c, int64_t N, uint64_t seed, int64_t env_id0, void **out) {
+    Sim *s = (Sim *)calloc(1, sizeof(Sim));
+    s->variant = variant; s->mc = mc; s->mp = mp; s->c = *c; s->k0 = (uint32_t)seed; s->k1 = (uint32_t)(seed >> 32);
+    s->env_id0 = env_id0; s->a.N = N;
+    s->a.car_a = (float4 *)calloc((size_t)N * mc, 16); s->a.car_b = (float4 *)calloc((size_t)N * mc, 16);
+    s->a.ped_a = (float4 *)calloc((size_t)N * mp, 16); s->a.ped_b = (float4 *)calloc((size_t)N * mp, 16);
+    s->a.ped_c = (float4 *)calloc((size_t)N * mp, 16); s->a.env_e = (float4 *)calloc((size_t)N, 16);
+    *out = s;
+    return 0;
+}
+void hs_destroy(void *h) {
+    Sim *s = (Sim *)h;
+    free(s->a.car_a); free(s->a.car_b); free(s->a.ped_a); free(s->a.ped_b); free(s->a.ped_c); free(s->a.env_e); free(s);
+}
+int hs_reset(void *h, const uint8_t *mask, View obs) { Sim *s = (Sim *)h; DISPATCH(sim_reset, s, mask, obs); return 0; }
+int hs_step(void *h, View actions, View obs, View rewards, View reward_light, uint8_t *done, int autoreset, View term_obs) {
+    Sim *s = (Sim *)h; DISPATCH(sim_step, s, actions, obs, rewards, reward_light, done, autoreset, term_obs); return 0;
+}
+void hs_export(void *h, float *car_f, int32_t *car_i, float *ped_f, int32_t *ped_i, double *env_f, int64_t *env_i) {
+    Sim *s = (Sim *)h; DumpPtrs d{car_f, car_i, ped_f, ped_i, env_f, env_i};
+    for (int64_t n = 0; n < s->a.N; ++n) export_one(s->a, s->c, n, d);
+}
+void hs_import(void *h, float *car_f, int32_t *car_i, float *ped_f, int32_t *ped_i, double *env_f, int64_t *env_i) {
+    Sim *s = (Sim *)h; DumpPtrs d{car_f, car_i, ped_f, ped_i, env_f, env_i};
+    for (int64_t n = 0; n < s->a.N; ++n) import_one(s->a, s->c, n, d);
+}
+int hs_sizeof_envconst(void) { return (int)sizeof(EnvConst); }
+}
