@@ -6,8 +6,9 @@
 // classes; the behavioural deltas between the files are compile-time switches (`VT<V>`).
 //
 // Design (B200-first, not a translation of the Python object graph):
-//  * thread = env, lane = env inside a warp; car/ped slots are fully unrolled register arrays, so
-//    the reference's filtered Python lists become bit masks over slots (order preserved);
+//  * thread = env, lane = env inside a warp; car slots are unrolled register arrays, so the
+//    reference's filtered Python lists become bit masks over slots (order preserved); the step
+//    itself (env_step.cuh) streams the pedestrians through one rolled loop;
 //  * persisted state is fp32 / packed integers in HBM (env_state.cuh), arithmetic is fp64 in the
 //    reference's operation order (compile with -fmad=false) so threshold flags are bit-exact and
 //    values differ from the fp64 reference only by the final fp32 rounding;
@@ -15,6 +16,9 @@
 //  * the data-dependent RNG consumption of the reference is reproduced with a per-env Philox
 //    cursor (philox.cuh); throw-away draws (SC:153) just advance the counter;
 //  * auto-reset runs inside the step kernel through a non-inlined reset on a scratch copy.
+//
+// This header holds the shared pieces: behaviour table, register structs, geometry predicates,
+// car dynamics, the full observation writer and the episode reset.
 //
 // The file is also compilable as plain C++ (tests/hostsim) so the kernel logic can be unit-tested
 // against the golden fixtures on a machine without a GPU; the product never runs that build.
@@ -123,274 +127,6 @@ MH_HD double cg_score(const PedR &p, double size, Rng &rng) {
     lv = lv + -0.1810 * (double)(p.age == 2);
     lv = lv + rng.normal(0.0, 0.09);
     return pow(10.0, lv);
-}
-
-// pedestrian.choix_pedestrian, SC:139-174 / NA:138-177.  `seen` = slots handed to pedestrian.step
-// (existing cars in scalable SC:803-806, leaders+followers in 4cars C4:796-799, all otherwise).
-template <int V, int MC>
-MH_HD bool choix(const Geo &g, const PedR &p, const CarR (&car)[MC], uint32_t seen, int nseen, Rng &rng) {
-    typedef VT<V> T;
-    if (p.fl & PF_FOLLOW) {
-        if (T::naif) {
-            // NA:151 really permutes the visiting order (every naif car exists: slot == list index)
-            uint64_t ord = 0xFEDCBA9876543210ull;
-            if (nseen > 1)
-                for (int i = nseen - 1; i > 0; --i) {
-                    int j = (int)floor(rng.random() * (double)(i + 1));
-                    if (j > i) j = i;
-                    const uint64_t a = (ord >> (4 * i)) & 15u, b = (ord >> (4 * j)) & 15u;
-                    ord &= ~((15ull << (4 * i)) | (15ull << (4 * j)));
-                    ord |= (b << (4 * i)) | (a << (4 * j));
-                }
-            for (int k = 0; k < nseen; ++k) {                      // NA:153-155
-                const int i = (int)((ord >> (4 * k)) & 15u);
-                bool hit = false;
-#pragma unroll
-                for (int s = 0; s < MC; ++s)
-                    if (s == i)
-                        hit = crossing_in_front(g, p, car[s].line, 0.5) && in_front(g, p, car[s].line, 1.0) &&
-                              (car[s].Sc < 4.0 + p.Spx) && (car[s].Sc > p.Spx);
-                if (hit) return false;
-            }
-            for (int k = 0; k < nseen; ++k) {                      // NA:156-158
-                const int i = (int)((ord >> (4 * k)) & 15u);
-                bool hit = false;
-#pragma unroll
-                for (int s = 0; s < MC; ++s)
-                    if (s == i) hit = (car[s].Sc < p.Spx) && (car[s].light < 0.0);
-                if (hit) return false;
-            }
-        } else {
-            if (T::burn_shuffle && nseen > 1) rng.skip(nseen - 1);  // SC:152-153: shuffles a temporary
-#pragma unroll
-            for (int i = 0; i < MC; ++i)                            // SC:154-158
-                if ((seen >> i) & 1u)
-                    if (crossing_in_front(g, p, car[i].line, 0.5) && in_front(g, p, car[i].line, 1.0))
-                        if ((car[i].Sc < 4.0 + p.Spx) && (car[i].Sc > p.Spx)) return false;
-#pragma unroll
-            for (int i = 0; i < MC; ++i)                            // SC:159-161
-                if ((seen >> i) & 1u)
-                    if (car[i].Sc < p.Spx && car[i].light != 0.0) return car[i].light > 0.0;
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < MC; ++i) {                                  // SC:162-173
-        if (!((seen >> i) & 1u)) continue;
-        if (in_front(g, p, car[i].line, 1.0)) {
-            if ((car[i].Sc < 4.0 + p.Spx) && (car[i].Sc > p.Spx)) return false;
-            if (car[i].Sc < p.Spx) {
-                const double car_time = fabs((car[i].Sc - p.Spx) / (car[i].Vc + 10e-3));
-                const double CG = cg_score(p, fabs((double)(p.lpos - car[i].line)) * g.cross, rng);
-                if (car_time + car[i].light < CG) return false;
-            }
-        }
-    }
-    return true;
-}
-
-// pedestrian.function_step: sin profile SC:436-443 (parameters SC:94-102) or uniform SC:433-434
-MH_HD void walk_model(const EnvConst &c, const Geo &g, const PedR &p, int step, double &pos, double &spd) {
-    if (c.sin_model && (p.fl & PF_CROSSING)) {
-        const double PI_ = 3.141592653589793, Vm = 2.5;
-        const double av = fabs(p.v0y);
-        const double T = g.W / (av + 10e-3);
-        const bool check = ((av * PI_) / 2.0 <= Vm);
-        const double A = check ? (PI_ * av / 2.0 + 0.0) : (0.0 + (Vm - av) / (1.0 - (2.0 / PI_)));
-        const double B = check ? 0.0 : (Vm - A);
-        const double w = PI_ / T;
-        const double t = (double)step * c.dt + c.dt, t0 = (double)p.t0c * c.dt;
-        const double ph = w * (t - t0);
-        double sn, cs;
-        sincos(ph, &sn, &cs);
-        const double speed_p = A * sn + B;
-        const double pos_p = g.Hn + (A * (-cs + 1.0) / w);
-        if (!(pos_p >= 0.0 && speed_p < av)) {
-            pos = (double)p.dir * pos_p; spd = (double)p.dir * speed_p;
-            return;
-        }
-    }
-    pos = p.Spy + p.v0y * c.dt; spd = p.v0y;
-}
-
-// pedestrian.step, SC:297-417
-template <int V, int MC>
-MH_HD void ped_step(const EnvConst &c, const Geo &g, PedR &p, const CarR (&car)[MC], uint32_t seen, int nseen,
-                    int step, Rng &rng) {
-    typedef VT<V> T;
-    const double dt = c.dt;
-    const double pp_y = p.Spy + p.v0y * dt;                                          // SC:298
-    const double dy = (double)p.dir * p.Spy;                                         // boolean_ped_position SC:266-275
-    p.fl &= ~(PF_LEFT | PF_IN_CROSS);
-    if (dy >= g.Hp) p.fl |= PF_LEFT;
-    else if (dy > g.Hn) p.fl |= PF_IN_CROSS;
-    if (!(p.fl & PF_CROSSING)) return;                                               // SC:308
-    bool choose = true;
-    if (!(p.fl & PF_DECISION) && (p.fl & PF_AT_CROSSING)) {                          // SC:311-318
-        choose = choix<V, MC>(g, p, car, seen, nseen, rng);
-        if (choose) { p.lpos = (p.dir < 0) ? (c.L - 1) : 0; p.fl &= ~PF_AT_CROSSING; }
-        p.fl |= PF_DECISION;
-        p.t0c = step;
-    }
-    if ((dy < g.Hn) && (pp_y * (double)p.dir > g.Hn) && !(p.fl & PF_DECISION)) {     // SC:320-328
-        const double px = (p.Vpx * dt) * (fabs(g.Hn - dy) / fabs(p.Vpy * dt + 10e-3));
-        p.Vpx = px / dt;
-        p.Spx = p.Spx + px;
-        p.Vpy = (double)p.dir * fabs(-dy - g.Hp) / dt;
-        p.Spy = (double)(-p.dir) * g.W / 2.0;
-        p.tstop = 0;
-        p.fl |= PF_AT_CROSSING;
-    } else if ((fabs(p.Spy) <= g.Hp) || (p.fl & PF_DECISION)) {                      // SC:331
-        if (p.tstop != 0) {                                                          // SC:335-339
-            p.Vpx = 0.0; p.Vpy = 0.0; p.tstop -= 1; p.t0c += 1;
-        } else {
-            const double u = rng.random();                                           // SC:346: always drawn
-            if ((u < 0.98) && choose) {
-                p.fl &= ~PF_DECISION;
-                double ny, nv;
-                walk_model(c, g, p, step, ny, nv);                                   // SC:348
-                bool change_line = false;                                            // will_change_line SC:281-286
-                if (fabs(ny) < g.Hp) {
-                    const double nl = floor((ny + g.Hp) / g.cross);
-                    if (nl != (double)p.lpos && fabs(p.Spy) < g.Hp) change_line = true;
-                }
-                double dtc = ((double)(c.L - p.lpos - 1) * g.cross) * (double)(p.dir > 0);   // SC:350-351
-                dtc += ((double)p.lpos * g.cross) * (double)(p.dir < 0);
-                bool new_choice = false;
-                if (change_line && (dtc > 0.0 && dtc < g.W)) {                       // SC:353-357
-                    new_choice = choix<V, MC>(g, p, car, seen, nseen, rng);
-                    if (new_choice) p.fl &= ~PF_STOP;
-                }
-                if (p.fl & PF_STOP) {                                                // SC:363-369
-                    p.Vpx = 0.0; p.Vpy = 0.0; p.t0c += 1;
-                    if (change_line) p.waitc += 1;
-                } else if (T::has_need_to_stop && (p.fl & PF_NEED_STOP) && p.Spy < p.cstop && pp_y > p.cstop) {
-                    p.tstop = rng.randint(T::nts_lo, T::nts_hi);                     // SC:371-380
-                    p.fl &= ~PF_NEED_STOP;
-                    p.Vpx = 0.0; p.Vpy = 0.0; p.t0c += 1;
-                } else if (!change_line || new_choice) {                             // SC:382-387
-                    const double ratio = p.v0x / p.v0y;                              // SC:73
-                    p.Spy = ny; p.Vpy = nv;
-                    p.Spx = p.Spx + p.Vpy * ratio * dt;
-                    p.Vpx = p.Vpy * ratio;
-                    p.crossc += 1;
-                    if (change_line) {                                               // apply_change_line SC:288-294
-                        if (fabs(ny) >= g.Hp) p.lpos = (p.dir < 0) ? c.L : ((p.dir > 0) ? -1 : 0);
-                        else p.lpos = (int)floor((ny + g.Hp) / g.cross);
-                    }
-                } else {                                                             // SC:389-397
-                    p.fl |= PF_STOP;
-                    const double d = fabs(((double)p.dir * (g.W - dtc) - (double)p.dir * g.W / 2.0) - p.Spy);
-                    const double px = p.Vpx * d / fabs(p.Vpy + 10e-3);
-                    p.Vpx = px / dt;
-                    p.Spx = p.Spx + px;
-                    p.Vpy = (double)p.dir * d / dt;
-                    p.Spy = (double)p.dir * ((g.W - dtc) - g.W / 2.0);
-                }
-            } else {                                                                 // SC:405-413
-                p.tstop = rng.randint(T::rs_lo, T::rs_hi);
-                if (!choose) { p.fl &= ~PF_DECISION; p.tstop = 0; p.waitc += 1; }
-                p.Vpx = 0.0; p.Vpy = 0.0; p.t0c += 1;
-            }
-        }
-    } else {                                                                         // SC:415-417
-        p.Spx = p.Spx + p.v0x * dt; p.Vpx = p.v0x;
-        p.Spy = p.Spy + p.v0y * dt; p.Vpy = p.v0y;
-    }
-}
-
-// pedestrian.worst_delta_l, SC:522-527
-template <int V>
-MH_HD double worst_delta_l(const EnvConst &c, const Geo &g, const PedR &p, const CarR &k) {
-    if (k.Sc > p.Spx || (p.fl & PF_LEFT) || !in_front(g, p, k.line, 0.0)) return VT<V>::far;
-    return fabs(k.Sc - p.Spx) - (k.Vc * k.Vc / (-2.0 * c.acc_lo));
-}
-
-// pedestrian.detection, SC:176-264; `res` is accumulated into reward_light by the caller (SC:841-846)
-template <int V, int MC>
-MH_HD void detection(const EnvConst &c, const Geo &g, PedR &p, CarR (&car)[MC], const double (&prevSc)[MC],
-                     double (&res)[MC]) {
-    typedef VT<V> T;
-    const double time_braking = -(10.0 / (2.0 * c.acc_lo)) + 1.0;                    // SC:580 (Vc = 10 at construction)
-    const double wait_t = (double)p.waitc * c.dt, cross_t = (double)p.crossc * c.dt;
-#pragma unroll
-    for (int i = 0; i < MC; ++i) {
-        if (i >= c.nlead) continue;                                                  // C4:815: leaders only
-        CarR &k = car[i];
-        if (!in_front(g, p, k.line, 0.0)) continue;                                  // SC:180
-        if (T::scal && !k.exist) continue;
-        const bool cif = crossing_in_front(g, p, k.line, 0.0);
-        const double wdl = worst_delta_l<V>(c, g, p, k);
-        bool ped_accident;
-        if (T::naif) {                                                               // NA:181-185: new flag first
-            p.fl = (wdl < 0.0) ? (p.fl | PF_WORST_ACC) : (p.fl & ~PF_WORST_ACC);
-            ped_accident = !(p.fl & PF_ACCIDENT) && (p.fl & PF_WORST_ACC);
-        } else {                                                                     // SC:181-182
-            ped_accident = !(p.fl & PF_ACCIDENT) && (p.fl & PF_WORST_ACC);
-            p.fl = (wdl < 0.0) ? (p.fl | PF_WORST_ACC) : (p.fl & ~PF_WORST_ACC);
-        }
-        if (ped_accident && cif && (prevSc[i] < p.Spx) && (k.Sc > p.Spx)) p.fl |= PF_ACCIDENT;   // SC:184-185
-        if (cif) {                                                                   // SC:187-201
-            const double dl = (k.Vc < 0.05) ? T::far : wdl / k.Vc;
-            double pa;
-            if (dl > 0.0) pa = -1.0 * exp(-4.0 * dl);
-            else pa = T::neg_dl ? (-1.0 * dl - 1.0) : (1.0 * dl - 1.0);
-            k.pa = dmin(k.pa, pa);
-        }
-        if (k.Sc < p.Spx) {                                                          // SC:206-208 / NA:207-208
-            double ts;
-            if (T::naif) ts = ((wait_t + 10.0 * cross_t) - time_braking) + 1.0;
-            else {
-                double nwait = 0.0;
-#pragma unroll
-                for (int q = 0; q < MC; ++q)
-                    if (q < c.nlead && car[q].light > 0.0 && car[q].Sc < p.Spx && (!T::scal || car[q].exist)) nwait += 1.0;
-                ts = (((1.0 + nwait) * wait_t + 2.0 * cross_t) - time_braking) + 1.0;
-            }
-            k.Ts = dmax(ts, k.Ts);
-        }
-        if (k.light < 0.0) {                                                         // SC:216-228
-            const double ne = (k.Ts < 0.0) ? (-1.0 * exp(4.0 * k.Ts)) : (-1.0 * (1.0 + k.Ts));
-            if (!T::naif && cif && (k.Sc < p.Spx)) p.fl |= PF_NOT_WAITING;
-            k.es = dmin(ne, k.es);
-        }
-        if (k.light > 0.0) {                                                         // SC:230-237
-            const double gap = p.Spx - k.Sc;
-            const double ne = (gap > 0.0) ? (-1.0 * exp(-4.0 * gap)) : (-1.0 * ((1.0 + k.Sc) - p.Spx));
-            k.es = dmin(ne, k.es);
-        }
-    }
-    double green = 0.0;                                                              // SC:246
-#pragma unroll
-    for (int q = 0; q < MC; ++q)
-        if (q < c.nlead && car[q].light > 0.0 && (!T::scal || car[q].exist)) green += 1.0;
-#pragma unroll
-    for (int i = 0; i < MC; ++i) {                                                   // SC:250-263
-        double r = car[i].pa + car[i].es;
-        if (T::danger_sign != 0) {
-            const double extra = (0.5 * green * (double)(car[i].light < 0.0)) * (double)(car[i].Ts > 0.0);
-            r = (T::danger_sign > 0) ? (r + extra) : (r - extra);
-        }
-        if (T::scal && !car[i].exist) r = 0.0;
-        res[i] = r;
-    }
-}
-
-// pedestrian.new_reward_wait_safety, SC:478-506 (+ delta_l SC:516-520)
-template <int V>
-MH_HD double wait_safety(const EnvConst &c, const Geo &g, PedR &p, const CarR &k) {
-    if (!(p.fl & PF_LEFT) && (p.fl & PF_CROSSING) && (k.Sc < p.Spx) && in_front(g, p, k.line, 0.0)) {
-        double e;
-        if (k.Vc < VT<V>::wait_thr) e = 0.0;
-        else {
-            const double d = (fabs(k.Sc - p.Spx) - (k.Vc * k.Vc / (-2.0 * c.acc_lo))) - 1.0 * k.Vc;
-            const double dl = d / k.Vc;
-            if (dl >= -1.0) e = dmax(-20.0 * exp(-4.0 * dl - 4.0), -20.0);
-            else e = 20.0 * dl;
-        }
-        e = e - ((p.fl & PF_ACCIDENT) ? 20.0 : 0.0);
-        if (e < p.wdl) p.wdl = e;
-    }
-    return p.wdl;
 }
 
 // car.sigma SC:592-602
@@ -566,100 +302,4 @@ MH_NOINLINE void reset_env(const EnvConst &c, EnvR<MC, MP> &e) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Action vector of one env split per car slot: acc[s] = actions[s], light[s] = actions[nA/2 + s]
-// (SC:798-802 [acc x 2L, light x 2L]; CO:754-755; C42:809-811 [acc_l, acc_f, light_l, light_f] with
-// follower slot s = nb_car + i).
-template <int MC>
-struct ActR { float acc[MC], light[MC]; };
-
-// one env.step: SC:789-878.  Returns done.  rewards / reward_light are written through
-// RewOut(i, reward, reward_light).
-template <int V, int MC, int MP, class RewOut>
-MH_HD bool step_env(const EnvConst &c, EnvR<MC, MP> &e, const ActR<MC> &act, RewOut &rew_out) {
-    typedef VT<V> T;
-    const Geo g = make_geo(e.cross, c.L);
-    double prevSc[MC];
-#pragma unroll
-    for (int i = 0; i < MC; ++i) prevSc[i] = e.car[i].Sc;                            // SC:797
-    // ---- cars (SC:798-802 / C4:792-795 / C42:808-811 / CO:754-755)
-    if (T::scal) {
-#pragma unroll
-        for (int i = 0; i < MC; ++i) {
-            if (i >= c.nC) continue;
-            double a = (double)act.acc[i];
-            if ((i & 1) && e.car[i > 0 ? i - 1 : 0].exist && e.car[i].exist)
-                a = dmin(idm(c, e.car[i], e.car[i > 0 ? i - 1 : 0].Sc, e.car[i > 0 ? i - 1 : 0].Vc), a);
-            else a = dmin(2.0, a);
-            car_move<V>(c, e.car[i], a, (double)act.light[i]);
-        }
-    } else if (T::four) {
-        const int n = c.nb_car;
-#pragma unroll
-        for (int i = 0; i < MC / 2; ++i) {
-            if (i >= n) continue;
-            car_move<V>(c, e.car[i], (double)act.acc[i], (double)act.light[i]);
-        }
-#pragma unroll
-        for (int i = 0; i < MC / 2; ++i) {
-            if (i >= n) continue;
-            // follower slot n+i; static register index needs the compile-time bound MC/2 == n
-            CarR &f = e.car[MC / 2 + i];
-            const double a_idm = idm(c, f, e.car[i].Sc, e.car[i].Vc);
-            if (V == V_4CARS2) car_move<V>(c, f, dmin(a_idm, (double)act.acc[MC / 2 + i]), (double)act.light[MC / 2 + i]);
-            else car_move<V>(c, f, a_idm, e.car[i].light);
-        }
-    } else {
-#pragma unroll
-        for (int i = 0; i < MC; ++i) {
-            if (i >= c.nC) continue;
-            car_move<V>(c, e.car[i], (double)act.acc[i], (double)act.light[i]);
-        }
-    }
-    // ---- pedestrians (SC:803-809)
-    uint32_t seen = 0; int nseen = 0;
-#pragma unroll
-    for (int i = 0; i < MC; ++i)
-        if (i < c.nC && (!T::scal || e.car[i].exist)) { seen |= 1u << i; ++nseen; }
-#pragma unroll
-    for (int j = 0; j < MP; ++j)
-        if (j < c.nP) ped_step<V, MC>(c, g, e.ped[j], e.car, seen, nseen, e.step, e.rng);
-    // ---- danger detection (SC:841-846)
-    double rl[MC];
-#pragma unroll
-    for (int i = 0; i < MC; ++i) rl[i] = 0.0;
-#pragma unroll
-    for (int j = 0; j < MP; ++j) {
-        if (j >= c.nP) continue;
-        double res[MC];
-        detection<V, MC>(c, g, e.ped[j], e.car, prevSc, res);
-        const bool add = (e.ped[j].fl & PF_CROSSING) && (!T::scal || (e.ped[j].fl & PF_EXIST));
-        if (add) {
-#pragma unroll
-            for (int i = 0; i < MC; ++i) rl[i] += res[i];
-        }
-    }
-    // ---- rewards (SC:849-858)
-#pragma unroll
-    for (int i = 0; i < MC; ++i) {
-        if (i >= c.nlead) continue;
-        const CarR &k = e.car[i];
-        const double d = k.Vc - 10.0;
-        double r = (-10.0 * (d * d)) / 100.0;                                        // SC:657-665
-        if (!(k.light <= 0.0)) {
-            bool any = false; double m = 0.0;
-#pragma unroll
-            for (int j = 0; j < MP; ++j) {
-                if (j >= c.nP || !(e.ped[j].fl & PF_EXIST)) continue;
-                const double w = wait_safety<V>(c, g, e.ped[j], k);
-                if (!any || w < m) { m = w; any = true; }
-            }
-            if (any) r += m;
-        }
-        rew_out(i, r, rl[i]);
-    }
-    const bool done = (e.step >= c.done_idx) || (e.ped_traffic <= 0);                // SC:874
-    e.step += 1;                                                                     // SC:875
-    return done;
-}
-
 }  // namespace mhppo

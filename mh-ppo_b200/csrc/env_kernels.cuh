@@ -9,74 +9,18 @@
 #pragma once
 #include <cuda_runtime.h>
 
-#include "../../include/mhppo.h"
-#include "env_state.cuh"
+#include "env_step.cuh"
 
 namespace mhppo {
 
 constexpr int kEnvBlock = 128;
-
-struct RngKey { uint32_t k0, k1; int64_t env_id0; };
-
-struct StepIO {
-    mhppo_view actions, obs, rewards, reward_light, term_obs;
-    uint8_t *done;
-    int autoreset;
-};
-
-struct ViewOut {
-    float *p; int64_t cs;
-    __device__ __forceinline__ void operator()(int k, float v) const { p[(int64_t)k * cs] = v; }
-};
-struct NullOut {
-    __device__ __forceinline__ void operator()(int, float) const {}
-};
+constexpr int kEnvMinBlocks = 3;   // register cap 168/thread -> 12 warps/SM
 
 template <int V, int MC, int MP>
-__global__ void __launch_bounds__(kEnvBlock) k_env_step(EnvArena a, EnvConst c, RngKey key, StepIO io) {
+__global__ void __launch_bounds__(kEnvBlock, kEnvMinBlocks) k_env_step(EnvArena a, EnvConst c, RngKey key, StepIO io) {
     const int64_t n = (int64_t)blockIdx.x * kEnvBlock + threadIdx.x;
     if (n >= a.N) return;
-    EnvR<MC, MP> e;
-    const uint64_t gid = (uint64_t)(key.env_id0 + n);
-    e.rng.env_lo = (uint32_t)gid; e.rng.env_hi = (uint32_t)(gid >> 32); e.rng.k0 = key.k0; e.rng.k1 = key.k1;
-    load_env<MC, MP>(a, c, n, e);
-
-    // action vector of this env, read once up front: acc[s] = a[s], light[s] = a[nA/2 + s]
-    ActR<MC> act;
-    {
-        const float *ap = io.actions.ptr + n * io.actions.env_stride;
-        const int half = c.nA / 2;
-#pragma unroll
-        for (int s = 0; s < MC; ++s) {
-            act.acc[s] = (s < half) ? ap[(int64_t)s * io.actions.comp_stride] : 0.f;
-            act.light[s] = (s < half) ? ap[(int64_t)(half + s) * io.actions.comp_stride] : 0.f;
-        }
-    }
-    float *rp = io.rewards.ptr ? io.rewards.ptr + n * io.rewards.env_stride : nullptr;
-    float *lp = io.reward_light.ptr ? io.reward_light.ptr + n * io.reward_light.env_stride : nullptr;
-    auto rew_out = [&](int i, double r, double rl) {
-        if (rp) rp[(int64_t)i * io.rewards.comp_stride] = (float)r;
-        if (lp) lp[(int64_t)i * io.reward_light.comp_stride] = (float)rl;
-    };
-    const bool done = step_env<V, MC, MP>(c, e, act, rew_out);
-    if (io.done) io.done[n] = done ? 1 : 0;
-
-    const bool do_reset = done && io.autoreset;
-#pragma unroll 1
-    for (int pass = 0; pass < 2; ++pass) {
-        const bool last = !do_reset || pass == 1;
-        const mhppo_view &v = last ? io.obs : io.term_obs;
-        if (v.ptr) {
-            ViewOut out{v.ptr + n * v.env_stride, v.comp_stride};
-            write_obs<V, MC, MP>(c, e, pass == 1, out);
-        }
-        if (last) break;
-        EnvR<MC, MP> fresh;                 // scratch copy: only this rare branch touches local memory
-        fresh.rng = e.rng;
-        reset_env<V, MC, MP>(c, fresh);
-        e = fresh;
-    }
-    store_env<MC, MP>(a, c, n, e);
+    env_step_thread<V, MC, MP>(a, c, key, io, n);
 }
 
 template <int V, int MC, int MP>
@@ -85,14 +29,11 @@ __global__ void __launch_bounds__(kEnvBlock) k_env_reset(EnvArena a, EnvConst c,
     const int64_t n = (int64_t)blockIdx.x * kEnvBlock + threadIdx.x;
     if (n >= a.N) return;
     if (mask && !mask[n]) return;
-    EnvR<MC, MP> e;
+    Rng rng;
     const uint64_t gid = (uint64_t)(key.env_id0 + n);
-    e.rng.env_lo = (uint32_t)gid; e.rng.env_hi = (uint32_t)(gid >> 32); e.rng.k0 = key.k0; e.rng.k1 = key.k1;
-    e.rng.ctr = f2u(a.env_e[n].w);          // the stream cursor survives resets (episodes share one stream)
-    reset_env<V, MC, MP>(c, e);
-    if (obs.ptr) { ViewOut out{obs.ptr + n * obs.env_stride, obs.comp_stride}; write_obs<V, MC, MP>(c, e, true, out); }
-    else { NullOut nul; write_obs<V, MC, MP>(c, e, true, nul); }   // get_data still updates the running-min delta
-    store_env<MC, MP>(a, c, n, e);
+    rng.env_lo = (uint32_t)gid; rng.env_hi = (uint32_t)(gid >> 32); rng.k0 = key.k0; rng.k1 = key.k1;
+    rng.ctr = f2u(a.env_e[n].w);            // the stream cursor survives resets (episodes share one stream)
+    reset_and_store<V, MC, MP>(a, c, n, rng, obs);
 }
 
 // ---- instantiation table -----------------------------------------------------------------------

@@ -8,7 +8,7 @@ CSRC = os.path.join(HERE, "..", "..", "mh-ppo_b200", "csrc")
 
 
 def build(force=False):
-    srcs = [os.path.join(HERE, "hostsim.cpp")] + [os.path.join(CSRC, f) for f in ("env_core.cuh", "env_state.cuh", "philox.cuh")]
+    srcs = [os.path.join(HERE, "hostsim.cpp")] + [os.path.join(CSRC, f) for f in ("env_core.cuh", "env_state.cuh", "env_step.cuh", "philox.cuh")]
     if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= max(os.path.getmtime(s) for s in srcs):
         return LIB
     subprocess.run(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-D_GNU_SOURCE",

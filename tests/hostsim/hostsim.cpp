@@ -7,13 +7,11 @@
 #include <stdlib.h>
 #include <math.h>
 #define _GNU_SOURCE 1
-#include "../../mh-ppo_b200/csrc/env_state.cuh"
+#include "../../mh-ppo_b200/csrc/env_step.cuh"
 
 using namespace mhppo;
 
-struct View { float *ptr; int64_t env_stride, comp_stride; };
-struct HostOut { float *p; int64_t cs; void operator()(int k, float v) const { p[(int64_t)k * cs] = v; } };
-struct NullOutH { void operator()(int, float) const {} };
+typedef mhppo_view View;
 
 struct Sim {
     int variant, mc, mp;
@@ -21,57 +19,25 @@ struct Sim {
 };
 
 template <int V, int MC, int MP>
-static void sim_reset(Sim *s, const uint8_t *mask, View obs) {
+static void sim_reset(Sim *s, const uint8_t *mask, mhppo_view obs) {
     for (int64_t n = 0; n < s->a.N; ++n) {
         if (mask && !mask[n]) continue;
-        EnvR<MC, MP> e; memset(&e, 0, sizeof(e));
+        Rng rng;
         const uint64_t gid = (uint64_t)(s->env_id0 + n);
-        e.rng.env_lo = (uint32_t)gid; e.rng.env_hi = (uint32_t)(gid >> 32); e.rng.k0 = s->k0; e.rng.k1 = s->k1;
-        e.rng.ctr = f2u(s->a.env_e[n].w);
-        reset_env<V, MC, MP>(s->c, e);
-        if (obs.ptr) { HostOut out{obs.ptr + n * obs.env_stride, obs.comp_stride}; write_obs<V, MC, MP>(s->c, e, true, out); }
-        else { NullOutH nul; write_obs<V, MC, MP>(s->c, e, true, nul); }
-        store_env<MC, MP>(s->a, s->c, n, e);
+        rng.env_lo = (uint32_t)gid; rng.env_hi = (uint32_t)(gid >> 32); rng.k0 = s->k0; rng.k1 = s->k1;
+        rng.ctr = f2u(s->a.env_e[n].w);
+        reset_and_store<V, MC, MP>(s->a, s->c, n, rng, obs);
     }
 }
 
 template <int V, int MC, int MP>
-static void sim_step(Sim *s, View actions, View obs, View rewards, View reward_light, uint8_t *done, int autoreset,
-                     View term_obs) {
-    const EnvConst &c = s->c;
-    for (int64_t n = 0; n < s->a.N; ++n) {
-        EnvR<MC, MP> e; memset(&e, 0, sizeof(e));
-        const uint64_t gid = (uint64_t)(s->env_id0 + n);
-        e.rng.env_lo = (uint32_t)gid; e.rng.env_hi = (uint32_t)(gid >> 32); e.rng.k0 = s->k0; e.rng.k1 = s->k1;
-        load_env<MC, MP>(s->a, c, n, e);
-        ActR<MC> act;
-        const float *ap = actions.ptr + n * actions.env_stride;
-        const int half = c.nA / 2;
-        for (int q = 0; q < MC; ++q) {
-            act.acc[q] = (q < half) ? ap[(int64_t)q * actions.comp_stride] : 0.f;
-            act.light[q] = (q < half) ? ap[(int64_t)(half + q) * actions.comp_stride] : 0.f;
-        }
-        float *rp = rewards.ptr ? rewards.ptr + n * rewards.env_stride : nullptr;
-        float *lp = reward_light.ptr ? reward_light.ptr + n * reward_light.env_stride : nullptr;
-        auto rew_out = [&](int i, double r, double rl) {
-            if (rp) rp[(int64_t)i * rewards.comp_stride] = (float)r;
-            if (lp) lp[(int64_t)i * reward_light.comp_stride] = (float)rl;
-        };
-        const bool d = step_env<V, MC, MP>(c, e, act, rew_out);
-        if (done) done[n] = d ? 1 : 0;
-        const bool do_reset = d && autoreset;
-        for (int pass = 0; pass < 2; ++pass) {
-            const bool last = !do_reset || pass == 1;
-            const View &v = last ? obs : term_obs;
-            if (v.ptr) { HostOut out{v.ptr + n * v.env_stride, v.comp_stride}; write_obs<V, MC, MP>(c, e, pass == 1, out); }
-            if (last) break;
-            EnvR<MC, MP> fresh; memset(&fresh, 0, sizeof(fresh));
-            fresh.rng = e.rng;
-            reset_env<V, MC, MP>(c, fresh);
-            e = fresh;
-        }
-        store_env<MC, MP>(s->a, c, n, e);
-    }
+static void sim_step(Sim *s, mhppo_view actions, mhppo_view obs, mhppo_view rewards, mhppo_view reward_light, uint8_t *done,
+                     int autoreset, mhppo_view term_obs) {
+    StepIO io;
+    io.actions = actions; io.obs = obs; io.rewards = rewards; io.reward_light = reward_light; io.term_obs = term_obs;
+    io.done = done; io.autoreset = autoreset;
+    RngKey key; key.k0 = s->k0; key.k1 = s->k1; key.env_id0 = s->env_id0;
+    for (int64_t n = 0; n < s->a.N; ++n) env_step_thread<V, MC, MP>(s->a, s->c, key, io, n);   // the kernel's thread body
 }
 
 #define DISPATCH(FN, ...)                                                                          \
