@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmhppo_b200.so")
+LIB_PATH = os.environ.get("MHPPO_LIB", os.path.join(_HERE, "libmhppo_b200.so"))  # override: kernel-tuning experiments only
 
 
 class LibraryMissing(RuntimeError):

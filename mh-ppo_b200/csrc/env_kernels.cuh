@@ -14,18 +14,22 @@
 namespace mhppo {
 
 constexpr int kEnvBlock = 128;
-constexpr int kEnvMinBlocks = 3;   // register cap 168/thread -> 12 warps/SM
+#ifndef MH_ENV_MIN_BLOCKS
+#define MH_ENV_MIN_BLOCKS 3
+#endif
+constexpr int kEnvMinBlocks = MH_ENV_MIN_BLOCKS;   // 3 -> register cap 168/thread, 12 warps/SM
 
 template <int V, int MC, int MP>
-__global__ void __launch_bounds__(kEnvBlock, kEnvMinBlocks) k_env_step(EnvArena a, EnvConst c, RngKey key, StepIO io) {
+__global__ void __launch_bounds__(kEnvBlock, kEnvMinBlocks) k_env_step(const __grid_constant__ EnvArena a, const __grid_constant__ EnvConst c,
+                                                                           const __grid_constant__ RngKey key, const __grid_constant__ StepIO io) {
     const int64_t n = (int64_t)blockIdx.x * kEnvBlock + threadIdx.x;
     if (n >= a.N) return;
     env_step_thread<V, MC, MP>(a, c, key, io, n);
 }
 
 template <int V, int MC, int MP>
-__global__ void __launch_bounds__(kEnvBlock) k_env_reset(EnvArena a, EnvConst c, RngKey key, const uint8_t *mask,
-                                                         mhppo_view obs) {
+__global__ void __launch_bounds__(kEnvBlock) k_env_reset(const __grid_constant__ EnvArena a, const __grid_constant__ EnvConst c,
+                                                         const __grid_constant__ RngKey key, const uint8_t *mask, mhppo_view obs) {
     const int64_t n = (int64_t)blockIdx.x * kEnvBlock + threadIdx.x;
     if (n >= a.N) return;
     if (mask && !mask[n]) return;

@@ -11,9 +11,10 @@
 //    fields, so interleaving them per pedestrian is exactly equivalent (DESIGN.md "Step kernel").
 //    It keeps one pedestrian in registers instead of P, and the hot loop body exists once in SASS
 //    (the first version unrolled everything: 28k instructions, instruction-fetch bound).
-//  * rare, bulky paths are single out-of-line copies working on a compact scratch copy:
-//    the gap-acceptance decision `choix_pedestrian` (log10/pow/normal draw), the sin walking
-//    profile (fp64 sincos) and the episode reset.
+//  * bulky paths are single out-of-line copies: the sin walking profile (fp64 sincos), the
+//    episode reset, and the exact fp64 critical gap.  The gap-acceptance decision
+//    `choix_pedestrian` runs every step for a waiting pedestrian, so its log10/pow/normal-draw
+//    comparison is a filtered predicate: fp32 with an error bound, fp64 only when undecidable.
 //  * geometry predicates is_in_front / is_crossing_in_front are evaluated once per (ped, car)
 //    into bit masks and reused by detection, rewards and the observation.
 //  * reward-shaping exponentials feed only fp32 outputs: their argument is formed in fp64 and the
@@ -34,58 +35,99 @@ struct StepIO {
 };
 
 // ---------------------------------------------------------------------------------------------
-// out-of-line rare paths
-struct ChoixCar { double Sc, Vc, light; int line; };
-struct ChoixIn {
-    PedR p;            // only Spx, Spy, v0y, dir, lpos, gender, age, fl are read
-    double cross;
-    int L, n;
-    ChoixCar car[16];  // the cars handed to pedestrian.step, in list order
-};
+// gap-acceptance decision
 
-// pedestrian.choix_pedestrian, SC:139-174 / NA:138-177.  Returns (new_ctr << 1) | choose.
-template <int V>
-MH_NOINLINE uint64_t choix_slow(const ChoixIn *in, Rng rng) {
+// Exact critical gap of pedestrian.CG_score (SC:419-428) from the two uniforms of its normal draw.
+// Out of line: only reached when the fp32 filter below cannot decide (~1e-4 of the draws).
+static MH_NOINLINE double cg_exact(double v0y, int gender, int age, double size, double u1, double u2) {
+    double lv = 0.09 + log10(size / fabs(v0y + 10e-3));
+    lv = lv + 0.0369 * (double)(gender == 1);
+    lv = lv + -0.0355 * (double)(age == 0);
+    lv = lv + -0.0221 * (double)(age == 1);
+    lv = lv + -0.1810 * (double)(age == 2);
+    lv = lv + (0.0 + 0.09 * (sqrt(-2.0 * log(1.0 - u1)) * cos(2.0 * 3.141592653589793 * u2)));
+    return pow(10.0, lv);
+}
+
+// `car_time + light < CG` of SC:167-170, bit-exact at fp32 cost: the comparison is first evaluated
+// in fp32 with a conservative error bound (filtered predicate); only an undecidable case recomputes
+// both sides in fp64 exactly as the reference does.  One Philox block per call, like CG_score.
+// Returns (new_ctr << 1) | refused.  Out of line (one copy): a few of these run per waiting pedestrian.
+static MH_NOINLINE uint64_t gap_refused_ol(double Spx, double v0y, int dlines, int gender, int age, bool crossing,
+                                           double Sc, double Vc, double light, double cross, Rng rng) {
+    const double dx = Sc - Spx, vden = Vc + 10e-3;
+    bool refused;
+    if (!crossing) refused = (fabs(dx / vden) + light) < 0.0;                        // CG = 0., no draw (SC:427-428)
+    else {
+        const PhiloxBlock b = rng.next();
+        const double u1 = u53(b.w0, b.w1), u2 = u53(b.w2, b.w3);
+        const double size = fabs((double)dlines) * cross;
+        const double pden = fabs(v0y + 10e-3);
+        // fp32 estimate: CG = size/|v0y+.01| * 10^(0.09 + gender/age terms + 0.09*z)
+        const float adj = 0.09f + ((gender == 1) ? 0.0369f : 0.f) + ((age == 0) ? -0.0355f : ((age == 1) ? -0.0221f : -0.1810f));
+#ifdef __CUDA_ARCH__
+        const float cz = cospif(2.0f * (float)u2);
+#else
+        const float cz = cosf(6.2831853f * (float)u2);
+#endif
+        const float z = sqrtf(-2.0f * logf((float)(1.0 - u1))) * cz;
+        const float cg = ((float)size / (float)pden) * exp2f(3.3219280948873623f * (adj + 0.09f * z));
+        const float lhs = fabsf((float)dx / (float)vden) + (float)light;
+        const float tol = 2e-4f * (fabsf(lhs) + cg) + 1e-30f;
+        if (fabsf(lhs - cg) > tol) refused = lhs < cg;
+        else refused = (fabs(dx / vden) + light) < cg_exact(v0y, gender, age, size, u1, u2);
+    }
+    return ((uint64_t)rng.ctr << 1) | (refused ? 1u : 0u);
+}
+MH_HD bool gap_refused(const PedR &p, const CarR &k, double cross, Rng &rng) {
+    const uint64_t r = gap_refused_ol(p.Spx, p.v0y, p.lpos - k.line, p.gender, p.age, (p.fl & PF_CROSSING) != 0, k.Sc, k.Vc,
+                                      k.light, cross, rng);
+    rng.ctr = (uint32_t)(r >> 1);
+    return (r & 1u) != 0;
+}
+
+// pedestrian.choix_pedestrian, SC:139-174 / NA:138-177.  `seen` = slots handed to pedestrian.step
+// (existing cars in scalable SC:803-806, leaders+followers in 4cars C4:796-799, all otherwise).
+template <int V, int MC>
+MH_HD bool choix_fast(const Geo &g, const PedR &p, const CarR (&car)[MC], uint32_t seen, Rng &rng) {
     typedef VT<V> T;
-    const PedR &p = in->p;
-    const Geo g = make_geo(in->cross, in->L);
-    const int n = in->n;
-    bool result = true, decided = false;
+    const int nseen = __builtin_popcount(seen);
+    // per-car predicates of this decision
+    uint32_t inf1 = 0, on_cross = 0, behind = 0, blocked = 0;
+#pragma unroll
+    for (int i = 0; i < MC; ++i) {
+        if (!((seen >> i) & 1u)) continue;
+        const bool f1 = in_front(g, p, car[i].line, 1.0);
+        const bool over = (car[i].Sc < 4.0 + p.Spx) && (car[i].Sc > p.Spx);          // car body on the crosswalk
+        if (f1) inf1 |= 1u << i;
+        if (over) on_cross |= 1u << i;
+        if (car[i].Sc < p.Spx) behind |= 1u << i;
+        if (over && f1 && crossing_in_front(g, p, car[i].line, 0.5)) blocked |= 1u << i;
+    }
     if (p.fl & PF_FOLLOW) {
-        int order[16];
-        for (int i = 0; i < n; ++i) order[i] = i;
-        if (n > 1) {
-            if (T::naif) {                                         // NA:151 permutes the visiting order
-                for (int i = n - 1; i > 0; --i) {
-                    int j = (int)floor(rng.random() * (double)(i + 1));
-                    if (j > i) j = i;
-                    const int t = order[i]; order[i] = order[j]; order[j] = t;
-                }
-            } else if (T::burn_shuffle) rng.skip(n - 1);           // SC:152-153 shuffles a temporary
-        }
-        for (int k = 0; k < n && !decided; ++k) {                  // SC:154-158
-            const ChoixCar &q = in->car[order[k]];
-            if (crossing_in_front(g, p, q.line, 0.5) && in_front(g, p, q.line, 1.0) && (q.Sc < 4.0 + p.Spx) && (q.Sc > p.Spx)) {
-                result = false; decided = true;
-            }
-        }
-        for (int k = 0; k < n && !decided; ++k) {                  // SC:159-161 / NA:156-158
-            const ChoixCar &q = in->car[order[k]];
-            if (T::naif) { if (q.Sc < p.Spx && q.light < 0.0) { result = false; decided = true; } }
-            else if (q.Sc < p.Spx && q.light != 0.0) { result = q.light > 0.0; decided = true; }
+        if (T::naif) {
+            // NA:151 shuffles the visiting order for real, but both loops below only ever return False
+            // (NA:153-158), so the order cannot change the outcome: only the n-1 draws are consumed
+            if (nseen > 1) rng.skip(nseen - 1);
+            if (blocked) return false;                                               // NA:153-155
+#pragma unroll
+            for (int i = 0; i < MC; ++i)                                             // NA:156-158
+                if (((seen & behind) >> i) & 1u) { if (car[i].light < 0.0) return false; }
+        } else {
+            if (T::burn_shuffle && nseen > 1) rng.skip(nseen - 1);                   // SC:152-153: shuffles a temporary
+            if (blocked) return false;                                               // SC:154-158
+#pragma unroll
+            for (int i = 0; i < MC; ++i)                                             // SC:159-161: first upstream car with a light
+                if (((seen & behind) >> i) & 1u) { if (car[i].light != 0.0) return car[i].light > 0.0; }
         }
     }
-    for (int i = 0; i < n && !decided; ++i) {                      // SC:162-173
-        const ChoixCar &q = in->car[i];
-        if (!in_front(g, p, q.line, 1.0)) continue;
-        if ((q.Sc < 4.0 + p.Spx) && (q.Sc > p.Spx)) { result = false; decided = true; break; }
-        if (q.Sc < p.Spx) {
-            const double car_time = fabs((q.Sc - p.Spx) / (q.Vc + 10e-3));
-            const double CG = cg_score(p, fabs((double)(p.lpos - q.line)) * g.cross, rng);
-            if (car_time + q.light < CG) { result = false; decided = true; }
-        }
+#pragma unroll
+    for (int i = 0; i < MC; ++i) {                                                   // SC:162-173
+        if (!(((seen & inf1) >> i) & 1u)) continue;
+        if ((on_cross >> i) & 1u) return false;
+        if ((behind >> i) & 1u) { if (gap_refused(p, car[i], g.cross, rng)) return false; }
     }
-    return ((uint64_t)rng.ctr << 1) | (result ? 1u : 0u);
+    return true;
 }
 
 struct WalkOut { double pos, spd; };
@@ -146,19 +188,7 @@ MH_HD void ped_step_stream(const EnvConst &c, const Geo &g, PedR &p, const CarR 
     else if (dy > g.Hn) p.fl |= PF_IN_CROSS;
     if (!(p.fl & PF_CROSSING)) return;                                               // SC:308
 
-    // the two places that may call choix_pedestrian share one out-of-line call site
-    auto choix = [&]() -> bool {
-        ChoixIn in;
-        in.p = p; in.cross = g.cross; in.L = c.L;
-        int m = 0;
-#pragma unroll
-        for (int i = 0; i < MC; ++i)
-            if ((seen >> i) & 1u) { in.car[m].Sc = car[i].Sc; in.car[m].Vc = car[i].Vc; in.car[m].light = car[i].light; in.car[m].line = car[i].line; ++m; }
-        in.n = m;
-        const uint64_t r = choix_slow<V>(&in, rng);
-        rng.ctr = (uint32_t)(r >> 1);
-        return (r & 1u) != 0;
-    };
+    auto choix = [&]() -> bool { return choix_fast<V, MC>(g, p, car, seen, rng); };
 
     bool choose = true;
     const bool first_decision = !(p.fl & PF_DECISION) && (p.fl & PF_AT_CROSSING);    // SC:311
@@ -380,42 +410,45 @@ MH_HD void env_step_thread(const EnvArena &a, const EnvConst &c, const RngKey &k
             if (((lead_ok & behind) >> i) & 1u) { if (car[i].light > 0.0) nwait += 1.0; }
         const double ts_new = T::naif ? (((wait_t + 10.0 * cross_t) - time_braking) + 1.0)
                                       : ((((1.0 + nwait) * wait_t + 2.0 * cross_t) - time_braking) + 1.0);
+        // Written branch-free on purpose: lanes (envs) disagree on every one of these conditions, so
+        // each pair is evaluated once with selects instead of serialising the sides of the branches.
+        uint32_t fl = p.fl;
 #pragma unroll
         for (int i = 0; i < MC; ++i) {
-            if (!(((lead_ok & inf) >> i) & 1u)) continue;                            // SC:180
+            if (i >= c.nlead) continue;
             CarR &k = car[i];
+            const bool gi = ((lead_ok & inf) >> i) & 1u;                             // SC:180
             const bool bi = (behind >> i) & 1u, ci = (cif >> i) & 1u;
-            const double wdl = (k.Sc > p.Spx || left) ? T::far : raw[i];             // worst_delta_l SC:522-527
-            bool ped_accident;
-            if (T::naif) {                                                           // NA:181-185
-                p.fl = (wdl < 0.0) ? (p.fl | PF_WORST_ACC) : (p.fl & ~PF_WORST_ACC);
-                ped_accident = !(p.fl & PF_ACCIDENT) && (p.fl & PF_WORST_ACC);
-            } else {                                                                 // SC:181-182
-                ped_accident = !(p.fl & PF_ACCIDENT) && (p.fl & PF_WORST_ACC);
-                p.fl = (wdl < 0.0) ? (p.fl | PF_WORST_ACC) : (p.fl & ~PF_WORST_ACC);
-            }
-            if (ped_accident && ci && (prevSc[i] < p.Spx) && (k.Sc > p.Spx)) p.fl |= PF_ACCIDENT;   // SC:184-185
-            if (ci) {                                                                // SC:187-201
+            const bool ahead = (k.Sc > p.Spx);
+            const double wdl = (ahead || left) ? T::far : raw[i];                    // worst_delta_l SC:522-527
+            const bool wneg = wdl < 0.0;
+            const bool acc0 = (fl & PF_ACCIDENT) != 0;
+            bool wa = (fl & PF_WORST_ACC) != 0;
+            const bool ped_accident = T::naif ? (!acc0 && wneg) : (!acc0 && wa);     // SC:181-182 / NA:181-185
+            wa = gi ? wneg : wa;
+            const bool hit = gi && ped_accident && ci && (prevSc[i] < p.Spx) && ahead;   // SC:184-185
+            fl = (fl & ~PF_WORST_ACC) | (wa ? PF_WORST_ACC : 0u) | (hit ? PF_ACCIDENT : 0u);
+            {                                                                        // SC:187-201
                 const bool slow = k.Vc < 0.05;
                 const double dl = slow ? T::far : wdl * rVc[i];
                 const bool pos = slow ? (T::far > 0.0) : (wdl > 0.0);
-                double pa;
-                if (pos) pa = -(double)exp_f32(-4.0 * dl);
-                else pa = T::neg_dl ? (-1.0 * dl - 1.0) : (1.0 * dl - 1.0);
-                k.pa = dmin(k.pa, pa);
+                const double lin = T::neg_dl ? (-1.0 * dl - 1.0) : (1.0 * dl - 1.0);
+                const double pa = pos ? -(double)exp_f32(-4.0 * dl) : lin;
+                k.pa = (gi && ci) ? dmin(k.pa, pa) : k.pa;
             }
-            if (bi) k.Ts = dmax(ts_new, k.Ts);                                       // SC:207-208
-            if (k.light < 0.0) {                                                     // SC:216-228
-                const double ne = (k.Ts < 0.0) ? -(double)exp_f32(4.0 * k.Ts) : (-1.0 * (1.0 + k.Ts));
-                if (!T::naif && ci && bi) p.fl |= PF_NOT_WAITING;
-                k.es = dmin(ne, k.es);
-            }
-            if (k.light > 0.0) {                                                     // SC:230-237
+            k.Ts = (gi && bi) ? dmax(ts_new, k.Ts) : k.Ts;                           // SC:207-208
+            {                                                                        // SC:216-237
+                const bool red = k.light < 0.0, grn = k.light > 0.0;
                 const double gap = p.Spx - k.Sc;
-                const double ne = (gap > 0.0) ? -(double)exp_f32(-4.0 * gap) : (-1.0 * ((1.0 + k.Sc) - p.Spx));
-                k.es = dmin(ne, k.es);
+                const bool use_exp = red ? (k.Ts < 0.0) : (gap > 0.0);
+                const double arg = red ? (4.0 * k.Ts) : (-4.0 * gap);
+                const double lin = red ? (-1.0 * (1.0 + k.Ts)) : (-1.0 * ((1.0 + k.Sc) - p.Spx));
+                const double ne = use_exp ? -(double)exp_f32(arg) : lin;
+                k.es = (gi && (red || grn)) ? dmin(ne, k.es) : k.es;
+                if (!T::naif) fl |= (gi && red && ci && bi) ? PF_NOT_WAITING : 0u;
             }
         }
+        p.fl = fl;
         if ((p.fl & PF_CROSSING) && (!T::scal || (p.fl & PF_EXIST))) {               // SC:844-845, res: SC:250-263
 #pragma unroll
             for (int i = 0; i < MC; ++i) {
@@ -433,28 +466,25 @@ MH_HD void env_step_thread(const EnvArena &a, const EnvConst &c, const RngKey &k
         // ---- wait-reward contribution (SC:855-857 with new_reward_wait_safety SC:478-506); the
         // reference loops cars outside / pedestrians inside, but worst_dl is per pedestrian and only
         // sees the cars in ascending order, which this loop preserves
-        if (p.fl & PF_EXIST) {
-            const bool guard_p = !left && (p.fl & PF_CROSSING);
+        {
+            const bool ex = (p.fl & PF_EXIST) != 0;
+            const bool guard_p = ex && !left && (p.fl & PF_CROSSING);
+            const double acc_pen = (p.fl & PF_ACCIDENT) ? 20.0 : 0.0;
 #pragma unroll
             for (int i = 0; i < MC; ++i) {
                 if (i >= c.nlead) continue;
                 const CarR &k = car[i];
-                if (!(k.light > 0.0)) continue;
-                if (guard_p && ((behind & inf) >> i) & 1u) {
-                    double e;
-                    if (k.Vc < T::wait_thr) e = 0.0;
-                    else {
-                        const double d = raw[i] - 1.0 * k.Vc;                        // delta_l SC:516-520
-                        const double dl = d * rVc[i];
-                        if (d >= -k.Vc) e = dmax(-20.0 * (double)exp_f32(-4.0 * dl - 4.0), -20.0);
-                        else e = 20.0 * dl;
-                    }
-                    e = e - ((p.fl & PF_ACCIDENT) ? 20.0 : 0.0);
-                    if (e < p.wdl) p.wdl = e;
-                }
-                wmin[i] = (!any_exist || p.wdl < wmin[i]) ? p.wdl : wmin[i];
+                const bool grn = ex && (k.light > 0.0);
+                const bool guard = grn && guard_p && (((behind & inf) >> i) & 1u);
+                const double d = raw[i] - 1.0 * k.Vc;                                // delta_l SC:516-520
+                const double dl = d * rVc[i];
+                const double soft = dmax(-20.0 * (double)exp_f32(-4.0 * dl - 4.0), -20.0);
+                double e = (k.Vc < T::wait_thr) ? 0.0 : ((d >= -k.Vc) ? soft : 20.0 * dl);
+                e = e - acc_pen;
+                p.wdl = (guard && e < p.wdl) ? e : p.wdl;
+                wmin[i] = grn ? ((!any_exist || p.wdl < wmin[i]) ? p.wdl : wmin[i]) : wmin[i];
             }
-            any_exist = true;
+            any_exist = any_exist || ex;
         }
 
         // ---- observation row (pedestrian.get_data SC:449-460, delta_l_all SC:508-514)

@@ -22,11 +22,18 @@
 #endif
 #endif
 
+// one out-of-line copy on the device: ~80 integer instructions per block, called from many places
+#ifdef __CUDACC__
+#define MH_PHILOX static __host__ __device__ __noinline__
+#else
+#define MH_PHILOX static inline
+#endif
+
 namespace mhppo {
 
 struct PhiloxBlock { uint32_t w0, w1, w2, w3; };
 
-MH_HD PhiloxBlock philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+MH_PHILOX PhiloxBlock philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
         const uint64_t p0 = (uint64_t)0xD2511F53u * c0;
