@@ -295,13 +295,17 @@ MH_HD void env_step_thread(const EnvArena &a, const EnvConst &c, const RngKey &k
     // ---- cars: load, act (SC:797-802 / C4:791-795 / C42:807-811 / CO:753-755)
     CarR car[MC];
     double prevSc[MC];
+    // running min/max shaping accumulators (possible_accident, error_scenario, Ts): kept in fp32.  They
+    // are stored as fp32 and only ever updated by min/max with a new candidate, and rounding is
+    // monotonic, so min(fp32 old, fp32(candidate)) == fp32(min(old, candidate)) bit for bit.
+    float paf[MC], esf[MC], Tsf[MC];
 #pragma unroll
     for (int i = 0; i < MC; ++i) {
         if (i >= c.nC) continue;
         const float4 ka = a.car_a[(int64_t)i * a.N + n], kb = a.car_b[(int64_t)i * a.N + n];
         CarR &k = car[i];
         k.Vc = (double)ka.x; k.Sc = (double)ka.y; k.light = (double)ka.z; k.Ac = (double)ka.w;
-        k.pa = (double)kb.x; k.es = (double)kb.y; k.Ts = (double)kb.z;
+        paf[i] = kb.x; esf[i] = kb.y; Tsf[i] = kb.z;
         const uint32_t b = f2u(kb.w);
         k.line = (int)(b & 255u); k.exist = (int)((b >> 8) & 1u);
         prevSc[i] = k.Sc;
@@ -368,9 +372,9 @@ MH_HD void env_step_thread(const EnvArena &a, const EnvConst &c, const RngKey &k
     const int ped_o = T::car_w * c.nC + env_w;
     const double time_braking = -(10.0 / (2.0 * c.acc_lo)) + 1.0;                    // SC:580
 
-    double rl[MC], wmin[MC];
+    float rl[MC], wmin[MC];
 #pragma unroll
-    for (int i = 0; i < MC; ++i) { rl[i] = 0.0; wmin[i] = 0.0; }
+    for (int i = 0; i < MC; ++i) { rl[i] = 0.f; wmin[i] = 0.f; }
     bool any_exist = false;
 
     // ---- pedestrians, streamed
@@ -408,8 +412,8 @@ MH_HD void env_step_thread(const EnvArena &a, const EnvConst &c, const RngKey &k
 #pragma unroll
         for (int i = 0; i < MC; ++i)
             if (((lead_ok & behind) >> i) & 1u) { if (car[i].light > 0.0) nwait += 1.0; }
-        const double ts_new = T::naif ? (((wait_t + 10.0 * cross_t) - time_braking) + 1.0)
-                                      : ((((1.0 + nwait) * wait_t + 2.0 * cross_t) - time_braking) + 1.0);
+        const float ts_new = (float)(T::naif ? (((wait_t + 10.0 * cross_t) - time_braking) + 1.0)
+                                             : ((((1.0 + nwait) * wait_t + 2.0 * cross_t) - time_braking) + 1.0));
         // Written branch-free on purpose: lanes (envs) disagree on every one of these conditions, so
         // each pair is evaluated once with selects instead of serialising the sides of the branches.
         uint32_t fl = p.fl;
@@ -430,21 +434,24 @@ MH_HD void env_step_thread(const EnvArena &a, const EnvConst &c, const RngKey &k
             fl = (fl & ~PF_WORST_ACC) | (wa ? PF_WORST_ACC : 0u) | (hit ? PF_ACCIDENT : 0u);
             {                                                                        // SC:187-201
                 const bool slow = k.Vc < 0.05;
-                const double dl = slow ? T::far : wdl * rVc[i];
+                const double dl64 = slow ? T::far : wdl * rVc[i];
+                const float dl = (float)dl64;
                 const bool pos = slow ? (T::far > 0.0) : (wdl > 0.0);
-                const double lin = T::neg_dl ? (-1.0 * dl - 1.0) : (1.0 * dl - 1.0);
-                const double pa = pos ? -(double)exp_f32(-4.0 * dl) : lin;
-                k.pa = (gi && ci) ? dmin(k.pa, pa) : k.pa;
+                // -dl-1 (ST:197, NA:200) cancels near dl = -1: that one difference is formed in fp64
+                const float lin = T::neg_dl ? (float)(-1.0 * dl64 - 1.0) : (1.0f * dl - 1.0f);
+                const float pa = pos ? -exp2f(-4.0f * 1.4426950408889634f * dl) : lin;
+                paf[i] = (gi && ci) ? fminf(paf[i], pa) : paf[i];
             }
-            k.Ts = (gi && bi) ? dmax(ts_new, k.Ts) : k.Ts;                           // SC:207-208
+            Tsf[i] = (gi && bi) ? fmaxf(ts_new, Tsf[i]) : Tsf[i];                    // SC:207-208
             {                                                                        // SC:216-237
                 const bool red = k.light < 0.0, grn = k.light > 0.0;
                 const double gap = p.Spx - k.Sc;
-                const bool use_exp = red ? (k.Ts < 0.0) : (gap > 0.0);
-                const double arg = red ? (4.0 * k.Ts) : (-4.0 * gap);
-                const double lin = red ? (-1.0 * (1.0 + k.Ts)) : (-1.0 * ((1.0 + k.Sc) - p.Spx));
-                const double ne = use_exp ? -(double)exp_f32(arg) : lin;
-                k.es = (gi && (red || grn)) ? dmin(ne, k.es) : k.es;
+                const float gapf = (float)gap;
+                const bool use_exp = red ? (Tsf[i] < 0.f) : (gap > 0.0);
+                const float arg = red ? (4.0f * Tsf[i]) : (-4.0f * gapf);
+                const float lin = red ? (-1.0f * (1.0f + Tsf[i])) : (-1.0f - (float)(k.Sc - p.Spx));
+                const float ne = use_exp ? -exp2f(1.4426950408889634f * arg) : lin;
+                esf[i] = (gi && (red || grn)) ? fminf(ne, esf[i]) : esf[i];
                 if (!T::naif) fl |= (gi && red && ci && bi) ? PF_NOT_WAITING : 0u;
             }
         }
@@ -453,12 +460,12 @@ MH_HD void env_step_thread(const EnvArena &a, const EnvConst &c, const RngKey &k
 #pragma unroll
             for (int i = 0; i < MC; ++i) {
                 if (i >= c.nlead) continue;
-                double r = car[i].pa + car[i].es;
+                float r = paf[i] + esf[i];
                 if (T::danger_sign != 0) {
-                    const double extra = (0.5 * green * (double)(car[i].light < 0.0)) * (double)(car[i].Ts > 0.0);
+                    const float extra = ((car[i].light < 0.0) && (Tsf[i] > 0.f)) ? 0.5f * (float)green : 0.f;
                     r = (T::danger_sign > 0) ? (r + extra) : (r - extra);
                 }
-                if (T::scal && !car[i].exist) r = 0.0;
+                if (T::scal && !car[i].exist) r = 0.f;
                 rl[i] += r;
             }
         }
@@ -469,7 +476,8 @@ MH_HD void env_step_thread(const EnvArena &a, const EnvConst &c, const RngKey &k
         {
             const bool ex = (p.fl & PF_EXIST) != 0;
             const bool guard_p = ex && !left && (p.fl & PF_CROSSING);
-            const double acc_pen = (p.fl & PF_ACCIDENT) ? 20.0 : 0.0;
+            const float acc_pen = (p.fl & PF_ACCIDENT) ? 20.0f : 0.0f;
+            float pwdl = (float)p.wdl;
 #pragma unroll
             for (int i = 0; i < MC; ++i) {
                 if (i >= c.nlead) continue;
@@ -477,13 +485,14 @@ MH_HD void env_step_thread(const EnvArena &a, const EnvConst &c, const RngKey &k
                 const bool grn = ex && (k.light > 0.0);
                 const bool guard = grn && guard_p && (((behind & inf) >> i) & 1u);
                 const double d = raw[i] - 1.0 * k.Vc;                                // delta_l SC:516-520
-                const double dl = d * rVc[i];
-                const double soft = dmax(-20.0 * (double)exp_f32(-4.0 * dl - 4.0), -20.0);
-                double e = (k.Vc < T::wait_thr) ? 0.0 : ((d >= -k.Vc) ? soft : 20.0 * dl);
+                const float dl = (float)(d * rVc[i]);
+                const float soft = fmaxf(-20.0f * exp2f(1.4426950408889634f * (-4.0f * dl - 4.0f)), -20.0f);
+                float e = (k.Vc < T::wait_thr) ? 0.0f : ((d >= -k.Vc) ? soft : 20.0f * dl);
                 e = e - acc_pen;
-                p.wdl = (guard && e < p.wdl) ? e : p.wdl;
-                wmin[i] = grn ? ((!any_exist || p.wdl < wmin[i]) ? p.wdl : wmin[i]) : wmin[i];
+                pwdl = (guard && e < pwdl) ? e : pwdl;
+                wmin[i] = grn ? ((!any_exist || pwdl < wmin[i]) ? pwdl : wmin[i]) : wmin[i];
             }
+            p.wdl = (double)pwdl;
             any_exist = any_exist || ex;
         }
 
@@ -526,9 +535,9 @@ MH_HD void env_step_thread(const EnvArena &a, const EnvConst &c, const RngKey &k
             if (i >= c.nlead) continue;
             const double d = car[i].Vc - 10.0;
             double r = (-10.0 * (d * d)) / 100.0;                                    // SC:657-665
-            if ((car[i].light > 0.0) && any_exist) r += wmin[i];
+            if ((car[i].light > 0.0) && any_exist) r += (double)wmin[i];
             if (rp) rp[(int64_t)i * io.rewards.comp_stride] = (float)r;
-            if (lp) lp[(int64_t)i * io.reward_light.comp_stride] = (float)rl[i];
+            if (lp) lp[(int64_t)i * io.reward_light.comp_stride] = rl[i];
         }
         if (io.done) io.done[n] = done ? 1 : 0;
     }
@@ -563,7 +572,7 @@ MH_HD void env_step_thread(const EnvArena &a, const EnvConst &c, const RngKey &k
         if (i >= c.nC) continue;
         const CarR &k = car[i];
         a.car_a[(int64_t)i * a.N + n] = make_float4((float)k.Vc, (float)k.Sc, (float)k.light, (float)k.Ac);
-        a.car_b[(int64_t)i * a.N + n] = make_float4((float)k.pa, (float)k.es, (float)k.Ts,
+        a.car_b[(int64_t)i * a.N + n] = make_float4(paf[i], esf[i], Tsf[i],
                                                     u2f(((uint32_t)k.line & 255u) | (((uint32_t)k.exist & 1u) << 8)));
     }
     a.env_e[n] = make_float4(ee.x, ee.y, u2f(pack_env_word(step, ped_traffic, car_traffic)), u2f(rng.ctr));
