@@ -1,0 +1,131 @@
+"""Pins oracle/ppo_oracle.py against the UNMODIFIED reference PPO classes (build container only)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import refdriver as rd
+
+pytestmark = pytest.mark.skipif(not rd.available(), reason="reference sources not present")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+
+
+@pytest.fixture(scope="module")
+def ref():
+    import refppo
+    ns = refppo.load_namespace()
+    algo, env = refppo.make_algo(ns, "coop_scalable", 4, 3, 2, seed=1)
+    return ns, algo, env
+
+
+def _sd(net):
+    return {k: v.detach().clone() for k, v in net.state_dict().items()}
+
+
+def test_feature_builders_match_reference(ref):
+    from oracle import ppo_oracle as PO
+    ns, algo, env = ref
+    r = algo.rollout
+    rng = np.random.default_rng(0)
+    for ep in range(6):
+        env._mh_rng.set_stream(50 + ep, ep, 0)
+        state, _ = env.reset()
+        for t in range(80):
+            obs = np.concatenate([state[k].ravel() for k in sorted(state)])
+            if t % 7 == 0:
+                for i in range(4):
+                    assert r.closest_ped_d(obs, i) == PO.closest_ped_d(obs[None], i, 3, 2)[0]
+                    for p in range(3):
+                        f_ref, ex_ref = r.obs_car_ped(obs, i, p)
+                        f, ex = PO.obs_car_ped(obs[None], i, p, 3, 2)
+                        np.testing.assert_allclose(f[0], np.asarray(f_ref, np.float32), rtol=1e-6, atol=1e-6)
+                        assert ex[0] == ex_ref
+                        d_ref, _ = r.obs_car_ped_d(obs, i, p)
+                        d, _ = PO.obs_car_ped_d(obs[None], i, p, 3, 2)
+                        np.testing.assert_allclose(d[0], np.asarray(d_ref, np.float32), rtol=1e-6, atol=1e-6)
+            a = rd.random_actions(rng, "coop_scalable", 4, 2, 1)[0]
+            state, *_ = env.step(a)
+
+
+def test_mlp_forward_matches_reference_on_shipped_checkpoints(ref):
+    from oracle import ppo_oracle as PO
+    ns, algo, env = ref
+    wdir = os.path.join(rd.REF_ROOT, "load_model", "weights")
+    x13 = torch.randn(64, 13, generator=torch.Generator().manual_seed(0))
+    for name, mt in (("cross", 1), ("wait", 1)):
+        sd = torch.load(os.path.join(wdir, "pappo-scalable-coop-%s-111-actor-step-1000.pth" % name))
+        net = ns["Model_PPO"](13, 1, mt, mean=-1.0, std=3.0)
+        net.load_state_dict(sd)
+        torch.testing.assert_close(net(x13), PO.mlp_forward(sd, x13, mt), rtol=1e-6, atol=1e-6)
+    sd = torch.load(os.path.join(wdir, "pappo-scalable-coop-choice-111-actor-step-1000.pth"))
+    net = ns["Model_PPO"](18, 2, 2)
+    net.load_state_dict(sd)
+    x18 = torch.randn(64, 18, generator=torch.Generator().manual_seed(1))
+    got = PO.mlp_forward(sd, x18, 2)
+    torch.testing.assert_close(torch.stack([net(x18[i:i + 1]) for i in range(64)]), got, rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("kind", ["c", "d"])
+def test_train_step_matches_reference(ref, kind):
+    from oracle import ppo_oracle as PO
+    ns, algo, env = ref
+    g = torch.Generator().manual_seed(3)
+    M, n_in = (257, 13) if kind == "c" else (61, 30)
+    states = torch.randn(M, n_in, generator=g).numpy()
+    rtgs = torch.randn(M, generator=g) * 5 - 3
+    if kind == "c":
+        actor_r, critic_r = algo.actor_net_cross, algo.critic_net_cross
+        opt_a, opt_c = algo.optimizer_actor_cross, algo.optimizer_critic_cross
+        actions = (torch.randn(M, 1, generator=g) * 2 - 1).numpy()
+        logp_old = (-torch.rand(M, generator=g) * 3).double().numpy()
+        actor_o, critic_o = PO.Net(13, 1, 1), PO.Net(13, 1, 0)
+        step_ref, step_o = algo.train_model_c, PO.train_step_c
+        cov = algo.cov_mat
+    else:
+        actor_r, critic_r = algo.actor_net_choice, algo.critic_net_choice
+        opt_a, opt_c = algo.optimizer_actor_choice, algo.optimizer_critic_choice
+        actions = torch.randint(0, 2, (M, 1), generator=g).double().numpy()
+        logp_old = (-torch.rand(M, generator=g) * 1.5).float().numpy()
+        actor_o, critic_o = PO.Net(30, 2, 2), PO.Net(30, 1, 0)
+        step_ref, step_o = algo.train_model_d, PO.train_step_d
+        cov = algo.cov_mat_d
+    actor_o.load_state_dict(_sd(actor_r)); critic_o.load_state_dict(_sd(critic_r))
+    oa = torch.optim.Adam(actor_o.parameters(), 3e-4); oc = torch.optim.Adam(critic_o.parameters(), 1e-3)
+    for epoch in range(4):
+        step_ref(actor_r, critic_r, opt_a, opt_c, states, actions, logp_old, rtgs, cov)
+        step_o(actor_o, critic_o, oa, oc, states, actions, logp_old, rtgs)
+    for (k, a), (_, b) in zip(list(actor_r.state_dict().items()) + list(critic_r.state_dict().items()),
+                              list(actor_o.state_dict().items()) + list(critic_o.state_dict().items())):
+        torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-7, msg=k)
+
+
+def test_rollout_episode_matches_reference(ref):
+    """Whole-episode integration: reference Env_rollout.iterations_rand (noise injected) vs the vectorised
+    oracle pipeline on the same streams: buffers, routing quirk (PY:491), episodic choice reward, RTG."""
+    import ref_rollout
+    from oracle import oracle as O
+    from oracle import ppo_oracle as PO
+    ns, algo, env = ref
+    sds = [_sd(n) for n in (algo.actor_net_cross, algo.actor_net_wait, algo.actor_net_choice)]
+    for ep, (seed, env_id) in enumerate([(777, 5), (778, 9), (901, 123), (5, 1), (6, 2), (7, 3)]):
+        want = ref_rollout.reference_episode(ns, algo, env, seed, env_id)
+        venv = O.OracleVecEnv("coop_scalable", 1, 4, 3, 2, seed=seed, env_id0=env_id, store_f32=False, n_threads=1)
+        b = PO.rollout_episode(venv, *sds, seed, [env_id], 3, 2)
+        np.testing.assert_array_equal(b["exist"][:, 0], want["car_exist"])
+        for name, r in (("cross", 0), ("wait", 1)):
+            cars = [i for i in range(4) if b["route"][i, 0] == r]
+            obs = np.concatenate([b["obs_c"][:, i, 0] for i in cars]) if cars else np.zeros((0, 13), np.float32)
+            np.testing.assert_allclose(obs, want["obs_" + name], rtol=2e-5, atol=2e-5)
+            for key, mine in (("acts", "act"), ("logp", "logp"), ("rews", "rew")):
+                got = np.concatenate([b[mine][:, i, 0] for i in cars]) if cars else np.zeros(0)
+                np.testing.assert_allclose(got, want[key + "_" + name], rtol=2e-5, atol=2e-5, err_msg="%s %s ep %d" % (key, name, ep))
+            rtg = np.concatenate([PO.reward_to_go(b["rew"][:, i, 0]) for i in cars]) if cars else np.zeros(0)
+            np.testing.assert_allclose(rtg, want["rtg_" + name], rtol=2e-5, atol=2e-5)
+        cars = [i for i in range(4) if b["exist"][i, 0]]
+        np.testing.assert_allclose(np.stack([b["obs_d"][i, 0] for i in cars]), want["obs_choice"], rtol=1e-5, atol=1e-5)
+        np.testing.assert_array_equal(np.array([b["act_d"][i, 0] for i in cars]), want["acts_choice"])
+        np.testing.assert_allclose(np.array([b["logp_d"][i, 0] for i in cars]), want["logp_choice"], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(np.array([b["rew_d"][i, 0] for i in cars]), want["rews_choice"], rtol=1e-6, atol=1e-9)
