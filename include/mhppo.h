@@ -121,6 +121,62 @@ int64_t mhppo_env_state_bytes_per_env(void *handle);
 /* number of kernel launches this library has issued in this process (bench.py "gpu_launches") */
 int64_t mhppo_launch_count(void);
 
+/* =====================================================================================================
+ * PPO side: Model_PPO / Env_rollout / Algo_PPO of Coop-MH-PPO-scalable.py (scalable env class).
+ *
+ * Networks (Model_PPO, PY:42-93): in -> 32 -> 64 -> 32 -> out, ReLU; heads: 0 linear (critics),
+ * 1 3*tanh(z)-1 (cross / wait actors, PY:1044-1045), 2 softmax over two logits (choice actor).
+ * Flat parameter layout shared by every kernel (host packs/unpacks state_dicts):
+ *   W1t[KP][32] b1[32] W2t[32][64] b2[64] W3t[64][32] b3[32] W4t[32][4] b4[4]   (weights transposed, zero padded;
+ *   KP = mhppo_net_padded_in(n_in)).
+ *
+ * Buffers (device, fp32, env index innermost): obs [n_obs][N] (the env's component-major observation);
+ * action_d int8 [C*P][N]; light [C][N]; sample s = (t*C + car)*N + env, S = T*C*N: obs_c [13][S], act, logp,
+ * rew, rl, rtg, V [S]; choice sample m = car*N + env, M = C*N: obs_d [D][M], act_d, logp_d, rew_d [M];
+ * route int8 [C][N] (0 cross, 1 wait, -1 car absent; PY:489-502).  C = 2*nb_lines, D = 2+6*(C-1)+10. */
+typedef struct mhppo_rollout_cfg {
+    int32_t nb_ped, nb_lines;
+    int32_t T;            /* steps per episode (80) */
+    int32_t reserved;
+    int64_t n_envs;
+    uint64_t seed;        /* same Philox key as the env */
+    int64_t env_id0;
+} mhppo_rollout_cfg;
+
+int mhppo_net_padded_in(int32_t n_in);
+int mhppo_net_param_count(int32_t n_in);
+
+/* episode-start discrete decision of Env_rollout.iterations_rand (PY:400-428): obs_car_ped_d (PY:574-611) ->
+ * choice net -> Categorical sample per (car, ped); closest_ped_d (PY:614-627) picks the car's light */
+int mhppo_choice_act(const mhppo_rollout_cfg *cfg, const float *obs_dev, const float *net_choice_dev, uint32_t iteration,
+                     int8_t *action_d_dev, float *light_dev, float *obs_d_dev, float *act_d_dev, float *logp_d_dev,
+                     void *stream);
+/* per-step continuous action (PY:434-453): obs_car_ped (PY:541-572) -> cross|wait net per pair -> min over existing
+ * pedestrians -> N(mean, 0.5) sample + log-prob; writes the env's action buffer [2C][N] and the rollout buffers */
+int mhppo_policy_act(const mhppo_rollout_cfg *cfg, const float *obs_dev, const float *net_cross_dev, const float *net_wait_dev,
+                     const int8_t *action_d_dev, const float *light_dev, int32_t t, uint32_t iteration, float *actions_dev,
+                     float *obs_c_dev, float *act_dev, float *logp_dev, void *stream);
+/* Env_rollout.futur_rewards (PY:658-684): reverse scan rtg_t = r_t + gamma*rtg_{t+1}, zero bootstrap; and the
+ * episodic choice reward min(0, min_t reward_light) (PY:461).  CN = C*N */
+int mhppo_returns(const float *rew_dev, const float *rl_dev, int32_t T, int64_t CN, double gamma, float *rtg_dev,
+                  float *rew_d_dev, void *stream);
+
+/* Algo_PPO.train_model_c / train_model_d (PY:778-851), one epoch = value_stats -> [all-reduce] -> ppo_grad (actor),
+ * ppo_grad (critic) -> [all-reduce] -> adam.  x: features [D][S]; route/want select the samples (route NULL = all). */
+int64_t mhppo_update_workspace_bytes(int32_t n_in);
+int mhppo_value_stats(int32_t n_in, const float *x_dev, int32_t D, int64_t S, const int8_t *route_dev, int64_t CN, int32_t want,
+                      const float *critic_dev, const float *rtg_dev, float *V_dev, double *stats3_dev, void *workspace_dev,
+                      void *stream);
+/* head: 0 critic MSE, 1 Gaussian actor clipped surrogate, 2 categorical actor (with the (M,M) broadcast of PY:834-842,
+ * f0/f1 = fraction of selected samples whose action is 0/1).  grad_dev: flat gradient, loss_dev: fp64 scalar. */
+int mhppo_ppo_grad(int32_t n_in, int32_t head, const float *x_dev, int32_t D, int64_t S, const int8_t *route_dev, int64_t CN,
+                   int32_t want, const float *net_dev, const float *act_dev, const float *logp_old_dev, const float *rtg_dev,
+                   const float *V_dev, float adv_mean, float adv_inv_std, float inv_n, float f0, float f1, float *grad_dev,
+                   double *loss_dev, void *workspace_dev, void *stream);
+/* torch.optim.Adam defaults (PY:719-724); step counts from 1; grad_scale multiplies the gradient first */
+int mhppo_adam(float *param_dev, const float *grad_dev, float *m_dev, float *v_dev, int32_t n, float lr, float beta1,
+               float beta2, float eps, int32_t step, float grad_scale, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

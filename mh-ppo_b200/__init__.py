@@ -7,5 +7,9 @@ raises.
 """
 from ._lib import lib, LibraryMissing, MhppoError, launch_count  # noqa: F401
 from .vec_env import VecCrosswalkEnv, make, ENV_IDS  # noqa: F401
+from .policy import Model_PPO, Adam  # noqa: F401
+from .rollout import Env_rollout  # noqa: F401
+from .ppo import Algo_PPO  # noqa: F401
 
-__all__ = ["VecCrosswalkEnv", "make", "ENV_IDS", "lib", "LibraryMissing", "MhppoError", "launch_count"]
+__all__ = ["VecCrosswalkEnv", "make", "ENV_IDS", "Model_PPO", "Adam", "Env_rollout", "Algo_PPO", "lib", "LibraryMissing",
+           "MhppoError", "launch_count"]

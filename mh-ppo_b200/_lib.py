@@ -27,6 +27,11 @@ class EnvDims(C.Structure):
                 ("n_ped", C.c_int32), ("done_step", C.c_int32), ("reserved", C.c_int32 * 2)]
 
 
+class RolloutCfg(C.Structure):
+    _fields_ = [("nb_ped", C.c_int32), ("nb_lines", C.c_int32), ("T", C.c_int32), ("reserved", C.c_int32),
+                ("n_envs", C.c_int64), ("seed", C.c_uint64), ("env_id0", C.c_int64)]
+
+
 class View(C.Structure):
     _fields_ = [("ptr", C.c_void_p), ("env_stride", C.c_int64), ("comp_stride", C.c_int64)]
 
@@ -48,6 +53,16 @@ SYMBOLS = {
     "mhppo_env_import_state": (C.c_int, [C.c_void_p] * 8),
     "mhppo_env_state_bytes_per_env": (C.c_int64, [C.c_void_p]),
     "mhppo_launch_count": (C.c_int64, []),
+    "mhppo_net_padded_in": (C.c_int, [C.c_int32]),
+    "mhppo_net_param_count": (C.c_int, [C.c_int32]),
+    "mhppo_choice_act": (C.c_int, [C.POINTER(RolloutCfg), C.c_void_p, C.c_void_p, C.c_uint32] + [C.c_void_p] * 6),
+    "mhppo_policy_act": (C.c_int, [C.POINTER(RolloutCfg)] + [C.c_void_p] * 5 + [C.c_int32, C.c_uint32] + [C.c_void_p] * 5),
+    "mhppo_returns": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mhppo_update_workspace_bytes": (C.c_int64, [C.c_int32]),
+    "mhppo_value_stats": (C.c_int, [C.c_int32, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_int64, C.c_int32] + [C.c_void_p] * 6),
+    "mhppo_ppo_grad": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_int64, C.c_int32]
+                       + [C.c_void_p] * 5 + [C.c_float] * 5 + [C.c_void_p] * 4),
+    "mhppo_adam": (C.c_int, [C.c_void_p] * 4 + [C.c_int32] + [C.c_float] * 4 + [C.c_int32, C.c_float, C.c_void_p]),
 }
 
 _lib = None

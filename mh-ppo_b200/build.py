@@ -23,7 +23,8 @@ FLAGS = {"env": ["-fmad=false"], "default": []}
 
 def _flags_for(src):
     base = os.path.basename(src)
-    return FLAGS["env"] if base.startswith("env_") or base == "mhppo_api.cu" else FLAGS["default"]
+    # ppo_*.cu: the feature builders restate numpy fp32 mul/add (no contraction); the MLP uses explicit fmaf
+    return FLAGS["env"] if base.startswith(("env_", "ppo_")) or base == "mhppo_api.cu" else FLAGS["default"]
 
 
 def _deps():

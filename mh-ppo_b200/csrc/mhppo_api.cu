@@ -17,6 +17,8 @@ static thread_local std::string g_err;
 static std::atomic<int64_t> g_launches{0};
 
 static int fail(int code, const std::string &msg) { g_err = msg; return code; }
+int api_fail(int code, const std::string &msg) { return fail(code, msg); }   // shared with ppo_api.cu
+void api_count_launch() { g_launches.fetch_add(1); }
 static int cuda_fail(cudaError_t e, const char *what) {
     g_err = std::string(what) + ": " + cudaGetErrorString(e);
     return MHPPO_ECUDA;

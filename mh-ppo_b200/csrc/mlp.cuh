@@ -1,0 +1,80 @@
+// mlp.cuh -- the policy / value networks of MH-PPO on the SM (Model_PPO, PY:42-93).
+//
+// Every net is the same 4-layer MLP  in -> 32 -> 64 -> 32 -> out  with ReLU, and one of three heads:
+// type 0 linear (critics), type 1 `std*tanh(z)+mean` (Gaussian mean of the cross / wait actors,
+// std = 3, mean = -1 from PY:1044-1045), type 2 softmax over the two logits (choice actor).
+//
+// Flat parameter layout used by every kernel and by Adam (host packs/unpacks state_dicts,
+// mh-ppo_b200/policy.py):  W1t[KP][32] b1[32] W2t[32][64] b2[64] W3t[64][32] b3[32] W4t[32][4] b4[4]
+// -- weights TRANSPOSED ([in][out], out fastest) so a thread that owns one sample streams the
+// input index and reads 4 output weights per 128-bit shared-memory broadcast; the input width is
+// zero-padded to KP (13 -> 16, 18/30 -> 32, 54 -> 56) and the output width to 4.
+//
+// Execution model of all MLP kernels here: one thread owns one sample; activations live in shared
+// memory as [sample][feature] rows with an odd stride (conflict-free for lane = sample), weights
+// are staged once per CTA.  The 13..64-wide layers are far too small for a 128xN tcgen05 tile to pay
+// off without batching samples across the CTA -- that tensor-core formulation is the planned next
+// step (DESIGN.md "Next"); this version is exact fp32 FFMA, which is what the 1e-5 loss parity
+// bar (north_star) is checked with.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mhppo {
+
+constexpr int H1 = 32, H2 = 64, H3 = 32, OP = 4;
+constexpr int kMlpBlock = 128;
+
+__host__ __device__ constexpr int net_params(int KP) { return KP * H1 + H1 + H1 * H2 + H2 + H2 * H3 + H3 + H3 * OP + OP; }
+__host__ __device__ constexpr int off_b1(int KP) { return KP * H1; }
+__host__ __device__ constexpr int off_w2(int KP) { return off_b1(KP) + H1; }
+__host__ __device__ constexpr int off_b2(int KP) { return off_w2(KP) + H1 * H2; }
+__host__ __device__ constexpr int off_w3(int KP) { return off_b2(KP) + H2; }
+__host__ __device__ constexpr int off_b3(int KP) { return off_w3(KP) + H2 * H3; }
+__host__ __device__ constexpr int off_w4(int KP) { return off_b3(KP) + H3; }
+__host__ __device__ constexpr int off_b4(int KP) { return off_w4(KP) + H3 * OP; }
+
+// row strides of the activation tiles (odd => lane = sample is bank-conflict free)
+template <int KP> struct Strides { static constexpr int X = KP + 1, A1 = H1 + 1, A2 = H2 + 1, A3 = H3 + 1; };
+
+// one dense layer for the sample owned by this thread: out[j] = b[j] + sum_k in[k] * Wt[k][j]
+// `in` is this thread's row in shared memory; Wt/b are the CTA's staged weights.
+template <int K, int J, bool RELU>
+__device__ __forceinline__ void dense_fwd(const float *__restrict__ in, const float *__restrict__ Wt, const float *__restrict__ b,
+                                          float *__restrict__ out) {
+    float acc[J];
+#pragma unroll
+    for (int j = 0; j < J; ++j) acc[j] = b[j];
+#pragma unroll 2
+    for (int k = 0; k < K; ++k) {
+        const float a = in[k];
+        const float4 *w = reinterpret_cast<const float4 *>(Wt + k * J);
+#pragma unroll
+        for (int j4 = 0; j4 < J / 4; ++j4) {
+            const float4 ww = w[j4];
+            acc[4 * j4 + 0] = fmaf(a, ww.x, acc[4 * j4 + 0]); acc[4 * j4 + 1] = fmaf(a, ww.y, acc[4 * j4 + 1]);
+            acc[4 * j4 + 2] = fmaf(a, ww.z, acc[4 * j4 + 2]); acc[4 * j4 + 3] = fmaf(a, ww.w, acc[4 * j4 + 3]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < J; ++j) out[j] = RELU ? fmaxf(acc[j], 0.f) : acc[j];
+}
+
+// whole forward pass for this thread's sample; x/a1/a2/a3 are its rows; returns the 4 (padded) raw outputs
+template <int KP>
+__device__ __forceinline__ float4 mlp_fwd_rows(const float *__restrict__ sw, const float *x, float *a1, float *a2, float *a3) {
+    dense_fwd<KP, H1, true>(x, sw, sw + off_b1(KP), a1);
+    dense_fwd<H1, H2, true>(a1, sw + off_w2(KP), sw + off_b2(KP), a2);
+    dense_fwd<H2, H3, true>(a2, sw + off_w3(KP), sw + off_b3(KP), a3);
+    float o[OP];
+    dense_fwd<H3, OP, false>(a3, sw + off_w4(KP), sw + off_b4(KP), o);
+    return make_float4(o[0], o[1], o[2], o[3]);
+}
+
+// stage a net's flat parameters into shared memory (whole CTA)
+template <int KP>
+__device__ __forceinline__ void stage_net(float *sw, const float *__restrict__ g) {
+    for (int i = threadIdx.x; i < net_params(KP); i += blockDim.x) sw[i] = g[i];
+}
+
+}  // namespace mhppo

@@ -1,0 +1,165 @@
+// ppo_api.cu -- host side of the PPO part of the C ABI (include/mhppo.h).
+#include <cmath>
+#include <cstdio>
+#include <string>
+
+#include "../../include/mhppo.h"
+#include "ppo_rollout.cuh"
+#include "ppo_update.cuh"
+
+namespace mhppo {
+int api_fail(int code, const std::string &msg);      // mhppo_api.cu
+void api_count_launch();
+static int ck(cudaError_t e, const char *what) {
+    if (e == cudaSuccess) return 0;
+    return api_fail(MHPPO_ECUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+static int padded_in(int n_in) { return n_in <= 16 ? 16 : (n_in <= 32 ? 32 : (n_in <= 56 ? 56 : -1)); }
+constexpr int kUpdateGrid = 296;     // persistent CTAs of the update kernels: 2 per SM x 148 SMs
+
+template <int KP> static size_t smem_fwd(int nets) {
+    typedef Strides<KP> St;
+    const int ROW = (St::X + St::A1 + St::A2 + St::A3) | 1;
+    return sizeof(float) * ((size_t)nets * ((net_params(KP) + 3) & ~3) + (size_t)kMlpBlock * ROW);
+}
+template <int KP> static size_t smem_grad() {
+    typedef Strides<KP> St;
+    const int ROW = (St::X + St::A1 + St::A2 + St::A3 + OP) | 1;
+    return sizeof(float) * ((size_t)((net_params(KP) + 3) & ~3) + H2 * H1 + H3 * H2 + OP * H3 + (size_t)kMlpBlock * ROW);
+}
+static RolloutDims dims_of(const mhppo_rollout_cfg *c) {
+    RolloutDims d;
+    d.P = c->nb_ped; d.L = c->nb_lines; d.C = 2 * c->nb_lines; d.n_obs = 7 * d.C + 4 + 9 * d.P; d.D = 2 + 6 * (d.C - 1) + 10;
+    d.N = c->n_envs; d.k0 = (uint32_t)c->seed; d.k1 = (uint32_t)(c->seed >> 32); d.env_id0 = c->env_id0;
+    return d;
+}
+struct Workspace { float *gpartial; double *lpartial; double *spartial; };
+static Workspace carve(void *ws, int KP) {
+    Workspace w;
+    w.gpartial = (float *)ws;
+    size_t off = sizeof(float) * (size_t)kUpdateGrid * net_params(KP);
+    off = (off + 15) & ~(size_t)15;
+    w.lpartial = (double *)((char *)ws + off);
+    w.spartial = w.lpartial + kUpdateGrid;
+    return w;
+}
+}  // namespace mhppo
+
+using namespace mhppo;
+
+#define SET_SMEM(kernel, bytes)                                                                                      \
+    do {                                                                                                             \
+        int rc_ = ck(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)), #kernel); \
+        if (rc_) return rc_;                                                                                         \
+    } while (0)
+
+template <int KP>
+static int launch_grad(int head, const SampleSet &ss, const float *net, const LossArgs &la, const Workspace &w, cudaStream_t s) {
+    const size_t sm = smem_grad<KP>();
+    if (head == 0) { SET_SMEM((k_ppo_grad<KP, 0>), sm); k_ppo_grad<KP, 0><<<kUpdateGrid, kMlpBlock, sm, s>>>(ss, net, la, w.gpartial, w.lpartial); }
+    else if (head == 1) { SET_SMEM((k_ppo_grad<KP, 1>), sm); k_ppo_grad<KP, 1><<<kUpdateGrid, kMlpBlock, sm, s>>>(ss, net, la, w.gpartial, w.lpartial); }
+    else { SET_SMEM((k_ppo_grad<KP, 2>), sm); k_ppo_grad<KP, 2><<<kUpdateGrid, kMlpBlock, sm, s>>>(ss, net, la, w.gpartial, w.lpartial); }
+    api_count_launch();
+    return ck(cudaGetLastError(), "k_ppo_grad");
+}
+
+extern "C" {
+
+int mhppo_net_padded_in(int32_t n_in) { return padded_in(n_in); }
+int mhppo_net_param_count(int32_t n_in) { const int kp = padded_in(n_in); return kp < 0 ? -1 : net_params(kp); }
+
+int mhppo_choice_act(const mhppo_rollout_cfg *cfg, const float *obs, const float *net, uint32_t iteration, int8_t *action_d,
+                     float *light, float *obs_d, float *act_d, float *logp_d, void *stream) {
+    if (!cfg || !obs || !net || !action_d || !light || !obs_d || !act_d || !logp_d) return api_fail(MHPPO_EINVAL, "null argument");
+    const RolloutDims d = dims_of(cfg);
+    const int kp = padded_in(d.D);
+    if (kp < 0) return api_fail(MHPPO_EUNSUPPORTED, "choice features wider than 56 (nb_lines > 4)");
+    const dim3 grid((unsigned)((d.N + kMlpBlock - 1) / kMlpBlock), (unsigned)d.C);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (kp == 16) { SET_SMEM(k_choice_act<16>, smem_fwd<16>(1)); k_choice_act<16><<<grid, kMlpBlock, smem_fwd<16>(1), s>>>(d, obs, net, iteration, action_d, light, obs_d, act_d, logp_d); }
+    else if (kp == 32) { SET_SMEM(k_choice_act<32>, smem_fwd<32>(1)); k_choice_act<32><<<grid, kMlpBlock, smem_fwd<32>(1), s>>>(d, obs, net, iteration, action_d, light, obs_d, act_d, logp_d); }
+    else { SET_SMEM(k_choice_act<56>, smem_fwd<56>(1)); k_choice_act<56><<<grid, kMlpBlock, smem_fwd<56>(1), s>>>(d, obs, net, iteration, action_d, light, obs_d, act_d, logp_d); }
+    api_count_launch();
+    return ck(cudaGetLastError(), "k_choice_act");
+}
+
+int mhppo_policy_act(const mhppo_rollout_cfg *cfg, const float *obs, const float *net_cross, const float *net_wait,
+                     const int8_t *action_d, const float *light, int32_t t, uint32_t iteration, float *actions, float *obs_c,
+                     float *act, float *logp, void *stream) {
+    if (!cfg || !obs || !net_cross || !net_wait || !action_d || !light || !actions || !obs_c || !act || !logp)
+        return api_fail(MHPPO_EINVAL, "null argument");
+    const RolloutDims d = dims_of(cfg);
+    ActIO io; io.obs = obs; io.action_d = action_d; io.light = light; io.actions = actions; io.obs_c = obs_c; io.act = act;
+    io.logp = logp; io.t = t; io.T = cfg->T; io.iteration = iteration;
+    const dim3 grid((unsigned)((d.N + kMlpBlock - 1) / kMlpBlock), (unsigned)d.C);
+    SET_SMEM(k_policy_act, smem_fwd<16>(2));
+    k_policy_act<<<grid, kMlpBlock, smem_fwd<16>(2), (cudaStream_t)stream>>>(d, net_cross, net_wait, io);
+    api_count_launch();
+    return ck(cudaGetLastError(), "k_policy_act");
+}
+
+int mhppo_returns(const float *rew, const float *rl, int32_t T, int64_t CN, double gamma, float *rtg, float *rew_d, void *stream) {
+    if (!rew || !rl || !rtg || !rew_d) return api_fail(MHPPO_EINVAL, "null argument");
+    k_returns<<<(unsigned)((CN + 255) / 256), 256, 0, (cudaStream_t)stream>>>(rew, rl, T, CN, gamma, rtg, rew_d);
+    api_count_launch();
+    return ck(cudaGetLastError(), "k_returns");
+}
+
+int64_t mhppo_update_workspace_bytes(int32_t n_in) {
+    const int kp = padded_in(n_in);
+    if (kp < 0) return -1;
+    return (int64_t)(sizeof(float) * (size_t)kUpdateGrid * net_params(kp) + 16 + sizeof(double) * (size_t)kUpdateGrid * 4);
+}
+
+int mhppo_value_stats(int32_t n_in, const float *x, int32_t D, int64_t S, const int8_t *route, int64_t CN, int32_t want,
+                      const float *critic, const float *rtg, float *V, double *stats3, void *workspace, void *stream) {
+    if (!x || !critic || !rtg || !V || !stats3 || !workspace) return api_fail(MHPPO_EINVAL, "null argument");
+    const int kp = padded_in(n_in);
+    if (kp < 0 || D > kp) return api_fail(MHPPO_EUNSUPPORTED, "unsupported input width");
+    SampleSet ss; ss.x = x; ss.D = D; ss.S = S; ss.route = route; ss.CN = CN > 0 ? CN : 1; ss.want = want;
+    const Workspace w = carve(workspace, kp);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (kp == 16) { SET_SMEM(k_value_stats<16>, smem_fwd<16>(1)); k_value_stats<16><<<kUpdateGrid, kMlpBlock, smem_fwd<16>(1), s>>>(ss, critic, rtg, V, w.spartial); }
+    else if (kp == 32) { SET_SMEM(k_value_stats<32>, smem_fwd<32>(1)); k_value_stats<32><<<kUpdateGrid, kMlpBlock, smem_fwd<32>(1), s>>>(ss, critic, rtg, V, w.spartial); }
+    else { SET_SMEM(k_value_stats<56>, smem_fwd<56>(1)); k_value_stats<56><<<kUpdateGrid, kMlpBlock, smem_fwd<56>(1), s>>>(ss, critic, rtg, V, w.spartial); }
+    api_count_launch();
+    int rc = ck(cudaGetLastError(), "k_value_stats");
+    if (rc) return rc;
+    k_reduce_scalars<<<1, 32, 0, s>>>(w.spartial, kUpdateGrid, 3, stats3);
+    api_count_launch();
+    return ck(cudaGetLastError(), "k_reduce_scalars");
+}
+
+int mhppo_ppo_grad(int32_t n_in, int32_t head, const float *x, int32_t D, int64_t S, const int8_t *route, int64_t CN, int32_t want,
+                   const float *net, const float *act, const float *logp_old, const float *rtg, const float *V, float adv_mean,
+                   float adv_inv_std, float inv_n, float f0, float f1, float *grad, double *loss, void *workspace, void *stream) {
+    if (!x || !net || !rtg || !grad || !loss || !workspace) return api_fail(MHPPO_EINVAL, "null argument");
+    if (head < 0 || head > 2) return api_fail(MHPPO_EINVAL, "head must be 0, 1 or 2");
+    if (head != 0 && (!act || !logp_old || !V)) return api_fail(MHPPO_EINVAL, "actor heads need act, logp_old and V");
+    const int kp = padded_in(n_in);
+    if (kp < 0 || D > kp) return api_fail(MHPPO_EUNSUPPORTED, "unsupported input width");
+    SampleSet ss; ss.x = x; ss.D = D; ss.S = S; ss.route = route; ss.CN = CN > 0 ? CN : 1; ss.want = want;
+    LossArgs la; la.act = act; la.logp_old = logp_old; la.rtg = rtg; la.V = V; la.adv_mean = adv_mean; la.adv_inv_std = adv_inv_std;
+    la.inv_n = inv_n; la.f0 = f0; la.f1 = f1;
+    const Workspace w = carve(workspace, kp);
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = (kp == 16) ? launch_grad<16>(head, ss, net, la, w, s) : ((kp == 32) ? launch_grad<32>(head, ss, net, la, w, s) : launch_grad<56>(head, ss, net, la, w, s));
+    if (rc) return rc;
+    const int npar = net_params(kp);
+    k_reduce_partials<<<(npar + 255) / 256, 256, 0, s>>>(w.gpartial, kUpdateGrid, npar, grad);
+    k_reduce_scalars<<<1, 32, 0, s>>>(w.lpartial, kUpdateGrid, 1, loss);
+    api_count_launch(); api_count_launch();
+    return ck(cudaGetLastError(), "k_reduce_partials");
+}
+
+int mhppo_adam(float *p, const float *g, float *m, float *v, int32_t n, float lr, float beta1, float beta2, float eps, int32_t step,
+               float grad_scale, void *stream) {
+    if (!p || !g || !m || !v || n <= 0 || step < 1) return api_fail(MHPPO_EINVAL, "bad argument");
+    const double bc1 = 1.0 - std::pow((double)beta1, (double)step), bc2 = 1.0 - std::pow((double)beta2, (double)step);
+    const float step_size = (float)((double)lr / bc1), inv_sqrt_bc2 = (float)(1.0 / std::sqrt(bc2));
+    k_adam<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, beta1, beta2, step_size, inv_sqrt_bc2, eps, grad_scale);
+    api_count_launch();
+    return ck(cudaGetLastError(), "k_adam");
+}
+
+}  // extern "C"

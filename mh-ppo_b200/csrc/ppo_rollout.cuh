@@ -1,0 +1,206 @@
+// ppo_rollout.cuh -- rollout-side kernels of the PPO loop (Env_rollout.iterations_rand, PY:357-516):
+// per-(car, pedestrian) feature builders fused with the policy MLP, min-over-pedestrians, sampling and
+// log-prob, writing straight into the rollout buffers; and the reverse-scan reward-to-go.
+//
+// Data layout (all fp32, env index innermost so lane = env is coalesced):
+//   obs        [n_obs][N]      the env's component-major observation buffer (scalable class)
+//   action_d   [C*P][N] int8   +-1 per (car, ped): which continuous net drives that pair (PY:423)
+//   light      [C][N]          +-1 light per car, fixed for the episode (PY:424)
+//   sample s = (t*C + car)*N + env,  S = T*C*N
+//   obs_c      [13][S]         features of the arg-min pedestrian (PY:448-450)
+//   act, logp, rew, rl  [S]    rew / rl are written by the env-step kernel itself through its views
+//   choice sample m = car*N + env:  obs_d [D][M], act_d, logp_d, rew_d [M]
+#pragma once
+#include "mlp.cuh"
+#include "philox.cuh"
+
+namespace mhppo {
+
+struct RolloutDims {
+    int P, C, L, n_obs, D;      // D = 2 + 6*(C-1) + 8 + 2 (PY:111)
+    int64_t N;
+    uint32_t k0, k1;
+    int64_t env_id0;
+};
+
+// flat scalable observation (gym Dict key order car, env, ped; PY:543-554), component-major
+struct ObsView {
+    const float *o; int64_t N, n; int ped0, env0;
+    __device__ __forceinline__ float car(int i, int k) const { return o[(int64_t)(7 * i + k) * N + n]; }
+    __device__ __forceinline__ float env(int k) const { return o[(int64_t)(env0 + k) * N + n]; }
+    __device__ __forceinline__ float ped(int p, int k) const { return o[(int64_t)(ped0 + 9 * p + k) * N + n]; }
+};
+
+struct LaneGeom { float crossing, end_cross, dist_start, dist_end; };
+// Env_rollout.is_in_cross + leave_cross, PY:526-539 (fp32, reference operation order, no FMA)
+__device__ __forceinline__ LaneGeom lane_geom(float car_line, float py, float dir, float cl, float lines) {
+    const float cross = (cl * 2.0f) / lines;
+    const float ls = (-cl) + cross * car_line;
+    const float le = (-cl) + cross * (car_line + 1.0f);
+    LaneGeom g;
+    g.dist_start = (py - ls) * ((dir > 0.f) ? 1.f : 0.f) + (le - py) * ((dir < 0.f) ? 1.f : 0.f);
+    g.crossing = (py > ls && py < le) ? 1.f : 0.f;
+    const bool neg = (dir == -1.0f);
+    g.end_cross = (neg ? (py < ls) : (py > le)) ? 1.f : 0.f;
+    g.dist_end = neg ? (ls - py) : (py - le);
+    return g;
+}
+
+// Env_rollout.obs_car_ped, PY:541-572 -> 13 features into x[0..12]; returns ped exist
+__device__ __forceinline__ bool feat_c(const ObsView &v, int i, int p, float *x) {
+    const float Vc = v.car(i, 1), dVc = v.car(i, 2), cx = v.car(i, 3), line = v.car(i, 5);
+    const float vpx = v.ped(p, 0), vpy = v.ped(p, 1), px = v.ped(p, 2), py = v.ped(p, 3), dl = v.ped(p, 4), ex = v.ped(p, 7),
+                dir = v.ped(p, 8);
+    const float e0 = v.env(0), e3 = v.env(3);
+    const LaneGeom g = lane_geom(line, py, dir, e0, e3);
+    const bool front = px > cx;
+    const float dx = px - cx;
+    const float ttc = front ? fminf(10.0f, dx / fmaxf(Vc - vpx, 0.01f)) : 10.0f;
+    x[0] = Vc; x[1] = dVc; x[2] = vpy; x[3] = front ? 1.f : 0.f; x[4] = dx; x[5] = dl; x[6] = g.crossing; x[7] = g.end_cross;
+    x[8] = g.dist_start; x[9] = g.dist_end; x[10] = ttc; x[11] = e0; x[12] = e3;
+    return ex != 0.f;
+}
+
+// Env_rollout.obs_car_ped_d, PY:574-611 -> D features (note car_data[6], the OWN exist flag, PY:593)
+__device__ __forceinline__ void feat_d(const ObsView &v, int C, int i, int p, float *x) {
+    const float Vc = v.car(i, 1), dVc = v.car(i, 2), cx = v.car(i, 3), line = v.car(i, 5), own_exist = v.car(i, 6);
+    const float vpy = v.ped(p, 1), px = v.ped(p, 2), py = v.ped(p, 3), dl = v.ped(p, 4), dir = v.ped(p, 8);
+    int o = 0;
+    x[o++] = Vc; x[o++] = dVc;
+    for (int k = 0; k < C; ++k) {
+        if (k == i) continue;
+        const float x2 = v.car(k, 3);
+        x[o++] = v.car(k, 1); x[o++] = (px > x2) ? 1.f : 0.f; x[o++] = px - x2; x[o++] = v.car(k, 4);
+        x[o++] = v.car(k, 5) - line; x[o++] = own_exist;
+    }
+    const float e0 = v.env(0), e3 = v.env(3);
+    const LaneGeom g = lane_geom(line, py, dir, e0, e3);
+    x[o++] = vpy; x[o++] = (px > cx) ? 1.f : 0.f; x[o++] = px - cx; x[o++] = dl; x[o++] = g.crossing; x[o++] = g.end_cross;
+    x[o++] = g.dist_start; x[o++] = g.dist_end; x[o++] = e0; x[o++] = e3;
+}
+
+// policy-noise contract: counter = (index, stream | iteration << 8, env_lo, env_hi); the env's own stream uses
+// word 0 (philox.cuh), the continuous head 1, the discrete head 2
+__device__ __forceinline__ PhiloxBlock policy_block(const RolloutDims &d, int64_t n, uint32_t index, uint32_t stream_word) {
+    const uint64_t gid = (uint64_t)(d.env_id0 + n);
+    return philox4x32_10(index, stream_word, (uint32_t)gid, (uint32_t)(gid >> 32), d.k0, d.k1);
+}
+
+// ---- episode-start discrete decision (PY:400-428): thread = (env, car) -------------------------------
+template <int KP>
+__global__ void __launch_bounds__(kMlpBlock) k_choice_act(RolloutDims d, const float *__restrict__ obs, const float *__restrict__ net,
+                                                          uint32_t iteration, int8_t *__restrict__ action_d, float *__restrict__ light,
+                                                          float *__restrict__ obs_d, float *__restrict__ act_d, float *__restrict__ logp_d) {
+    extern __shared__ __align__(16) float smem[];
+    typedef Strides<KP> St;
+    float *sw = smem;
+    float *rows = smem + ((net_params(KP) + 3) & ~3);
+    constexpr int ROW = (St::X + St::A1 + St::A2 + St::A3) | 1;   // odd row stride: lane = sample is conflict-free
+    stage_net<KP>(sw, net);
+    __syncthreads();
+    const int64_t n = (int64_t)blockIdx.x * kMlpBlock + threadIdx.x;
+    const int i = blockIdx.y;
+    if (n >= d.N) return;
+    float *x = rows + (size_t)threadIdx.x * ROW, *a1 = x + St::X, *a2 = a1 + St::A1, *a3 = a2 + St::A2;
+    const ObsView v{obs, d.N, n, 7 * d.C + 4, 7 * d.C};
+    const float cx = v.car(i, 3);
+    int best = 0; float best_a = 0.f, best_lp = 0.f; double dmin = 1000000.0;    // closest_ped_d, PY:614-627
+    const float eps = 1.1920928955078125e-07f;
+    for (int p = 0; p < d.P; ++p) {
+        for (int k = 0; k < KP; ++k) x[k] = 0.f;
+        feat_d(v, d.C, i, p, x);
+        const float4 o = mlp_fwd_rows<KP>(sw, x, a1, a2, a3);
+        const float m = fmaxf(o.x, o.y);                                          // softmax over the pair, PY:81-83
+        const float e0 = expf(o.x - m), e1 = expf(o.y - m);
+        const float p0 = e0 / (e0 + e1), p1 = e1 / (e0 + e1);
+        const PhiloxBlock b = policy_block(d, n, (uint32_t)(i * d.P + p), 2u | (iteration << 8));
+        const float u = (float)u53(b.w0, b.w1);
+        const int a = (u >= p0) ? 1 : 0;                                          // Categorical.sample()
+        const float pa = fminf(fmaxf((a ? p1 : p0) / (p0 + p1), eps), 1.0f - eps);  // torch probs_to_logits clamp
+        const float lp = logf(pa);
+        action_d[(int64_t)(i * d.P + p) * d.N + n] = (int8_t)(2 * a - 1);
+        const double dist = (double)(v.ped(p, 2) - cx);
+        if (dist < dmin && v.ped(p, 7) != 0.f) { dmin = dist; best = p; }
+        if (p == 0 || best == p) { best_a = (float)a; best_lp = lp; }
+    }
+    // the car's light and its choice sample come from the closest pedestrian (PY:416-422)
+    for (int k = 0; k < KP; ++k) x[k] = 0.f;
+    feat_d(v, d.C, i, best, x);
+    const int64_t m_idx = (int64_t)i * d.N + n, M = (int64_t)d.C * d.N;
+    for (int k = 0; k < d.D; ++k) obs_d[(int64_t)k * M + m_idx] = x[k];
+    light[m_idx] = 2.f * best_a - 1.f;
+    act_d[m_idx] = best_a; logp_d[m_idx] = best_lp;
+}
+
+// ---- per-step continuous action (PY:434-453): thread = (env, car) -----------------------------------
+struct ActIO {
+    const float *obs; const int8_t *action_d; const float *light;
+    float *actions;                 // [2C][N]: acc rows then light rows, the env-step kernel's input view
+    float *obs_c, *act, *logp;      // rollout buffers
+    int t, T; uint32_t iteration;
+};
+
+__global__ void __launch_bounds__(kMlpBlock) k_policy_act(RolloutDims d, const float *__restrict__ net_cross,
+                                                          const float *__restrict__ net_wait, ActIO io) {
+    constexpr int KP = 16;
+    extern __shared__ __align__(16) float smem[];
+    typedef Strides<KP> St;
+    constexpr int NP = (net_params(KP) + 3) & ~3;
+    float *sw = smem;
+    float *rows = smem + 2 * NP;
+    constexpr int ROW = (St::X + St::A1 + St::A2 + St::A3) | 1;   // odd row stride: lane = sample is conflict-free
+    stage_net<KP>(sw, net_cross);
+    stage_net<KP>(sw + NP, net_wait);
+    __syncthreads();
+    const int64_t n = (int64_t)blockIdx.x * kMlpBlock + threadIdx.x;
+    const int i = blockIdx.y;
+    if (n >= d.N) return;
+    float *x = rows + (size_t)threadIdx.x * ROW, *a1 = x + St::X, *a2 = a1 + St::A1, *a3 = a2 + St::A2;
+    const ObsView v{io.obs, d.N, n, 7 * d.C + 4, 7 * d.C};
+    float mean = 2.0f;                                   // car_b[1,0], PY:436
+    float st[13];
+    x[13] = x[14] = x[15] = 0.f;
+    feat_c(v, i, 0, x);                                  // state_c_tensor starts as ped 0's features, PY:437
+#pragma unroll
+    for (int k = 0; k < 13; ++k) st[k] = x[k];
+    for (int p = 0; p < d.P; ++p) {
+        const bool ex = feat_c(v, i, p, x);
+        if (!ex) continue;                               // PY:440
+        const int sel = (io.action_d[(int64_t)(i * d.P + p) * d.N + n] <= 0) ? 0 : 1;   // cross | wait, PY:441-446
+        const float4 o = mlp_fwd_rows<KP>(sw + sel * NP, x, a1, a2, a3);
+        const float m = tanhf(o.x) * 3.0f + (-1.0f);     // head type 1, PY:88-90 (std 3, mean -1)
+        mean = fminf(mean, m);
+        if (m == mean) {                                 // PY:449-450 (ties: the later pedestrian)
+#pragma unroll
+            for (int k = 0; k < 13; ++k) st[k] = x[k];
+        }
+    }
+    const PhiloxBlock b = policy_block(d, n, (uint32_t)(io.t * d.C + i), 1u | (io.iteration << 8));
+    const double z = sqrt(-2.0 * log(1.0 - u53(b.w0, b.w1))) * cos(2.0 * 3.141592653589793 * u53(b.w2, b.w3));
+    const float a = mean + 0.70710678118654757f * (float)z;      // MultivariateNormal(mean, 0.5 I).sample()
+    const float lp = -((a - mean) * (a - mean)) - 0.57236494292470008f;   // log_prob = -(a-mu)^2 - ln(pi)/2
+    io.actions[(int64_t)i * d.N + n] = a;
+    io.actions[(int64_t)(d.C + i) * d.N + n] = io.light[(int64_t)i * d.N + n];
+    const int64_t S = (int64_t)io.T * d.C * d.N, s = ((int64_t)io.t * d.C + i) * d.N + n;
+#pragma unroll
+    for (int k = 0; k < 13; ++k) io.obs_c[(int64_t)k * S + s] = st[k];
+    io.act[s] = a; io.logp[s] = lp;
+}
+
+// ---- futur_rewards (PY:658-684) + episodic choice reward (PY:461): thread = (car, env) ---------------
+__global__ void __launch_bounds__(256) k_returns(const float *__restrict__ rew, const float *__restrict__ rl, int T, int64_t CN,
+                                                 double gamma, float *__restrict__ rtg, float *__restrict__ rew_d) {
+    const int64_t m = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (m >= CN) return;
+    double acc = 0.0;
+    float worst = 0.f;
+    for (int t = T - 1; t >= 0; --t) {
+        const int64_t s = (int64_t)t * CN + m;
+        acc = (double)rew[s] + gamma * acc;
+        rtg[s] = (float)acc;
+        worst = fminf(worst, rl[s]);
+    }
+    rew_d[m] = worst;
+}
+
+}  // namespace mhppo

@@ -1,0 +1,175 @@
+"""Algo_PPO -- vectorised mirror of the reference's PPO class (Coop-MH-PPO-scalable.py:698-1001) for the
+scalable env class: same constructor (`Algo_PPO(policy_class, env, **hyperparameters)`), same six networks
+and six Adam optimisers, same update rule (clipped surrogate 0.8/1.2, no entropy term, MSE critic, 10 full-batch
+epochs per net per iteration, advantages = reward-to-go - V normalised with the unbiased std).
+
+One iteration = one 80-step episode in every env of the vectorised env.  Multi-GPU: one process per GPU, envs
+sharded per rank; the only collectives are the all-reduce of the three advantage statistics and of the flat
+gradient buffers (NCCL through torch.distributed), so an R-rank run performs the same update as one rank
+holding all envs.
+"""
+import ctypes as C
+import math
+import os
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check
+from .policy import Adam, Model_PPO
+from .rollout import Env_rollout
+
+
+def _dist():
+    import torch.distributed as dist
+    return dist if (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1) else None
+
+
+def combine_stats(stats3):
+    """(sum A, sum A^2, n) -> (mean, 1/(unbiased std + 1e-10), n): advantage normalisation of PY:787 from partial sums."""
+    sA, sAA, n = float(stats3[0]), float(stats3[1]), float(stats3[2])
+    if n < 1:
+        return 0.0, 0.0, 0.0
+    mean = sA / n
+    var = max(sAA - n * mean * mean, 0.0) / (n - 1) if n > 1 else float("nan")
+    std = math.sqrt(var) if n > 1 else float("nan")
+    return mean, 1.0 / (std + 1e-10), n
+
+
+def allreduce_sum_(t):
+    d = _dist()
+    if d is not None:
+        d.all_reduce(t, op=d.ReduceOp.SUM)
+    return t
+
+
+class Algo_PPO:
+    def __init__(self, policy_class, env, **hyperparameters):
+        self._init_hyperparameters(hyperparameters)
+        self.env = env
+        self.max_steps = env.max_episode
+        dev = env.device
+        nc = 2 * env.nb_lines
+        mk = lambda *a, **k: policy_class(*a, device=dev, **k)
+        self.actor_net_cross = mk(self.num_states_c, self.num_actions, 1, nb_car=nc, mean=self.mean, std=self.std)      # PY:711-718
+        self.actor_net_wait = mk(self.num_states_c, self.num_actions, 1, nb_car=nc, mean=self.mean, std=self.std)
+        self.actor_net_choice = mk(self.num_states_d, 2, 2)
+        self.critic_net_cross = mk(self.num_states_c, 1, 0)
+        self.critic_net_wait = mk(self.num_states_c, 1, 0)
+        self.critic_net_choice = mk(self.num_states_d, 1, 0)
+        self.optimizer_critic_cross = Adam(self.critic_net_cross, self.critic_lr)                                        # PY:719-724
+        self.optimizer_critic_wait = Adam(self.critic_net_wait, self.critic_lr)
+        self.optimizer_critic_choice = Adam(self.critic_net_choice, self.critic_d_lr)
+        self.optimizer_actor_cross = Adam(self.actor_net_cross, self.actor_lr)
+        self.optimizer_actor_wait = Adam(self.actor_net_wait, self.actor_lr)
+        self.optimizer_actor_choice = Adam(self.actor_net_choice, self.actor_d_lr)
+        self.value_std, self.value_std_d = 0.5, 0.1                                                                      # PY:726-727
+        self.rollout = Env_rollout(env, nc, self.max_steps, self.dt)
+        self.ep_reward_cross, self.ep_reward_wait, self.ep_reward_choice, self.ep_scenario_balance = [], [], [], []
+        L = _lib.lib()
+        nbytes = max(L.mhppo_update_workspace_bytes(self.num_states_c), L.mhppo_update_workspace_bytes(self.num_states_d))
+        self._ws = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+        self._stats = torch.zeros(3, dtype=torch.float64, device=dev)
+        self._loss = torch.zeros(2, dtype=torch.float64, device=dev)
+        self.last_losses = {}
+
+    def _init_hyperparameters(self, hyperparameters):
+        """PY:919-933."""
+        self.num_algo, self.total_loop, self.batch_size, self.gamma = 1, 0, 2048, 0.99
+        self.critic_lr, self.actor_lr, self.critic_d_lr, self.actor_d_lr = 1e-3, 3e-4, 1e-3, 3e-4
+        self.num_states_c, self.num_states_d, self.num_actions, self.mean, self.std, self.dt = 13, None, 1, -1.0, 3.0, 0.3
+        for k, v in hyperparameters.items():
+            setattr(self, k, v)
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.env.device).cuda_stream)
+
+    # -- one epoch of train_model_c (PY:778-815) on the cross (want=0) or wait (want=1) buffer ------------------
+    def train_model_c(self, actor, critic, opti_actor, opti_critic, want):
+        r, L, st = self.rollout, _lib.lib(), self._stream()
+        ws = self._ws.data_ptr()
+        check(L.mhppo_value_stats(13, r.obs_c.data_ptr(), 13, r.S, r.route.data_ptr(), r.M, want, critic.flat.data_ptr(),
+                                  r.rtg.data_ptr(), r.V.data_ptr(), self._stats.data_ptr(), ws, st))
+        mean, inv_std, n = combine_stats(allreduce_sum_(self._stats).cpu())
+        if n < 1:
+            return False                                     # PY:869/874: the net is skipped when its buffer is empty
+        check(L.mhppo_ppo_grad(13, 1, r.obs_c.data_ptr(), 13, r.S, r.route.data_ptr(), r.M, want, actor.flat.data_ptr(),
+                               r.act.data_ptr(), r.logp.data_ptr(), r.rtg.data_ptr(), r.V.data_ptr(), mean, inv_std, 1.0 / n,
+                               0.0, 0.0, actor.grad.data_ptr(), self._loss.data_ptr(), ws, st))
+        check(L.mhppo_ppo_grad(13, 0, r.obs_c.data_ptr(), 13, r.S, r.route.data_ptr(), r.M, want, critic.flat.data_ptr(),
+                               None, None, r.rtg.data_ptr(), None, 0.0, 0.0, 1.0 / n, 0.0, 0.0, critic.grad.data_ptr(),
+                               self._loss.data_ptr() + 8, ws, st))
+        allreduce_sum_(actor.grad); allreduce_sum_(critic.grad)
+        opti_actor.step(); opti_critic.step()
+        return True
+
+    # -- one epoch of train_model_d (PY:818-851) on the choice buffer -------------------------------------------
+    def train_model_d(self, actor, critic, opti_actor, opti_critic):
+        r, L, st = self.rollout, _lib.lib(), self._stream()
+        ws, D = self._ws.data_ptr(), r.shape_env_d
+        check(L.mhppo_value_stats(D, r.obs_d.data_ptr(), D, r.M, r.exist.data_ptr(), r.M, 1, critic.flat.data_ptr(),
+                                  r.rew_d.data_ptr(), r.V_d.data_ptr(), self._stats.data_ptr(), ws, st))
+        ex = r.exist.view(-1) != 0
+        cnt = torch.stack([(ex & (r.act_d == 0)).sum(), (ex & (r.act_d == 1)).sum()]).double()
+        mean, inv_std, n = combine_stats(allreduce_sum_(self._stats).cpu())
+        cnt = allreduce_sum_(cnt).cpu()
+        if n < 1:
+            return False
+        f0, f1 = float(cnt[0]) / n, float(cnt[1]) / n
+        check(L.mhppo_ppo_grad(D, 2, r.obs_d.data_ptr(), D, r.M, r.exist.data_ptr(), r.M, 1, actor.flat.data_ptr(),
+                               r.act_d.data_ptr(), r.logp_d.data_ptr(), r.rew_d.data_ptr(), r.V_d.data_ptr(), mean, inv_std,
+                               1.0 / n, f0, f1, actor.grad.data_ptr(), self._loss.data_ptr(), ws, st))
+        check(L.mhppo_ppo_grad(D, 0, r.obs_d.data_ptr(), D, r.M, r.exist.data_ptr(), r.M, 1, critic.flat.data_ptr(),
+                               None, None, r.rew_d.data_ptr(), None, 0.0, 0.0, 1.0 / n, 0.0, 0.0, critic.grad.data_ptr(),
+                               self._loss.data_ptr() + 8, ws, st))
+        allreduce_sum_(actor.grad); allreduce_sum_(critic.grad)
+        opti_actor.step(); opti_critic.step()
+        return True
+
+    def update(self, epochs=10):
+        """The update half of train() (PY:866-882): 10 x (cross, wait) then 10 x choice."""
+        self.rollout.futur_rewards()
+        for _ in range(epochs):
+            self.train_model_c(self.actor_net_cross, self.critic_net_cross, self.optimizer_actor_cross, self.optimizer_critic_cross, 0)
+            self.train_model_c(self.actor_net_wait, self.critic_net_wait, self.optimizer_actor_wait, self.optimizer_critic_wait, 1)
+        for _ in range(epochs):
+            self.train_model_d(self.actor_net_choice, self.critic_net_choice, self.optimizer_actor_choice, self.optimizer_critic_choice)
+
+    def train(self, nb_loop, verbose=False):
+        """Training loop (PY:854-917)."""
+        for ep in range(nb_loop):
+            self.rollout.iterations_rand(self.actor_net_cross, self.actor_net_wait, self.actor_net_choice)
+            self.update()
+            cross, wait, choice = self.rollout.immediate_rewards()
+            nc, nw, nd = self.rollout.counts()
+            if cross is not None:
+                self.ep_reward_cross.append(float(cross))
+            if wait is not None:
+                self.ep_reward_wait.append(float(wait))
+            self.ep_reward_choice.append(float(choice))
+            self.ep_scenario_balance.append([nc, nw])
+            self.total_loop += 1
+            if verbose:
+                print("Episode * {} * cross {:.4f} wait {:.4f} choice {:.4f}  (#cross {} #wait {})".format(
+                    ep, np.mean(self.ep_reward_cross[-10:] or [0]), np.mean(self.ep_reward_wait[-10:] or [0]),
+                    np.mean(self.ep_reward_choice[-10:]), nc, nw))
+
+    # -- checkpoints: same file names and state_dict layout as the reference (PY:935-1001) ------------------------
+    _PATH = "load_model/weights/pappo-scalable-coop-{name}-{num_algo:02d}-{kind}-step-{epoch:03d}0.pth"
+
+    def _nets(self):
+        return [("cross", "actor", self.actor_net_cross), ("wait", "actor", self.actor_net_wait), ("choice", "actor", self.actor_net_choice),
+                ("cross", "critic", self.critic_net_cross), ("wait", "critic", self.critic_net_wait), ("choice", "critic", self.critic_net_choice)]
+
+    def saving(self, root="."):
+        for name, kind, net in self._nets():
+            path = os.path.join(root, self._PATH.format(name=name, kind=kind, num_algo=self.num_algo, epoch=int(self.total_loop / 10)))
+            os.makedirs(os.path.dirname(path), exist_ok=True)
+            torch.save(net.state_dict(), path)
+
+    def loading(self, num_algo, total_loop, root="."):
+        self.num_algo, self.total_loop = num_algo, total_loop
+        for name, kind, net in self._nets():
+            path = os.path.join(root, self._PATH.format(name=name, kind=kind, num_algo=num_algo, epoch=int(total_loop / 10)))
+            net.load_state_dict(torch.load(path, map_location="cpu"))

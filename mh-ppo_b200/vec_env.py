@@ -67,6 +67,7 @@ class VecCrosswalkEnv:
         self.car_b, self.ped_b, self.cross_b = np.asarray(car_b, float), np.asarray(ped_b, float), np.asarray(cross_b, float)
         self.speed_limit = 10                      # SC:892
         self.simulation, self.autoreset = simulation, bool(autoreset)
+        self._seed, self._env_id0 = int(seed), int(env_id0)
         cfg = EnvCfg(variant=VARIANT_ID[variant], nb_car=nb_car, nb_ped=nb_ped, nb_lines=nb_lines, max_episode=max_episode,
                      sin_model=int(simulation == "sin"), device=self.device.index, dt=dt, seed=seed, n_envs=self.n_envs,
                      env_id0=env_id0)

@@ -1,0 +1,183 @@
+"""Parity of the PPO kernels (rollout inference, returns, update) through the C ABI against oracle/ppo_oracle.py and
+the golden fixtures recorded from the unmodified reference PPO classes.  Tolerances: discrete decisions / routing /
+masks bit-exact; fp32 values 1e-5 relative for single kernels, 1e-4 for 80-step free-running episodes and multi-epoch
+updates (fp32 accumulation-order differences of the 4-layer MLP compound through the env and Adam)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN_DIR
+
+pytestmark = pytest.mark.gpu
+
+
+def _sd(z, prefix):
+    return {k[len(prefix) + 1:]: torch.as_tensor(z[k]) for k in z.files if k.startswith(prefix + ".")}
+
+
+@pytest.fixture(scope="module")
+def mh():
+    assert torch.cuda.is_available()
+    import mhppo_b200
+    return mhppo_b200
+
+
+def _algo(mh, N, seed, env_id0, z=None):
+    env = mh.VecCrosswalkEnv("coop_scalable", N, nb_car=4, nb_ped=3, nb_lines=2, seed=seed, env_id0=env_id0)
+    torch.manual_seed(0)
+    algo = mh.Algo_PPO(mh.Model_PPO, env, num_states_c=13, num_states_d=30, num_actions=1, mean=-1.0, std=3.0, nb_cars=4, dt=0.3)
+    if z is not None:
+        algo.actor_net_cross.load_state_dict(_sd(z, "cross")); algo.actor_net_wait.load_state_dict(_sd(z, "wait"))
+        algo.actor_net_choice.load_state_dict(_sd(z, "choice"))
+    return algo, env
+
+
+def test_rollout_matches_reference_golden(mh):
+    """GPU rollout (env kernel + policy kernels) vs whole episodes recorded from the reference's iterations_rand."""
+    z = np.load(os.path.join(GOLDEN_DIR, "ppo_rollout_432.npz"))
+    for e, (seed, env_id) in enumerate(z["streams"]):
+        algo, env = _algo(mh, 1, int(seed), int(env_id), z)
+        r = algo.rollout
+        r.iterations_rand(algo.actor_net_cross, algo.actor_net_wait, algo.actor_net_choice)
+        r.futur_rewards()
+        want = {k.split(".", 1)[1]: z[k] for k in z.files if k.startswith("ep%d." % e)}
+        exist = r.exist[:, 0].cpu().numpy() != 0
+        np.testing.assert_array_equal(exist, want["car_exist"])
+        route = r.route[:, 0].cpu().numpy()
+        T, C = r.T, r.C
+        obs_c = r.obs_c.view(13, T, C).cpu().numpy(); g = lambda t: t.view(T, C).cpu().numpy()
+        act, logp, rew, rtg = g(r.act), g(r.logp), g(r.rew), g(r.rtg)
+        for name, rt in (("cross", 0), ("wait", 1)):
+            cars = [i for i in range(C) if route[i] == rt]
+            if not cars:
+                assert want["acts_" + name].size == 0
+                continue
+            np.testing.assert_allclose(np.concatenate([obs_c[:, :, i].T for i in cars]), want["obs_" + name], rtol=1e-4, atol=1e-4)
+            np.testing.assert_allclose(np.concatenate([act[:, i] for i in cars]), want["acts_" + name], rtol=1e-4, atol=1e-4)
+            np.testing.assert_allclose(np.concatenate([logp[:, i] for i in cars]), want["logp_" + name], rtol=1e-4, atol=1e-4)
+            np.testing.assert_allclose(np.concatenate([rew[:, i] for i in cars]), want["rews_" + name], rtol=1e-4, atol=1e-4)
+            np.testing.assert_allclose(np.concatenate([rtg[:, i] for i in cars]), want["rtg_" + name], rtol=1e-4, atol=1e-4)
+        cars = [i for i in range(C) if exist[i]]
+        np.testing.assert_allclose(r.obs_d[:, :].cpu().numpy()[:, cars].T, want["obs_choice"], rtol=1e-5, atol=1e-5)
+        np.testing.assert_array_equal(r.act_d.cpu().numpy()[cars], want["acts_choice"])
+        np.testing.assert_allclose(r.logp_d.cpu().numpy()[cars], want["logp_choice"], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(r.rew_d.cpu().numpy()[cars], want["rews_choice"], rtol=1e-4, atol=1e-6)
+
+
+def test_rollout_matches_oracle_batch(mh, oracle_mod):
+    """512 envs for one episode: GPU pipeline vs the oracle pipeline (env oracle in HBM semantics + ppo_oracle)."""
+    from oracle import ppo_oracle as PO
+    N, seed, id0 = 512, 31, 4000
+    algo, env = _algo(mh, N, seed, id0)
+    sds = [{k: v.clone() for k, v in n.state_dict().items()} for n in (algo.actor_net_cross, algo.actor_net_wait, algo.actor_net_choice)]
+    r = algo.rollout
+    r.iterations_rand(algo.actor_net_cross, algo.actor_net_wait, algo.actor_net_choice)
+    r.futur_rewards()
+    venv = oracle_mod.OracleVecEnv("coop_scalable", N, 4, 3, 2, seed=seed, env_id0=id0, store_f32=True)
+    b = PO.rollout_episode(venv, *sds, seed, np.arange(id0, id0 + N), 3, 2)
+    T, C = r.T, r.C
+    np.testing.assert_array_equal(r.exist.cpu().numpy() != 0, b["exist"])
+    np.testing.assert_array_equal(r.route.cpu().numpy(), b["route"])
+    np.testing.assert_array_equal(r.act_d.view(C, N).cpu().numpy(), b["act_d"])
+    np.testing.assert_allclose(r.logp_d.view(C, N).cpu().numpy(), b["logp_d"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(r.obs_d.view(-1, C, N).cpu().numpy(), b["obs_d"].transpose(2, 0, 1), rtol=1e-5, atol=1e-5)
+    # 80 free-running steps: fp32 summation-order differences of the MLP (1e-7) feed back through the env, and features
+    # such as dist_start are differences of O(3) quantities, so a handful of near-zero entries move by ~1e-4 absolute
+    np.testing.assert_allclose(r.obs_c.view(13, T, C, N).cpu().numpy(), b["obs_c"].transpose(3, 0, 1, 2), rtol=1e-4, atol=5e-4)
+    np.testing.assert_allclose(r.act.view(T, C, N).cpu().numpy(), b["act"], rtol=1e-4, atol=5e-4)
+    np.testing.assert_allclose(r.logp.view(T, C, N).cpu().numpy(), b["logp"], rtol=1e-4, atol=5e-4)
+    np.testing.assert_allclose(r.rew.view(T, C, N).cpu().numpy(), b["rew"], rtol=1e-4, atol=5e-4)
+    np.testing.assert_allclose(r.rew_d.view(C, N).cpu().numpy(), b["rew_d"], rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(r.rtg.view(T, C, N).cpu().numpy(), PO.reward_to_go(b["rew"]), rtol=1e-4, atol=5e-3)
+
+
+def test_returns_kernel(mh):
+    import ctypes as C
+    from oracle import ppo_oracle as PO
+    T, CN = 80, 3000
+    g = torch.Generator(device="cuda").manual_seed(1)
+    rew = -torch.rand(T * CN, device="cuda", generator=g) * 10
+    rl = -torch.rand(T * CN, device="cuda", generator=g) * 3
+    rtg, rew_d = torch.zeros_like(rew), torch.zeros(CN, device="cuda")
+    mh._lib.check(mh.lib().mhppo_returns(rew.data_ptr(), rl.data_ptr(), T, CN, 0.99, rtg.data_ptr(), rew_d.data_ptr(), None))
+    torch.cuda.synchronize()
+    want = PO.reward_to_go(rew.view(T, CN).cpu().numpy())
+    np.testing.assert_allclose(rtg.view(T, CN).cpu().numpy(), want, rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(rew_d.cpu().numpy(), np.minimum(0, rl.view(T, CN).cpu().numpy().min(0)), rtol=0, atol=0)
+
+
+@pytest.mark.parametrize("kind", ["c", "d"])
+def test_update_matches_reference_golden(mh, kind):
+    """train_model_c / train_model_d: 4 epochs on the recorded batch reproduce the reference's weights."""
+    z = np.load(os.path.join(GOLDEN_DIR, "ppo_train_%s.npz" % kind))
+    N = z["states"].shape[0]
+    env = mh.VecCrosswalkEnv("coop_scalable", N, nb_car=4, nb_ped=3, nb_lines=2, seed=1)
+    algo = mh.Algo_PPO(mh.Model_PPO, env, num_states_c=13, num_states_d=30, num_actions=1, mean=-1.0, std=3.0, nb_cars=4, dt=0.3)
+    r = algo.rollout
+    dev = env.device
+    if kind == "c":
+        actor, critic, oa, oc = algo.actor_net_cross, algo.critic_net_cross, algo.optimizer_actor_cross, algo.optimizer_critic_cross
+        # place the batch in car slot 0 at t = 0 and select it with route
+        r.route.fill_(-1); r.route[0] = 0
+        r.obs_c.zero_(); r.obs_c.view(13, r.T, r.C, N)[:, 0, 0] = torch.as_tensor(z["states"].T).to(dev)
+        r.act.view(r.T, r.C, N)[0, 0] = torch.as_tensor(z["actions"][:, 0]).to(dev)
+        r.logp.view(r.T, r.C, N)[0, 0] = torch.as_tensor(z["logp_old"]).to(dev)
+        r.rtg.view(r.T, r.C, N)[0, 0] = torch.as_tensor(z["rtgs"]).to(dev)
+        # only t = 0 carries data: restrict the sample range to the first C*N samples
+        r.S = r.C * N
+        r.obs_c = r.obs_c.view(13, r.T, r.C * N)[:, 0].contiguous()
+    else:
+        actor, critic, oa, oc = algo.actor_net_choice, algo.critic_net_choice, algo.optimizer_actor_choice, algo.optimizer_critic_choice
+        r.exist.zero_(); r.exist[0] = 1
+        r.obs_d.zero_(); r.obs_d.view(30, r.C, N)[:, 0] = torch.as_tensor(z["states"].T).to(dev)
+        r.act_d.view(r.C, N)[0] = torch.as_tensor(z["actions"][:, 0]).to(dev)
+        r.logp_d.view(r.C, N)[0] = torch.as_tensor(z["logp_old"]).to(dev)
+        r.rew_d.view(r.C, N)[0] = torch.as_tensor(z["rtgs"]).to(dev)
+    actor.load_state_dict(_sd(z, "actor0")); critic.load_state_dict(_sd(z, "critic0"))
+    for ep in range(1, 5):
+        ok = algo.train_model_c(actor, critic, oa, oc, 0) if kind == "c" else algo.train_model_d(actor, critic, oa, oc)
+        assert ok
+        for net, pre in ((actor, "actor%d" % ep), (critic, "critic%d" % ep)):
+            for k, v in net.state_dict().items():
+                np.testing.assert_allclose(v.numpy(), z[pre + "." + k], rtol=1e-4, atol=2e-6, err_msg="%s %s" % (pre, k))
+
+
+def test_gradients_match_autograd(mh):
+    """One epoch's flat gradients and losses (actor + critic) against torch autograd on the same selected samples."""
+    from oracle import ppo_oracle as PO
+    N = 1500
+    env = mh.VecCrosswalkEnv("coop_scalable", N, nb_car=4, nb_ped=3, nb_lines=2, seed=2)
+    torch.manual_seed(5)
+    algo = mh.Algo_PPO(mh.Model_PPO, env, num_states_c=13, num_states_d=30, num_actions=1, mean=-1.0, std=3.0, nb_cars=4, dt=0.3)
+    r = algo.rollout
+    g = torch.Generator(device="cuda").manual_seed(3)
+    r.obs_c.copy_(torch.randn(r.obs_c.shape, device="cuda", generator=g))
+    r.act.copy_(torch.randn(r.S, device="cuda", generator=g) * 2 - 1)
+    r.logp.copy_(-torch.rand(r.S, device="cuda", generator=g) * 3)
+    r.rtg.copy_(torch.randn(r.S, device="cuda", generator=g) * 5 - 3)
+    r.route.copy_(torch.randint(-1, 2, r.route.shape, device="cuda", generator=g).to(torch.int8))
+    actor, critic = algo.actor_net_wait, algo.critic_net_wait
+    a_o, c_o = PO.Net(13, 1, 1), PO.Net(13, 1, 0)
+    a_o.load_state_dict(actor.state_dict()); c_o.load_state_dict(critic.state_dict())
+    sel = (r.route.view(1, r.C, N) == 1).expand(r.T, r.C, N).reshape(-1).cpu()
+    s = r.obs_c.t().cpu()[sel]
+    V = c_o(s).reshape(-1); rtg = r.rtg.cpu()[sel]
+    adv = rtg - V; adv = (adv - adv.mean()) / (adv.std() + 1e-10)
+    mu = a_o(s).reshape(-1); a = r.act.cpu()[sel]
+    ratio = torch.exp(-((a - mu) ** 2) - PO.LOG_PI_HALF - r.logp.cpu()[sel])
+    la = (-torch.min(ratio * adv.detach(), torch.clamp(ratio, 0.8, 1.2) * adv.detach())).mean()
+    lc = torch.nn.functional.mse_loss(V, rtg)
+    ga = torch.autograd.grad(la, list(a_o.parameters())); gc = torch.autograd.grad(lc, list(c_o.parameters()))
+    before_a, before_c = actor.flat.clone(), critic.flat.clone()
+    assert algo.train_model_c(actor, critic, algo.optimizer_actor_wait, algo.optimizer_critic_wait, 1)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(algo._loss.cpu().numpy(), [float(la), float(lc)], rtol=1e-5)
+    for net, grads, ref in ((actor, ga, a_o), (critic, gc, c_o)):
+        tmp = mh.Model_PPO(13, 1, net.model_type, device="cpu")
+        tmp.load_state_dict({k: gg for (k, _), gg in zip(ref.named_parameters(), grads)})
+        want = tmp.flat.numpy()
+        got = net.grad.cpu().numpy()
+        scale = np.abs(want).max()
+        np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-5 * scale)
