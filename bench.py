@@ -119,6 +119,49 @@ def cpu_port_rate(variant, nb_car, nb_ped, nb_lines, n_envs, n_steps, threads=0)
     return n_envs * n_steps / dt, dt, active
 
 
+def run_ppo(mh, torch, dist, world, rank, dev, n_envs, iters, warm=1):
+    """PPO samples/s (BASELINE.json metric, second half): one iteration = one 80-step episode in every env
+    (Env_rollout.iterations_rand) + reward-to-go + 10 x (cross, wait) + 10 x choice update epochs (Algo_PPO.train)."""
+    env = mh.VecCrosswalkEnv("coop_scalable", n_envs, nb_car=4, nb_ped=3, nb_lines=2, seed=1234, env_id0=rank * n_envs, device=dev)
+    torch.manual_seed(0)
+    algo = mh.Algo_PPO(mh.Model_PPO, env, num_states_c=13, num_states_d=30, num_actions=1, mean=-1.0, std=3.0, nb_cars=4, dt=0.3)
+    r = algo.rollout
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    for _ in range(warm):
+        r.iterations_rand(algo.actor_net_cross, algo.actor_net_wait, algo.actor_net_choice)
+        algo.update()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    n0 = mh.launch_count()
+    t_roll = t_upd = 0.0
+    samples = 0
+    for _ in range(iters):
+        e0, e1, e2 = ev(), ev(), ev()
+        e0.record()
+        r.iterations_rand(algo.actor_net_cross, algo.actor_net_wait, algo.actor_net_choice)
+        e1.record()
+        algo.update()
+        e2.record()
+        torch.cuda.synchronize()
+        t_roll += e0.elapsed_time(e1); t_upd += e1.elapsed_time(e2)
+        samples += sum(r.counts())
+    launches = mh.launch_count() - n0
+    t = torch.tensor([t_roll + t_upd, t_roll, t_upd, float(samples)], dtype=torch.float64, device=dev)
+    if world > 1:
+        mx = t.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX); dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        tot_ms, roll_ms, upd_ms, samples = mx[0].item(), mx[1].item(), mx[2].item(), t[3].item()
+    else:
+        tot_ms, roll_ms, upd_ms, samples = [x.item() for x in t]
+    del algo, env
+    torch.cuda.empty_cache()
+    return {"samples_per_s": samples / (tot_ms * 1e-3), "unit": "PPO samples/s (cross + wait + choice samples consumed by the update)",
+            "iteration_ms": tot_ms / iters, "rollout_ms": roll_ms / iters, "update_ms": upd_ms / iters, "iterations": iters,
+            "samples_per_iteration": samples / iters, "n_envs_per_gpu": n_envs, "update_epochs": "10 x (cross, wait) + 10 x choice",
+            "gpu_launches": int(launches),
+            "config": "Coop-MH-PPO-scalable on Env_hybrid_multi_coop_scalable nb_car=4 nb_ped=3 nb_lines=2, %d envs/GPU x 80 steps" % n_envs}
+
+
 def run_reference(args, wl):
     variant, nb_car, nb_ped, nb_lines, n_envs = wl
     rank = int(os.environ.get("RANK", "0"))
@@ -126,7 +169,7 @@ def run_reference(args, wl):
         return
     cores = os.cpu_count() or 1
     n_sample = 16384                      # bounded sample of the n_envs-per-GPU batch, per step
-    rate, dt, active = cpu_port_rate(variant, nb_car, nb_ped, nb_lines, n_sample, args.steps, threads=cores)
+    rate, dt, active = cpu_port_rate(variant, nb_car, nb_ped, nb_lines, n_sample, max(args.steps, 1), threads=cores)
     B, C, nobs = algorithmic_bytes(variant, nb_car, nb_ped, nb_lines)
     sample = "%d envs x %d steps of the %d-env batch, C oracle port (oracle/mhppo_oracle.c), %d threads" % (
         n_sample, args.steps, n_envs, cores)
@@ -155,6 +198,8 @@ def main():
     ap.add_argument("--envs", type=int, default=0, help="override envs per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
+    ap.add_argument("--ppo-envs", type=int, default=131072, help="envs per GPU of the PPO samples/s section (0 = skip)")
+    ap.add_argument("--ppo-iters", type=int, default=2)
     args = ap.parse_args()
     wl = list(WORKLOADS[args.workload])
     if args.envs:
@@ -181,6 +226,7 @@ def main():
     env = mhppo_b200.VecCrosswalkEnv(variant, n_envs, nb_car=nb_car, nb_ped=nb_ped, nb_lines=nb_lines,
                                      seed=1234, env_id0=rank * n_envs, device=dev, autoreset=True)
     A = env.n_action
+    state_bytes, n_obs_env, n_lead_env = env.state_bytes_per_env, env.n_obs, env.n_lead
     g = torch.Generator(device=dev).manual_seed(1000 + rank)
     pool = []
     for _ in range(4):   # synthetic actions resident in HBM: acc ~ U(-4,2), light in {-1,+1}
@@ -234,10 +280,14 @@ def main():
     barrier()
     e2e_s = time.perf_counter() - e0
     h2d = n_envs * A * 4
-    d2h = n_envs * (env.n_obs + 2 * env.n_lead) * 4 + n_envs
+    d2h = n_envs * (n_obs_env + 2 * n_lead_env) * 4 + n_envs
 
     st = env.get_state()
     active = float((st["env_i"][:, 1] + st["env_i"][:, 2]).float().mean().item())
+    flushed = flush is not None
+    del st, env, flush, pool, act_h, obs_h
+    torch.cuda.empty_cache()
+    ppo = run_ppo(mhppo_b200, torch, dist, world, rank, dev, args.ppo_envs, args.ppo_iters) if args.ppo_envs > 0 else None
     t_dev = torch.tensor([dev_ms, e2e_s, active], dtype=torch.float64, device=dev)
     if world > 1:
         mx = t_dev.clone()
@@ -258,7 +308,7 @@ def main():
             "config": {"workload": "Env_hybrid_multi_%s nb_car=%d nb_ped=%d nb_lines=%d, %d envs/GPU, env.step with in-kernel auto-reset" % (
                 variant, nb_car, nb_ped, nb_lines, n_envs),
                 "l2": "inputs+state+outputs per step exceed no cache assumption: L2 flushed by an untimed 256 MiB memset between timed steps"
-                if flush is not None else "not flushed", "state_bytes_per_env": env.state_bytes_per_env,
+                if flushed else "not flushed", "state_bytes_per_env": state_bytes,
                 "parallelism": "env shards per rank, no data-path collective"},
             "env_steps_per_s": env_steps, "slot_agent_steps_per_s": env_steps * (C + nb_ped),
             "active_agents_per_env": active, "wall_s_timed_region": wall, "gpu_launches": int(launches),
@@ -269,9 +319,13 @@ def main():
             "e2e": {"value": world * n_envs * Ke / e2e_s * active, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": Ke, "call": "mhppo_env_step_host (pinned host buffers, H2D+kernel+D2H+sync)"},
         }
+        if ppo is not None:
+            line["ppo"] = ppo
         if not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            ns, ks = 16384, 60
+            ns = 16384
+            r0, dt0, _ = cpu_port_rate(variant, nb_car, nb_ped, nb_lines, ns, 20, threads=cores)      # calibration
+            ks = int(max(40, min(20000, 12.0 * r0 / ns)))                                            # ~12 s of CPU work
             rate, dt, act_cpu = cpu_port_rate(variant, nb_car, nb_ped, nb_lines, ns, ks, threads=cores)
             line["cpu_baseline"] = {"value": rate * act_cpu, "unit": "agent-steps/s", "cores": cores, "kind": "port",
                                     "sample": "%d envs x %d steps of the same workload, C oracle port on all host threads (%.1f s)" % (ns, ks, dt),

@@ -21,9 +21,18 @@ from .policy import Adam, Model_PPO
 from .rollout import Env_rollout
 
 
+_USE_DIST = True
+
+
+def set_distributed(on):
+    """Tests only: run a single-rank reference pass inside an initialised process group."""
+    global _USE_DIST
+    _USE_DIST = bool(on)
+
+
 def _dist():
     import torch.distributed as dist
-    return dist if (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1) else None
+    return dist if (_USE_DIST and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1) else None
 
 
 def combine_stats(stats3):

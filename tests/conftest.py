@@ -18,7 +18,7 @@ def pytest_configure(config):
 
 
 def golden_files():
-    return sorted(glob.glob(os.path.join(GOLDEN_DIR, "*_[0-9][0-9][0-9].npz")))
+    return sorted(f for f in glob.glob(os.path.join(GOLDEN_DIR, "*_[0-9][0-9][0-9].npz")) if not os.path.basename(f).startswith("ppo_"))
 
 
 def load_golden(path):
