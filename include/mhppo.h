@@ -162,15 +162,16 @@ int mhppo_returns(const float *rew_dev, const float *rl_dev, int32_t T, int64_t 
                   float *rew_d_dev, void *stream);
 
 /* Algo_PPO.train_model_c / train_model_d (PY:778-851), one epoch = value_stats -> [all-reduce] -> ppo_grad (actor),
- * ppo_grad (critic) -> [all-reduce] -> adam.  x: features [D][S]; route/want select the samples (route NULL = all). */
+ * ppo_grad (critic) -> [all-reduce] -> adam.  x: features [D][S], sample slot s = t*CN + m.  idx: int32[K], the
+ * compacted list of the (car, env) columns m routed to the net being trained (PY:489-502), NULL = all CN columns. */
 int64_t mhppo_update_workspace_bytes(int32_t n_in);
-int mhppo_value_stats(int32_t n_in, const float *x_dev, int32_t D, int64_t S, const int8_t *route_dev, int64_t CN, int32_t want,
+int mhppo_value_stats(int32_t n_in, const float *x_dev, int32_t D, int64_t S, const int32_t *idx_dev, int64_t K, int64_t CN,
                       const float *critic_dev, const float *rtg_dev, float *V_dev, double *stats3_dev, void *workspace_dev,
                       void *stream);
 /* head: 0 critic MSE, 1 Gaussian actor clipped surrogate, 2 categorical actor (with the (M,M) broadcast of PY:834-842,
  * f0/f1 = fraction of selected samples whose action is 0/1).  grad_dev: flat gradient, loss_dev: fp64 scalar. */
-int mhppo_ppo_grad(int32_t n_in, int32_t head, const float *x_dev, int32_t D, int64_t S, const int8_t *route_dev, int64_t CN,
-                   int32_t want, const float *net_dev, const float *act_dev, const float *logp_old_dev, const float *rtg_dev,
+int mhppo_ppo_grad(int32_t n_in, int32_t head, const float *x_dev, int32_t D, int64_t S, const int32_t *idx_dev, int64_t K,
+                   int64_t CN, const float *net_dev, const float *act_dev, const float *logp_old_dev, const float *rtg_dev,
                    const float *V_dev, float adv_mean, float adv_inv_std, float inv_n, float f0, float f1, float *grad_dev,
                    double *loss_dev, void *workspace_dev, void *stream);
 /* torch.optim.Adam defaults (PY:719-724); step counts from 1; grad_scale multiplies the gradient first */

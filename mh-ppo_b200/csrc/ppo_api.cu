@@ -111,12 +111,20 @@ int64_t mhppo_update_workspace_bytes(int32_t n_in) {
     return (int64_t)(sizeof(float) * (size_t)kUpdateGrid * net_params(kp) + 16 + sizeof(double) * (size_t)kUpdateGrid * 4);
 }
 
-int mhppo_value_stats(int32_t n_in, const float *x, int32_t D, int64_t S, const int8_t *route, int64_t CN, int32_t want,
+static int make_set(SampleSet &ss, const float *x, int32_t D, int64_t S, const int32_t *idx, int64_t K, int64_t CN) {
+    if (CN <= 0 || S % CN != 0) return api_fail(MHPPO_EINVAL, "S must be a multiple of CN");
+    ss.x = x; ss.D = D; ss.S = S; ss.idx = idx; ss.CN = CN; ss.K = idx ? K : CN; ss.Q = (S / CN) * ss.K;
+    if (ss.K < 0 || ss.K > CN) return api_fail(MHPPO_EINVAL, "bad selection count");
+    return 0;
+}
+
+int mhppo_value_stats(int32_t n_in, const float *x, int32_t D, int64_t S, const int32_t *idx, int64_t K, int64_t CN,
                       const float *critic, const float *rtg, float *V, double *stats3, void *workspace, void *stream) {
     if (!x || !critic || !rtg || !V || !stats3 || !workspace) return api_fail(MHPPO_EINVAL, "null argument");
     const int kp = padded_in(n_in);
     if (kp < 0 || D > kp) return api_fail(MHPPO_EUNSUPPORTED, "unsupported input width");
-    SampleSet ss; ss.x = x; ss.D = D; ss.S = S; ss.route = route; ss.CN = CN > 0 ? CN : 1; ss.want = want;
+    SampleSet ss;
+    { const int rc0 = make_set(ss, x, D, S, idx, K, CN); if (rc0) return rc0; }
     const Workspace w = carve(workspace, kp);
     cudaStream_t s = (cudaStream_t)stream;
     if (kp == 16) { SET_SMEM(k_value_stats<16>, smem_fwd<16>(1)); k_value_stats<16><<<kUpdateGrid, kMlpBlock, smem_fwd<16>(1), s>>>(ss, critic, rtg, V, w.spartial); }
@@ -130,7 +138,7 @@ int mhppo_value_stats(int32_t n_in, const float *x, int32_t D, int64_t S, const 
     return ck(cudaGetLastError(), "k_reduce_scalars");
 }
 
-int mhppo_ppo_grad(int32_t n_in, int32_t head, const float *x, int32_t D, int64_t S, const int8_t *route, int64_t CN, int32_t want,
+int mhppo_ppo_grad(int32_t n_in, int32_t head, const float *x, int32_t D, int64_t S, const int32_t *idx, int64_t K, int64_t CN,
                    const float *net, const float *act, const float *logp_old, const float *rtg, const float *V, float adv_mean,
                    float adv_inv_std, float inv_n, float f0, float f1, float *grad, double *loss, void *workspace, void *stream) {
     if (!x || !net || !rtg || !grad || !loss || !workspace) return api_fail(MHPPO_EINVAL, "null argument");
@@ -138,7 +146,8 @@ int mhppo_ppo_grad(int32_t n_in, int32_t head, const float *x, int32_t D, int64_
     if (head != 0 && (!act || !logp_old || !V)) return api_fail(MHPPO_EINVAL, "actor heads need act, logp_old and V");
     const int kp = padded_in(n_in);
     if (kp < 0 || D > kp) return api_fail(MHPPO_EUNSUPPORTED, "unsupported input width");
-    SampleSet ss; ss.x = x; ss.D = D; ss.S = S; ss.route = route; ss.CN = CN > 0 ? CN : 1; ss.want = want;
+    SampleSet ss;
+    { const int rc0 = make_set(ss, x, D, S, idx, K, CN); if (rc0) return rc0; }
     LossArgs la; la.act = act; la.logp_old = logp_old; la.rtg = rtg; la.V = V; la.adv_mean = adv_mean; la.adv_inv_std = adv_inv_std;
     la.inv_n = inv_n; la.f0 = f0; la.f1 = f1;
     const Workspace w = carve(workspace, kp);

@@ -22,13 +22,19 @@ namespace mhppo {
 struct SampleSet {
     const float *x;        // features, feature-major [D][S]
     int D;                 // real feature count (<= KP)
-    int64_t S;             // samples
-    const int8_t *route;   // [CN] or null; sample s belongs to route[s % CN]
-    int64_t CN;
-    int want;              // selected route value (0 cross, 1 wait); choice: route = exist mask, want = 1
+    int64_t S;             // sample slots in the buffers (row pitch of x)
+    const int32_t *idx;    // compacted list of the selected (car, env) columns m in [0, CN), or null = every column
+    int64_t K;             // number of selected columns (CN when idx is null)
+    int64_t CN;            // columns per time step; sample slot s = t*CN + m
+    int64_t Q;             // work items = T*K; item q -> (t = q / K, k = q % K)
 };
-__device__ __forceinline__ bool selected(const SampleSet &ss, int64_t s) {
-    return s < ss.S && (!ss.route || ss.route[s % ss.CN] == (int8_t)ss.want);
+// work item -> sample slot; false past the end.  The update walks only the samples routed to the net being
+// trained (cross or wait buffer, PY:489-502), so every lane of a tile is busy.
+__device__ __forceinline__ bool map_sample(const SampleSet &ss, int64_t q, int64_t &s) {
+    if (q >= ss.Q) return false;
+    const int64_t t = q / ss.K, k = q - t * ss.K;
+    s = t * ss.CN + (ss.idx ? (int64_t)ss.idx[k] : k);
+    return true;
 }
 
 template <int KP>
@@ -61,9 +67,9 @@ __global__ void __launch_bounds__(kMlpBlock) k_value_stats(SampleSet ss, const f
     __syncthreads();
     float *x = rows + (size_t)threadIdx.x * ROW, *a1 = x + St::X, *a2 = a1 + St::A1, *a3 = a2 + St::A2;
     double sA = 0.0, sAA = 0.0, cnt = 0.0;
-    for (int64_t base = (int64_t)blockIdx.x * kMlpBlock; base < ss.S; base += (int64_t)gridDim.x * kMlpBlock) {
-        const int64_t s = base + threadIdx.x;
-        if (selected(ss, s)) {
+    for (int64_t base = (int64_t)blockIdx.x * kMlpBlock; base < ss.Q; base += (int64_t)gridDim.x * kMlpBlock) {
+        int64_t s = 0;
+        if (map_sample(ss, base + threadIdx.x, s)) {
             load_row<KP>(ss, s, x);
             const float v = mlp_fwd_rows<KP>(sw, x, a1, a2, a3).x;
             V[s] = v;
@@ -154,9 +160,9 @@ __global__ void __launch_bounds__(kMlpBlock) k_ppo_grad(SampleSet ss, const floa
     for (int j = 0; j < 16; ++j) { g2[j] = 0.f; g3[j] = 0.f; }
     double loss = 0.0;
 
-    for (int64_t base = (int64_t)blockIdx.x * kMlpBlock; base < ss.S; base += (int64_t)gridDim.x * kMlpBlock) {
-        const int64_t s = base + tid;
-        const bool sel = selected(ss, s);
+    for (int64_t base = (int64_t)blockIdx.x * kMlpBlock; base < ss.Q; base += (int64_t)gridDim.x * kMlpBlock) {
+        int64_t s = 0;
+        const bool sel = map_sample(ss, base + tid, s);
         float dz[OP] = {0.f, 0.f, 0.f, 0.f};
         if (sel) {
             load_row<KP>(ss, s, x);

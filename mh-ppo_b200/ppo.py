@@ -82,6 +82,7 @@ class Algo_PPO:
         self._stats = torch.zeros(3, dtype=torch.float64, device=dev)
         self._loss = torch.zeros(2, dtype=torch.float64, device=dev)
         self.last_losses = {}
+        self._sel_cache = {}
 
     def _init_hyperparameters(self, hyperparameters):
         """PY:919-933."""
@@ -95,18 +96,31 @@ class Algo_PPO:
         return C.c_void_p(torch.cuda.current_stream(self.env.device).cuda_stream)
 
     # -- one epoch of train_model_c (PY:778-815) on the cross (want=0) or wait (want=1) buffer ------------------
+    def _selection(self, want):
+        """Compacted (car, env) columns routed to the cross (0) / wait (1) buffer, or the existing cars (want=None)."""
+        r = self.rollout
+        key = (r.iteration, want, r.route.data_ptr(), int(r.route._version), int(r.exist._version))
+        if self._sel_cache.get("key") != key:
+            self._sel_cache = {"key": key}
+        if want not in self._sel_cache:
+            mask = (r.exist.view(-1) != 0) if want is None else (r.route.view(-1) == want)
+            sel = torch.nonzero(mask).view(-1).to(torch.int32)
+            self._sel_cache[want] = (sel if sel.numel() else torch.zeros(1, dtype=torch.int32, device=mask.device), sel.numel())
+        return self._sel_cache[want]
+
     def train_model_c(self, actor, critic, opti_actor, opti_critic, want):
         r, L, st = self.rollout, _lib.lib(), self._stream()
         ws = self._ws.data_ptr()
-        check(L.mhppo_value_stats(13, r.obs_c.data_ptr(), 13, r.S, r.route.data_ptr(), r.M, want, critic.flat.data_ptr(),
+        idx, K = self._selection(want)                                      # K == 0 still runs (zero partials): other ranks may have samples
+        check(L.mhppo_value_stats(13, r.obs_c.data_ptr(), 13, r.S, idx.data_ptr(), K, r.M, critic.flat.data_ptr(),
                                   r.rtg.data_ptr(), r.V.data_ptr(), self._stats.data_ptr(), ws, st))
         mean, inv_std, n = combine_stats(allreduce_sum_(self._stats).cpu())
         if n < 1:
             return False                                     # PY:869/874: the net is skipped when its buffer is empty
-        check(L.mhppo_ppo_grad(13, 1, r.obs_c.data_ptr(), 13, r.S, r.route.data_ptr(), r.M, want, actor.flat.data_ptr(),
+        check(L.mhppo_ppo_grad(13, 1, r.obs_c.data_ptr(), 13, r.S, idx.data_ptr(), K, r.M, actor.flat.data_ptr(),
                                r.act.data_ptr(), r.logp.data_ptr(), r.rtg.data_ptr(), r.V.data_ptr(), mean, inv_std, 1.0 / n,
                                0.0, 0.0, actor.grad.data_ptr(), self._loss.data_ptr(), ws, st))
-        check(L.mhppo_ppo_grad(13, 0, r.obs_c.data_ptr(), 13, r.S, r.route.data_ptr(), r.M, want, critic.flat.data_ptr(),
+        check(L.mhppo_ppo_grad(13, 0, r.obs_c.data_ptr(), 13, r.S, idx.data_ptr(), K, r.M, critic.flat.data_ptr(),
                                None, None, r.rtg.data_ptr(), None, 0.0, 0.0, 1.0 / n, 0.0, 0.0, critic.grad.data_ptr(),
                                self._loss.data_ptr() + 8, ws, st))
         allreduce_sum_(actor.grad); allreduce_sum_(critic.grad)
@@ -117,7 +131,8 @@ class Algo_PPO:
     def train_model_d(self, actor, critic, opti_actor, opti_critic):
         r, L, st = self.rollout, _lib.lib(), self._stream()
         ws, D = self._ws.data_ptr(), r.shape_env_d
-        check(L.mhppo_value_stats(D, r.obs_d.data_ptr(), D, r.M, r.exist.data_ptr(), r.M, 1, critic.flat.data_ptr(),
+        idx, K = self._selection(None)
+        check(L.mhppo_value_stats(D, r.obs_d.data_ptr(), D, r.M, idx.data_ptr(), K, r.M, critic.flat.data_ptr(),
                                   r.rew_d.data_ptr(), r.V_d.data_ptr(), self._stats.data_ptr(), ws, st))
         ex = r.exist.view(-1) != 0
         cnt = torch.stack([(ex & (r.act_d == 0)).sum(), (ex & (r.act_d == 1)).sum()]).double()
@@ -126,10 +141,10 @@ class Algo_PPO:
         if n < 1:
             return False
         f0, f1 = float(cnt[0]) / n, float(cnt[1]) / n
-        check(L.mhppo_ppo_grad(D, 2, r.obs_d.data_ptr(), D, r.M, r.exist.data_ptr(), r.M, 1, actor.flat.data_ptr(),
+        check(L.mhppo_ppo_grad(D, 2, r.obs_d.data_ptr(), D, r.M, idx.data_ptr(), K, r.M, actor.flat.data_ptr(),
                                r.act_d.data_ptr(), r.logp_d.data_ptr(), r.rew_d.data_ptr(), r.V_d.data_ptr(), mean, inv_std,
                                1.0 / n, f0, f1, actor.grad.data_ptr(), self._loss.data_ptr(), ws, st))
-        check(L.mhppo_ppo_grad(D, 0, r.obs_d.data_ptr(), D, r.M, r.exist.data_ptr(), r.M, 1, critic.flat.data_ptr(),
+        check(L.mhppo_ppo_grad(D, 0, r.obs_d.data_ptr(), D, r.M, idx.data_ptr(), K, r.M, critic.flat.data_ptr(),
                                None, None, r.rew_d.data_ptr(), None, 0.0, 0.0, 1.0 / n, 0.0, 0.0, critic.grad.data_ptr(),
                                self._loss.data_ptr() + 8, ws, st))
         allreduce_sum_(actor.grad); allreduce_sum_(critic.grad)
