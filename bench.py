@@ -53,6 +53,16 @@ def algorithmic_bytes(variant, nb_car, nb_ped, nb_lines):
     return 2 * S + 8 * C_act + 8 * C + 4 * obs + 4, C, obs
 
 
+def recorded_traffic(n_envs):
+    """dram__bytes_read.sum + dram__bytes_write.sum of k_env_step from the committed ncu --set full capture."""
+    p = os.path.join(ROOT, "profiles", "round1_env_step_ncu_metrics.json")
+    try:
+        d = json.load(open(p))
+        return d["traffic_bytes_per_launch"] if int(d["n_envs"]) == int(n_envs) else None
+    except Exception:
+        return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -262,7 +272,6 @@ def main():
     wall = time.perf_counter() - wall0
     launches = mhppo_b200.launch_count() - n0
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
-    clocks = sampler.stop()
 
     # ---- end-to-end region: host buffers through the reference-facing call -------------------------
     Ke = max(8, min(K, 40))
@@ -288,6 +297,7 @@ def main():
     del st, env, flush, pool, act_h, obs_h
     torch.cuda.empty_cache()
     ppo = run_ppo(mhppo_b200, torch, dist, world, rank, dev, args.ppo_envs, args.ppo_iters) if args.ppo_envs > 0 else None
+    clocks = sampler.stop()        # sampled every 200 ms from the start of the device-timed region to the end of the PPO section
     t_dev = torch.tensor([dev_ms, e2e_s, active], dtype=torch.float64, device=dev)
     if world > 1:
         mx = t_dev.clone()
@@ -314,7 +324,8 @@ def main():
             "active_agents_per_env": active, "wall_s_timed_region": wall, "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "algorithmic_bytes_per_env_step": B, "peak_source": peak_src,
+                         "traffic": recorded_traffic(n_envs) if args.workload == "scalable_432" else None,
+                         "traffic_source": "profiles/round1_env_step_ncu_metrics.json (ncu --set full, bytes per launch)", "algorithmic_bytes_per_env_step": B, "peak_source": peak_src,
                          "kernel": "k_env_step<%s>" % variant},
             "e2e": {"value": world * n_envs * Ke / e2e_s * active, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": Ke, "call": "mhppo_env_step_host (pinned host buffers, H2D+kernel+D2H+sync)"},
