@@ -39,9 +39,9 @@ template <int KP> struct Strides { static constexpr int X = KP + 1, A1 = H1 + 1,
 
 // one dense layer for the sample owned by this thread: out[j] = b[j] + sum_k in[k] * Wt[k][j]
 // `in` is this thread's row in shared memory; Wt/b are the CTA's staged weights.
+// `out` may alias `in`: every input is read before the first output is written (the accumulators are registers).
 template <int K, int J, bool RELU>
-__device__ __forceinline__ void dense_fwd(const float *__restrict__ in, const float *__restrict__ Wt, const float *__restrict__ b,
-                                          float *__restrict__ out) {
+__device__ __forceinline__ void dense_fwd(const float *in, const float *__restrict__ Wt, const float *__restrict__ b, float *out) {
     float acc[J];
 #pragma unroll
     for (int j = 0; j < J; ++j) acc[j] = b[j];
@@ -68,6 +68,20 @@ __device__ __forceinline__ float4 mlp_fwd_rows(const float *__restrict__ sw, con
     dense_fwd<H2, H3, true>(a2, sw + off_w3(KP), sw + off_b3(KP), a3);
     float o[OP];
     dense_fwd<H3, OP, false>(a3, sw + off_w4(KP), sw + off_b4(KP), o);
+    return make_float4(o[0], o[1], o[2], o[3]);
+}
+
+// forward-only variant: ONE row of kRowFwd floats per sample, every layer computed in place (65 floats instead of 148 per
+// sample: 2 x 256-thread CTAs per SM instead of 1 x 128)
+constexpr int kRowFwd = H2 + 1;
+constexpr int kFwdBlock = 256;
+template <int KP>
+__device__ __forceinline__ float4 mlp_fwd_inplace(const float *__restrict__ sw, float *row) {
+    dense_fwd<KP, H1, true>(row, sw, sw + off_b1(KP), row);
+    dense_fwd<H1, H2, true>(row, sw + off_w2(KP), sw + off_b2(KP), row);
+    dense_fwd<H2, H3, true>(row, sw + off_w3(KP), sw + off_b3(KP), row);
+    float o[OP];
+    dense_fwd<H3, OP, false>(row, sw + off_w4(KP), sw + off_b4(KP), o);
     return make_float4(o[0], o[1], o[2], o[3]);
 }
 

@@ -15,17 +15,15 @@ static int ck(cudaError_t e, const char *what) {
     return api_fail(MHPPO_ECUDA, std::string(what) + ": " + cudaGetErrorString(e));
 }
 static int padded_in(int n_in) { return n_in <= 16 ? 16 : (n_in <= 32 ? 32 : (n_in <= 56 ? 56 : -1)); }
-constexpr int kUpdateGrid = 296;     // persistent CTAs of the update kernels: 2 per SM x 148 SMs
+constexpr int kUpdateGrid = 296;     // gradient partials of the update kernels: 148 SMs x 2 (CTAs of k_value_stats, teams of k_ppo_grad)
 
 template <int KP> static size_t smem_fwd(int nets) {
-    typedef Strides<KP> St;
-    const int ROW = (St::X + St::A1 + St::A2 + St::A3) | 1;
-    return sizeof(float) * ((size_t)nets * ((net_params(KP) + 3) & ~3) + (size_t)kMlpBlock * ROW);
+    return sizeof(float) * ((size_t)nets * ((net_params(KP) + 3) & ~3) + (size_t)kFwdBlock * kRowFwd);
 }
 template <int KP> static size_t smem_grad() {
     typedef Strides<KP> St;
     const int ROW = (St::X + St::A1 + St::A2 + St::A3 + OP) | 1;
-    return sizeof(float) * ((size_t)((net_params(KP) + 3) & ~3) + H2 * H1 + H3 * H2 + OP * H3 + (size_t)kMlpBlock * ROW);
+    return sizeof(float) * ((size_t)((net_params(KP) + 3) & ~3) + H2 * H1 + H3 * H2 + OP * H3 + (size_t)kTeams * kMlpBlock * ROW);
 }
 static RolloutDims dims_of(const mhppo_rollout_cfg *c) {
     RolloutDims d;
@@ -56,9 +54,9 @@ using namespace mhppo;
 template <int KP>
 static int launch_grad(int head, const SampleSet &ss, const float *net, const LossArgs &la, const Workspace &w, cudaStream_t s) {
     const size_t sm = smem_grad<KP>();
-    if (head == 0) { SET_SMEM((k_ppo_grad<KP, 0>), sm); k_ppo_grad<KP, 0><<<kUpdateGrid, kMlpBlock, sm, s>>>(ss, net, la, w.gpartial, w.lpartial); }
-    else if (head == 1) { SET_SMEM((k_ppo_grad<KP, 1>), sm); k_ppo_grad<KP, 1><<<kUpdateGrid, kMlpBlock, sm, s>>>(ss, net, la, w.gpartial, w.lpartial); }
-    else { SET_SMEM((k_ppo_grad<KP, 2>), sm); k_ppo_grad<KP, 2><<<kUpdateGrid, kMlpBlock, sm, s>>>(ss, net, la, w.gpartial, w.lpartial); }
+    if (head == 0) { SET_SMEM((k_ppo_grad<KP, 0>), sm); k_ppo_grad<KP, 0><<<kUpdateGrid / kTeams, kMlpBlock * kTeams, sm, s>>>(ss, net, la, w.gpartial, w.lpartial); }
+    else if (head == 1) { SET_SMEM((k_ppo_grad<KP, 1>), sm); k_ppo_grad<KP, 1><<<kUpdateGrid / kTeams, kMlpBlock * kTeams, sm, s>>>(ss, net, la, w.gpartial, w.lpartial); }
+    else { SET_SMEM((k_ppo_grad<KP, 2>), sm); k_ppo_grad<KP, 2><<<kUpdateGrid / kTeams, kMlpBlock * kTeams, sm, s>>>(ss, net, la, w.gpartial, w.lpartial); }
     api_count_launch();
     return ck(cudaGetLastError(), "k_ppo_grad");
 }
@@ -74,11 +72,11 @@ int mhppo_choice_act(const mhppo_rollout_cfg *cfg, const float *obs, const float
     const RolloutDims d = dims_of(cfg);
     const int kp = padded_in(d.D);
     if (kp < 0) return api_fail(MHPPO_EUNSUPPORTED, "choice features wider than 56 (nb_lines > 4)");
-    const dim3 grid((unsigned)((d.N + kMlpBlock - 1) / kMlpBlock), (unsigned)d.C);
+    const dim3 grid((unsigned)((d.N + kFwdBlock - 1) / kFwdBlock), (unsigned)d.C);
     cudaStream_t s = (cudaStream_t)stream;
-    if (kp == 16) { SET_SMEM(k_choice_act<16>, smem_fwd<16>(1)); k_choice_act<16><<<grid, kMlpBlock, smem_fwd<16>(1), s>>>(d, obs, net, iteration, action_d, light, obs_d, act_d, logp_d); }
-    else if (kp == 32) { SET_SMEM(k_choice_act<32>, smem_fwd<32>(1)); k_choice_act<32><<<grid, kMlpBlock, smem_fwd<32>(1), s>>>(d, obs, net, iteration, action_d, light, obs_d, act_d, logp_d); }
-    else { SET_SMEM(k_choice_act<56>, smem_fwd<56>(1)); k_choice_act<56><<<grid, kMlpBlock, smem_fwd<56>(1), s>>>(d, obs, net, iteration, action_d, light, obs_d, act_d, logp_d); }
+    if (kp == 16) { SET_SMEM(k_choice_act<16>, smem_fwd<16>(1)); k_choice_act<16><<<grid, kFwdBlock, smem_fwd<16>(1), s>>>(d, obs, net, iteration, action_d, light, obs_d, act_d, logp_d); }
+    else if (kp == 32) { SET_SMEM(k_choice_act<32>, smem_fwd<32>(1)); k_choice_act<32><<<grid, kFwdBlock, smem_fwd<32>(1), s>>>(d, obs, net, iteration, action_d, light, obs_d, act_d, logp_d); }
+    else { SET_SMEM(k_choice_act<56>, smem_fwd<56>(1)); k_choice_act<56><<<grid, kFwdBlock, smem_fwd<56>(1), s>>>(d, obs, net, iteration, action_d, light, obs_d, act_d, logp_d); }
     api_count_launch();
     return ck(cudaGetLastError(), "k_choice_act");
 }
@@ -91,9 +89,9 @@ int mhppo_policy_act(const mhppo_rollout_cfg *cfg, const float *obs, const float
     const RolloutDims d = dims_of(cfg);
     ActIO io; io.obs = obs; io.action_d = action_d; io.light = light; io.actions = actions; io.obs_c = obs_c; io.act = act;
     io.logp = logp; io.t = t; io.T = cfg->T; io.iteration = iteration;
-    const dim3 grid((unsigned)((d.N + kMlpBlock - 1) / kMlpBlock), (unsigned)d.C);
+    const dim3 grid((unsigned)((d.N + kFwdBlock - 1) / kFwdBlock), (unsigned)d.C);
     SET_SMEM(k_policy_act, smem_fwd<16>(2));
-    k_policy_act<<<grid, kMlpBlock, smem_fwd<16>(2), (cudaStream_t)stream>>>(d, net_cross, net_wait, io);
+    k_policy_act<<<grid, kFwdBlock, smem_fwd<16>(2), (cudaStream_t)stream>>>(d, net_cross, net_wait, io);
     api_count_launch();
     return ck(cudaGetLastError(), "k_policy_act");
 }
@@ -127,9 +125,9 @@ int mhppo_value_stats(int32_t n_in, const float *x, int32_t D, int64_t S, const 
     { const int rc0 = make_set(ss, x, D, S, idx, K, CN); if (rc0) return rc0; }
     const Workspace w = carve(workspace, kp);
     cudaStream_t s = (cudaStream_t)stream;
-    if (kp == 16) { SET_SMEM(k_value_stats<16>, smem_fwd<16>(1)); k_value_stats<16><<<kUpdateGrid, kMlpBlock, smem_fwd<16>(1), s>>>(ss, critic, rtg, V, w.spartial); }
-    else if (kp == 32) { SET_SMEM(k_value_stats<32>, smem_fwd<32>(1)); k_value_stats<32><<<kUpdateGrid, kMlpBlock, smem_fwd<32>(1), s>>>(ss, critic, rtg, V, w.spartial); }
-    else { SET_SMEM(k_value_stats<56>, smem_fwd<56>(1)); k_value_stats<56><<<kUpdateGrid, kMlpBlock, smem_fwd<56>(1), s>>>(ss, critic, rtg, V, w.spartial); }
+    if (kp == 16) { SET_SMEM(k_value_stats<16>, smem_fwd<16>(1)); k_value_stats<16><<<kUpdateGrid, kFwdBlock, smem_fwd<16>(1), s>>>(ss, critic, rtg, V, w.spartial); }
+    else if (kp == 32) { SET_SMEM(k_value_stats<32>, smem_fwd<32>(1)); k_value_stats<32><<<kUpdateGrid, kFwdBlock, smem_fwd<32>(1), s>>>(ss, critic, rtg, V, w.spartial); }
+    else { SET_SMEM(k_value_stats<56>, smem_fwd<56>(1)); k_value_stats<56><<<kUpdateGrid, kFwdBlock, smem_fwd<56>(1), s>>>(ss, critic, rtg, V, w.spartial); }
     api_count_launch();
     int rc = ck(cudaGetLastError(), "k_value_stats");
     if (rc) return rc;

@@ -88,20 +88,18 @@ __device__ __forceinline__ PhiloxBlock policy_block(const RolloutDims &d, int64_
 
 // ---- episode-start discrete decision (PY:400-428): thread = (env, car) -------------------------------
 template <int KP>
-__global__ void __launch_bounds__(kMlpBlock) k_choice_act(RolloutDims d, const float *__restrict__ obs, const float *__restrict__ net,
+__global__ void __launch_bounds__(kFwdBlock, 2) k_choice_act(RolloutDims d, const float *__restrict__ obs, const float *__restrict__ net,
                                                           uint32_t iteration, int8_t *__restrict__ action_d, float *__restrict__ light,
                                                           float *__restrict__ obs_d, float *__restrict__ act_d, float *__restrict__ logp_d) {
     extern __shared__ __align__(16) float smem[];
-    typedef Strides<KP> St;
     float *sw = smem;
     float *rows = smem + ((net_params(KP) + 3) & ~3);
-    constexpr int ROW = (St::X + St::A1 + St::A2 + St::A3) | 1;   // odd row stride: lane = sample is conflict-free
     stage_net<KP>(sw, net);
     __syncthreads();
-    const int64_t n = (int64_t)blockIdx.x * kMlpBlock + threadIdx.x;
+    const int64_t n = (int64_t)blockIdx.x * kFwdBlock + threadIdx.x;
     const int i = blockIdx.y;
     if (n >= d.N) return;
-    float *x = rows + (size_t)threadIdx.x * ROW, *a1 = x + St::X, *a2 = a1 + St::A1, *a3 = a2 + St::A2;
+    float *x = rows + (size_t)threadIdx.x * kRowFwd;      // one in-place row per sample (odd stride: conflict-free)
     const ObsView v{obs, d.N, n, 7 * d.C + 4, 7 * d.C};
     const float cx = v.car(i, 3);
     int best = 0; float best_a = 0.f, best_lp = 0.f; double dmin = 1000000.0;    // closest_ped_d, PY:614-627
@@ -109,7 +107,7 @@ __global__ void __launch_bounds__(kMlpBlock) k_choice_act(RolloutDims d, const f
     for (int p = 0; p < d.P; ++p) {
         for (int k = 0; k < KP; ++k) x[k] = 0.f;
         feat_d(v, d.C, i, p, x);
-        const float4 o = mlp_fwd_rows<KP>(sw, x, a1, a2, a3);
+        const float4 o = mlp_fwd_inplace<KP>(sw, x);
         const float m = fmaxf(o.x, o.y);                                          // softmax over the pair, PY:81-83
         const float e0 = expf(o.x - m), e1 = expf(o.y - m);
         const float p0 = e0 / (e0 + e1), p1 = e1 / (e0 + e1);
@@ -140,34 +138,32 @@ struct ActIO {
     int t, T; uint32_t iteration;
 };
 
-__global__ void __launch_bounds__(kMlpBlock) k_policy_act(RolloutDims d, const float *__restrict__ net_cross,
+__global__ void __launch_bounds__(kFwdBlock, 2) k_policy_act(RolloutDims d, const float *__restrict__ net_cross,
                                                           const float *__restrict__ net_wait, ActIO io) {
     constexpr int KP = 16;
     extern __shared__ __align__(16) float smem[];
-    typedef Strides<KP> St;
     constexpr int NP = (net_params(KP) + 3) & ~3;
     float *sw = smem;
     float *rows = smem + 2 * NP;
-    constexpr int ROW = (St::X + St::A1 + St::A2 + St::A3) | 1;   // odd row stride: lane = sample is conflict-free
     stage_net<KP>(sw, net_cross);
     stage_net<KP>(sw + NP, net_wait);
     __syncthreads();
-    const int64_t n = (int64_t)blockIdx.x * kMlpBlock + threadIdx.x;
+    const int64_t n = (int64_t)blockIdx.x * kFwdBlock + threadIdx.x;
     const int i = blockIdx.y;
     if (n >= d.N) return;
-    float *x = rows + (size_t)threadIdx.x * ROW, *a1 = x + St::X, *a2 = a1 + St::A1, *a3 = a2 + St::A2;
+    float *row = rows + (size_t)threadIdx.x * kRowFwd;   // one in-place row per sample (odd stride: conflict-free)
     const ObsView v{io.obs, d.N, n, 7 * d.C + 4, 7 * d.C};
     float mean = 2.0f;                                   // car_b[1,0], PY:436
-    float st[13];
-    x[13] = x[14] = x[15] = 0.f;
-    feat_c(v, i, 0, x);                                  // state_c_tensor starts as ped 0's features, PY:437
-#pragma unroll
-    for (int k = 0; k < 13; ++k) st[k] = x[k];
+    float st[13], x[13];
+    feat_c(v, i, 0, st);                                 // state_c_tensor starts as ped 0's features, PY:437
     for (int p = 0; p < d.P; ++p) {
         const bool ex = feat_c(v, i, p, x);
         if (!ex) continue;                               // PY:440
         const int sel = (io.action_d[(int64_t)(i * d.P + p) * d.N + n] <= 0) ? 0 : 1;   // cross | wait, PY:441-446
-        const float4 o = mlp_fwd_rows<KP>(sw + sel * NP, x, a1, a2, a3);
+#pragma unroll
+        for (int k = 0; k < 13; ++k) row[k] = x[k];
+        row[13] = row[14] = row[15] = 0.f;
+        const float4 o = mlp_fwd_inplace<KP>(sw + sel * NP, row);
         const float m = tanhf(o.x) * 3.0f + (-1.0f);     // head type 1, PY:88-90 (std 3, mean -1)
         mean = fminf(mean, m);
         if (m == mean) {                                 // PY:449-450 (ties: the later pedestrian)

@@ -43,41 +43,43 @@ __device__ __forceinline__ void load_row(const SampleSet &ss, int64_t s, float *
     for (int k = 0; k < KP; ++k) x[k] = (k < ss.D) ? ss.x[(int64_t)k * ss.S + s] : 0.f;
 }
 
-__device__ __forceinline__ double block_sum(double v, double *red) {
+// sum over a team of `nthreads` consecutive threads (a whole CTA, or one 128-thread team of it synchronising on its own
+// named barrier `bar`); the result is valid in the team's first thread
+__device__ __forceinline__ void team_sync(int bar, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(bar), "r"(nthreads) : "memory"); }
+__device__ __forceinline__ double team_sum(double v, double *red, int ltid, int nthreads, int bar) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-    __syncthreads();
+    if ((ltid & 31) == 0) red[ltid >> 5] = v;
+    team_sync(bar, nthreads);
     double r = 0.0;
-    if (threadIdx.x == 0) for (int w = 0; w < kMlpBlock / 32; ++w) r += red[w];
-    __syncthreads();
-    return r;   // valid in thread 0
+    if (ltid == 0) for (int w = 0; w < nthreads / 32; ++w) r += red[w];
+    team_sync(bar, nthreads);
+    return r;
 }
 
 // ---- 1. critic forward + advantage statistics --------------------------------------------------------
 template <int KP>
-__global__ void __launch_bounds__(kMlpBlock) k_value_stats(SampleSet ss, const float *__restrict__ critic, const float *__restrict__ rtg,
+__global__ void __launch_bounds__(kFwdBlock, 2) k_value_stats(SampleSet ss, const float *__restrict__ critic, const float *__restrict__ rtg,
                                                            float *__restrict__ V, double *__restrict__ partial /* [grid][3] */) {
     extern __shared__ __align__(16) float smem[];
-    typedef Strides<KP> St;
     float *sw = smem;
     float *rows = smem + ((net_params(KP) + 3) & ~3);
-    constexpr int ROW = (St::X + St::A1 + St::A2 + St::A3) | 1;   // odd row stride: lane = sample is conflict-free
-    __shared__ double red[kMlpBlock / 32];
+    __shared__ double red[kFwdBlock / 32];
     stage_net<KP>(sw, critic);
     __syncthreads();
-    float *x = rows + (size_t)threadIdx.x * ROW, *a1 = x + St::X, *a2 = a1 + St::A1, *a3 = a2 + St::A2;
+    float *x = rows + (size_t)threadIdx.x * kRowFwd;      // one in-place row per sample
     double sA = 0.0, sAA = 0.0, cnt = 0.0;
-    for (int64_t base = (int64_t)blockIdx.x * kMlpBlock; base < ss.Q; base += (int64_t)gridDim.x * kMlpBlock) {
+    for (int64_t base = (int64_t)blockIdx.x * kFwdBlock; base < ss.Q; base += (int64_t)gridDim.x * kFwdBlock) {
         int64_t s = 0;
         if (map_sample(ss, base + threadIdx.x, s)) {
             load_row<KP>(ss, s, x);
-            const float v = mlp_fwd_rows<KP>(sw, x, a1, a2, a3).x;
+            const float v = mlp_fwd_inplace<KP>(sw, x).x;
             V[s] = v;
             const double A = (double)(rtg[s] - v);          // advantage_batch = rtgs - V, fp32 like torch (PY:786)
             sA += A; sAA += A * A; cnt += 1.0;
         }
     }
-    const double t0 = block_sum(sA, red), t1 = block_sum(sAA, red), t2 = block_sum(cnt, red);
+    const double t0 = team_sum(sA, red, threadIdx.x, kFwdBlock, 0), t1 = team_sum(sAA, red, threadIdx.x, kFwdBlock, 0),
+                 t2 = team_sum(cnt, red, threadIdx.x, kFwdBlock, 0);
     if (threadIdx.x == 0) { partial[blockIdx.x * 3 + 0] = t0; partial[blockIdx.x * 3 + 1] = t1; partial[blockIdx.x * 3 + 2] = t2; }
 }
 
@@ -125,8 +127,12 @@ __device__ __forceinline__ void wgrad_strip(float (&acc)[NJ], const float *__res
 }
 
 // HEAD: 0 = critic (MSE), 1 = Gaussian actor (clipped surrogate), 2 = categorical actor with the (M,M) broadcast
+// A CTA holds kTeams independent 128-thread teams that share the staged weights; each team walks its own tiles and
+// synchronises on its own named barrier, so two tiles are in flight per SM (shared memory allows one 128-row tile set
+// per team, registers allow 256 threads).
+constexpr int kTeams = 1;
 template <int KP, int HEAD>
-__global__ void __launch_bounds__(kMlpBlock) k_ppo_grad(SampleSet ss, const float *__restrict__ net, LossArgs la,
+__global__ void __launch_bounds__(kMlpBlock * kTeams) k_ppo_grad(SampleSet ss, const float *__restrict__ net, LossArgs la,
                                                         float *__restrict__ gpartial /* [grid][net_params] */,
                                                         double *__restrict__ lpartial /* [grid] */) {
     extern __shared__ __align__(16) float smem[];
@@ -138,15 +144,19 @@ __global__ void __launch_bounds__(kMlpBlock) k_ppo_grad(SampleSet ss, const floa
     float *W4 = W3 + H3 * H2;                          // [OP][H3]
     float *rows = W4 + OP * H3;
     constexpr int ROW = (St::X + St::A1 + St::A2 + St::A3 + OP) | 1;   // odd row stride: lane = sample is conflict-free
-    __shared__ double red[kMlpBlock / 32];
+    __shared__ double red_all[kTeams][kMlpBlock / 32];
     stage_net<KP>(sw, net);
     __syncthreads();
-    for (int i = threadIdx.x; i < H1 * H2; i += kMlpBlock) { const int k = i / H2, j = i % H2; W2[j * H1 + k] = sw[off_w2(KP) + i]; }
-    for (int i = threadIdx.x; i < H2 * H3; i += kMlpBlock) { const int k = i / H3, j = i % H3; W3[j * H2 + k] = sw[off_w3(KP) + i]; }
-    for (int i = threadIdx.x; i < H3 * OP; i += kMlpBlock) { const int k = i / OP, j = i % OP; W4[j * H3 + k] = sw[off_w4(KP) + i]; }
+    for (int i = threadIdx.x; i < H1 * H2; i += blockDim.x) { const int k = i / H2, j = i % H2; W2[j * H1 + k] = sw[off_w2(KP) + i]; }
+    for (int i = threadIdx.x; i < H2 * H3; i += blockDim.x) { const int k = i / H3, j = i % H3; W3[j * H2 + k] = sw[off_w3(KP) + i]; }
+    for (int i = threadIdx.x; i < H3 * OP; i += blockDim.x) { const int k = i / OP, j = i % OP; W4[j * H3 + k] = sw[off_w4(KP) + i]; }
     __syncthreads();
 
-    const int tid = threadIdx.x;
+    const int team = threadIdx.x / kMlpBlock, tid = threadIdx.x % kMlpBlock, bar = team + 1;
+    const int unit = blockIdx.x * kTeams + team, nunits = gridDim.x * kTeams;
+    rows += (size_t)team * kMlpBlock * ROW;
+    double *red = red_all[team];
+#define TEAM_SYNC() team_sync(bar, kMlpBlock)
     float *x = rows + (size_t)tid * ROW, *a1 = x + St::X, *a2 = a1 + St::A1, *a3 = a2 + St::A2, *d4 = a3 + St::A3;
     // weight-gradient strips of this thread (persist over all tiles of this CTA)
     constexpr int NJ1 = (KP <= 16) ? 4 : ((KP <= 32) ? 8 : 16);
@@ -160,7 +170,7 @@ __global__ void __launch_bounds__(kMlpBlock) k_ppo_grad(SampleSet ss, const floa
     for (int j = 0; j < 16; ++j) { g2[j] = 0.f; g3[j] = 0.f; }
     double loss = 0.0;
 
-    for (int64_t base = (int64_t)blockIdx.x * kMlpBlock; base < ss.Q; base += (int64_t)gridDim.x * kMlpBlock) {
+    for (int64_t base = (int64_t)unit * kMlpBlock; base < ss.Q; base += (int64_t)nunits * kMlpBlock) {
         int64_t s = 0;
         const bool sel = map_sample(ss, base + tid, s);
         float dz[OP] = {0.f, 0.f, 0.f, 0.f};
@@ -212,7 +222,7 @@ __global__ void __launch_bounds__(kMlpBlock) k_ppo_grad(SampleSet ss, const floa
         }
 #pragma unroll
         for (int j = 0; j < OP; ++j) d4[j] = dz[j];
-        __syncthreads();
+        TEAM_SYNC();
         // layer-4 weight / bias gradient: thread (k = tid % 32, j = tid / 32), 32*4 = 128 entries
         {
             const int kk = tid & 31, j = tid >> 5;
@@ -225,17 +235,17 @@ __global__ void __launch_bounds__(kMlpBlock) k_ppo_grad(SampleSet ss, const floa
             g4 += acc;
             if (kk == 0) gb += accb;          // b4[j]
         }
-        __syncthreads();
+        TEAM_SYNC();
         dense_bwd_data<H3, OP>(a3, d4, W4);                            // a3 now holds delta3
-        __syncthreads();
+        TEAM_SYNC();
         wgrad_strip<16>(g3, rows + St::X + St::A1, ROW, tid & 63, rows + St::X + St::A1 + St::A2, ROW, (tid >> 6) * 16, true);   // dW3t[k<64][j<32]
-        __syncthreads();
+        TEAM_SYNC();
         dense_bwd_data<H2, H3>(a2, a3, W3);                            // a2 now holds delta2
-        __syncthreads();
+        TEAM_SYNC();
         wgrad_strip<16>(g2, rows + St::X, ROW, tid & 31, rows + St::X + St::A1, ROW, (tid >> 5) * 16, true);                      // dW2t[k<32][j<64]
-        __syncthreads();
+        TEAM_SYNC();
         dense_bwd_data<H1, H2>(a1, a2, W2);                            // a1 now holds delta1
-        __syncthreads();
+        TEAM_SYNC();
         wgrad_strip<NJ1>(g1, rows, ROW, tid % KK1, rows + St::X, ROW, (tid / KK1) * NJ1, (tid % KK1) < KP);                        // dW1t[k<KP][j<32]
         // bias gradients b3, b2, b1: the deltas now sit in a3, a2, a1 of every row
         {
@@ -244,9 +254,9 @@ __global__ void __launch_bounds__(kMlpBlock) k_ppo_grad(SampleSet ss, const floa
             for (int s2 = 0; s2 < kMlpBlock; ++s2) acc += rows[s2 * ROW + bias_off];
             gbias += acc;
         }
-        __syncthreads();
+        TEAM_SYNC();
     }
-    float *gp = gpartial + (size_t)blockIdx.x * NPAR;
+    float *gp = gpartial + (size_t)unit * NPAR;
     {
         const int kk = tid % KK1, j0 = (tid / KK1) * NJ1;
         if (kk < KP)
@@ -269,8 +279,9 @@ __global__ void __launch_bounds__(kMlpBlock) k_ppo_grad(SampleSet ss, const floa
         if (kk == 0) gp[off_b4(KP) + j] = gb;
     }
     gp[(tid < 32) ? (off_b3(KP) + tid) : ((tid < 96) ? (off_b2(KP) + tid - 32) : (off_b1(KP) + tid - 96))] = gbias;
-    const double lt = block_sum(loss, red);
-    if (tid == 0) lpartial[blockIdx.x] = lt;
+    const double lt = team_sum(loss, red, tid, kMlpBlock, bar);
+    if (tid == 0) lpartial[unit] = lt;
+#undef TEAM_SYNC
 }
 
 // ---- 4. deterministic reduction of the per-CTA partials ----------------------------------------------
