@@ -178,6 +178,10 @@ int mhppo_ppo_grad(int32_t n_in, int32_t head, const float *x_dev, int32_t D, in
 int mhppo_adam(float *param_dev, const float *grad_dev, float *m_dev, float *v_dev, int32_t n, float lr, float beta1,
                float beta2, float eps, int32_t step, float grad_scale, void *stream);
 
+/* Self-test of the tcgen05 / TMEM building blocks behind the policy GEMMs: D[128,N] = A[128,K] * B[N,K]^T on one CTA,
+ * mode 0 = one tf32 pass, mode 1 = 3xTF32 split accumulation.  (N,K) in {(64,32),(32,64),(64,16),(16,32)}. */
+int mhppo_tc_selftest(const float *A_dev, const float *B_dev, float *D_dev, int32_t N, int32_t K, int32_t mode, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
