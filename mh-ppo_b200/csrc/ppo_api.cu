@@ -6,6 +6,8 @@
 #include "../../include/mhppo.h"
 #include "ppo_rollout.cuh"
 #include "ppo_update.cuh"
+#include "tc_kernels.cuh"
+#include <cstdlib>
 
 namespace mhppo {
 int api_fail(int code, const std::string &msg);      // mhppo_api.cu
@@ -15,6 +17,20 @@ static int ck(cudaError_t e, const char *what) {
     return api_fail(MHPPO_ECUDA, std::string(what) + ": " + cudaGetErrorString(e));
 }
 static int padded_in(int n_in) { return n_in <= 16 ? 16 : (n_in <= 32 ? 32 : (n_in <= 56 ? 56 : -1)); }
+// Which implementation serves the 13-input nets' forward-only kernels (mhppo_set_mlp_mode):
+//   0 auto : tcgen05 for the critic forward of the update (faster), FFMA for the rollout's per-step inference (the
+//            tensor-core version of that kernel is latency-bound with one tile in flight per CTA, DESIGN.md "Kernels")
+//   1 ffma : exact-fp32 CUDA-core kernels everywhere (cross-check)      2 tc : tcgen05 wherever a kernel exists
+static int g_mlp_mode = []() { const char *e = std::getenv("MHPPO_MLP"); return (e && std::string(e) == "ffma") ? 1 : ((e && std::string(e) == "tc") ? 2 : 0); }();
+static bool use_tc(bool rollout) { return g_mlp_mode == 2 || (g_mlp_mode == 0 && !rollout); }
+static int *fail_flag() {
+    static int *p = nullptr;
+    if (!p) { cudaMalloc(&p, sizeof(int)); cudaMemset(p, 0, sizeof(int)); }
+    return p;
+}
+static size_t smem_tc(int nets) {
+    return sizeof(float) * ((size_t)nets * ((tcm::NetTiles<16>::FLOATS + 255) & ~255) + 2 * 128 * H2) + 1024;
+}
 constexpr int kUpdateGrid = 296;     // gradient partials of the update kernels: 148 SMs x 2 (CTAs of k_value_stats, teams of k_ppo_grad)
 
 template <int KP> static size_t smem_fwd(int nets) {
@@ -89,6 +105,13 @@ int mhppo_policy_act(const mhppo_rollout_cfg *cfg, const float *obs, const float
     const RolloutDims d = dims_of(cfg);
     ActIO io; io.obs = obs; io.action_d = action_d; io.light = light; io.actions = actions; io.obs_c = obs_c; io.act = act;
     io.logp = logp; io.t = t; io.T = cfg->T; io.iteration = iteration;
+    if (use_tc(true)) {
+        const dim3 g2((unsigned)((d.N + 127) / 128), (unsigned)d.C);
+        SET_SMEM(k_policy_act_tc, smem_tc(2));
+        k_policy_act_tc<<<g2, 128, smem_tc(2), (cudaStream_t)stream>>>(d, net_cross, net_wait, io, fail_flag());
+        api_count_launch();
+        return ck(cudaGetLastError(), "k_policy_act_tc");
+    }
     const dim3 grid((unsigned)((d.N + kFwdBlock - 1) / kFwdBlock), (unsigned)d.C);
     SET_SMEM(k_policy_act, smem_fwd<16>(2));
     k_policy_act<<<grid, kFwdBlock, smem_fwd<16>(2), (cudaStream_t)stream>>>(d, net_cross, net_wait, io);
@@ -101,6 +124,18 @@ int mhppo_returns(const float *rew, const float *rl, int32_t T, int64_t CN, doub
     k_returns<<<(unsigned)((CN + 255) / 256), 256, 0, (cudaStream_t)stream>>>(rew, rl, T, CN, gamma, rtg, rew_d);
     api_count_launch();
     return ck(cudaGetLastError(), "k_returns");
+}
+
+int mhppo_set_mlp_mode(int32_t mode) {
+    if (mode < 0 || mode > 2) return api_fail(MHPPO_EINVAL, "mode must be 0 (auto), 1 (ffma) or 2 (tc)");
+    g_mlp_mode = mode;
+    return 0;
+}
+
+int mhppo_tc_failures(void) {      /* 1 if any tensor-core kernel timed out waiting for its MMAs (should never happen) */
+    int v = 0;
+    cudaMemcpy(&v, fail_flag(), sizeof(int), cudaMemcpyDeviceToHost);
+    return v;
 }
 
 int64_t mhppo_update_workspace_bytes(int32_t n_in) {
@@ -125,7 +160,8 @@ int mhppo_value_stats(int32_t n_in, const float *x, int32_t D, int64_t S, const 
     { const int rc0 = make_set(ss, x, D, S, idx, K, CN); if (rc0) return rc0; }
     const Workspace w = carve(workspace, kp);
     cudaStream_t s = (cudaStream_t)stream;
-    if (kp == 16) { SET_SMEM(k_value_stats<16>, smem_fwd<16>(1)); k_value_stats<16><<<kUpdateGrid, kFwdBlock, smem_fwd<16>(1), s>>>(ss, critic, rtg, V, w.spartial); }
+    if (kp == 16 && use_tc(false)) { SET_SMEM(k_value_stats_tc, smem_tc(1)); k_value_stats_tc<<<kUpdateGrid, 128, smem_tc(1), s>>>(ss, critic, rtg, V, w.spartial, fail_flag()); }
+    else if (kp == 16) { SET_SMEM(k_value_stats<16>, smem_fwd<16>(1)); k_value_stats<16><<<kUpdateGrid, kFwdBlock, smem_fwd<16>(1), s>>>(ss, critic, rtg, V, w.spartial); }
     else if (kp == 32) { SET_SMEM(k_value_stats<32>, smem_fwd<32>(1)); k_value_stats<32><<<kUpdateGrid, kFwdBlock, smem_fwd<32>(1), s>>>(ss, critic, rtg, V, w.spartial); }
     else { SET_SMEM(k_value_stats<56>, smem_fwd<56>(1)); k_value_stats<56><<<kUpdateGrid, kFwdBlock, smem_fwd<56>(1), s>>>(ss, critic, rtg, V, w.spartial); }
     api_count_launch();

@@ -17,11 +17,16 @@ def _sd(z, prefix):
     return {k[len(prefix) + 1:]: torch.as_tensor(z[k]) for k in z.files if k.startswith(prefix + ".")}
 
 
-@pytest.fixture(scope="module")
-def mh():
+@pytest.fixture(scope="module", params=["auto", "ffma", "tc"])
+def mh(request):
+    """Every test runs with the three implementations of the 13-input nets' forward kernels (mhppo_set_mlp_mode)."""
     assert torch.cuda.is_available()
     import mhppo_b200
-    return mhppo_b200
+    mhppo_b200._lib.check(mhppo_b200.lib().mhppo_set_mlp_mode({"auto": 0, "ffma": 1, "tc": 2}[request.param]))
+    mhppo_b200.mlp_mode = request.param
+    yield mhppo_b200
+    assert mhppo_b200.lib().mhppo_tc_failures() == 0
+    mhppo_b200.lib().mhppo_set_mlp_mode(0)
 
 
 def _algo(mh, N, seed, env_id0, z=None):
@@ -85,12 +90,21 @@ def test_rollout_matches_oracle_batch(mh, oracle_mod):
     np.testing.assert_allclose(r.obs_d.view(-1, C, N).cpu().numpy(), b["obs_d"].transpose(2, 0, 1), rtol=1e-5, atol=1e-5)
     # 80 free-running steps: fp32 summation-order differences of the MLP (1e-7) feed back through the env, and features
     # such as dist_start are differences of O(3) quantities, so a handful of near-zero entries move by ~1e-4 absolute
-    np.testing.assert_allclose(r.obs_c.view(13, T, C, N).cpu().numpy(), b["obs_c"].transpose(3, 0, 1, 2), rtol=1e-4, atol=5e-4)
-    np.testing.assert_allclose(r.act.view(T, C, N).cpu().numpy(), b["act"], rtol=1e-4, atol=5e-4)
-    np.testing.assert_allclose(r.logp.view(T, C, N).cpu().numpy(), b["logp"], rtol=1e-4, atol=5e-4)
-    np.testing.assert_allclose(r.rew.view(T, C, N).cpu().numpy(), b["rew"], rtol=1e-4, atol=5e-4)
-    np.testing.assert_allclose(r.rew_d.view(C, N).cpu().numpy(), b["rew_d"], rtol=1e-4, atol=1e-6)
-    np.testing.assert_allclose(r.rtg.view(T, C, N).cpu().numpy(), PO.reward_to_go(b["rew"]), rtol=1e-4, atol=5e-3)
+    # The stored state is the feature vector of the arg-min pedestrian (PY:448-450).  When two pedestrians' means tie to
+    # within fp32 rounding (typically both saturated at tanh = 1 -> mean 2.0) the reference's own pick is rounding noise,
+    # so a sample whose stored features belong to the other pedestrian is tolerated if its mean/action agree; such
+    # samples must stay rare.
+    oc, ob = r.obs_c.view(13, T, C, N).cpu().numpy(), b["obs_c"].transpose(3, 0, 1, 2)
+    bad = (np.abs(oc - ob) > 5e-4 + 1e-4 * np.abs(ob)).any(axis=0)
+    assert bad.mean() < 1e-3, bad.mean()
+    # 3xTF32 carries ~5e-7 of the LARGEST product of a dot product; an absent car's placeholder row has x = -1000
+    # (SC:654), so its features reach 1e3 and its (never trained on) mean moves by ~1e-3 in the tensor-core rollout
+    tol = dict(rtol=1e-4, atol=5e-4) if mh.mlp_mode != "tc" else dict(rtol=2e-3, atol=5e-3)
+    np.testing.assert_allclose(r.act.view(T, C, N).cpu().numpy(), b["act"], **tol)
+    np.testing.assert_allclose(r.logp.view(T, C, N).cpu().numpy(), b["logp"], **tol)
+    np.testing.assert_allclose(r.rew.view(T, C, N).cpu().numpy(), b["rew"], **tol)
+    np.testing.assert_allclose(r.rew_d.view(C, N).cpu().numpy(), b["rew_d"], rtol=tol["rtol"], atol=1e-6 if mh.mlp_mode != "tc" else 5e-3)
+    np.testing.assert_allclose(r.rtg.view(T, C, N).cpu().numpy(), PO.reward_to_go(b["rew"]), rtol=1e-4 if mh.mlp_mode != "tc" else 2e-3, atol=5e-3 if mh.mlp_mode != "tc" else 5e-2)
 
 
 def test_returns_kernel(mh):
