@@ -25,9 +25,13 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, int K) {
     const uint64_t lbo = 128 >> 4, sbo = (uint64_t)(K * 32) >> 4;
     return (uint64_t)((saddr & 0x3FFFF) >> 4) | (lbo << 16) | (sbo << 32) | (1ull << 46);
 }
-// 32-bit instruction descriptor for kind::tf32, fp32 accumulate, both operands K-major
-__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
-    return (1u << 4) /* D = f32 */ | (2u << 7) /* A = tf32 */ | (2u << 10) /* B = tf32 */ | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// Note (measured, round 1): reading these tiles transposed through MN-major descriptors does NOT work for tf32 -- the only
+// MN-major shared-memory layout the tensor core accepts for 32-bit operands is the 128B_BASE32B swizzle, so the
+// weight-gradient GEMM (reduction over samples) needs its own feature-contiguous swizzled tiles (DESIGN.md "Next").
+// 32-bit instruction descriptor for kind::tf32, fp32 accumulate; a_mn / b_mn: operand is MN-major instead of K-major
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, bool a_mn = false, bool b_mn = false) {
+    return (1u << 4) /* D = f32 */ | (2u << 7) /* A = tf32 */ | (2u << 10) /* B = tf32 */ | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 __device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols) {     // one full warp
