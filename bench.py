@@ -296,7 +296,7 @@ def main():
     flushed = flush is not None
     del st, env, flush, pool, act_h, obs_h
     torch.cuda.empty_cache()
-    ppo = run_ppo(mhppo_b200, torch, dist, world, rank, dev, args.ppo_envs, args.ppo_iters) if args.ppo_envs > 0 else None
+    ppo = run_ppo(mhppo_b200, torch, dist, world, rank, dev, args.ppo_envs, args.ppo_iters) if args.ppo_envs > 0 and args.ppo_iters > 0 else None
     clocks = sampler.stop()        # sampled every 200 ms from the start of the device-timed region to the end of the PPO section
     t_dev = torch.tensor([dev_ms, e2e_s, active], dtype=torch.float64, device=dev)
     if world > 1:

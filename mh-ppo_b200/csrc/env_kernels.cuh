@@ -15,16 +15,28 @@ namespace mhppo {
 
 constexpr int kEnvBlock = 128;
 #ifndef MH_ENV_MIN_BLOCKS
-#define MH_ENV_MIN_BLOCKS 3
+#define MH_ENV_MIN_BLOCKS 4
 #endif
-constexpr int kEnvMinBlocks = MH_ENV_MIN_BLOCKS;   // 3 -> register cap 168/thread, 12 warps/SM
+constexpr int kEnvMinBlocks = MH_ENV_MIN_BLOCKS;   // CTAs per SM the register allocation is capped for
+
+// dynamic shared memory of the step kernel: the CTA's car slots and one gap queue per warp
+template <int MC>
+struct StepShared {
+    CarSlots<MC, kEnvBlock> cars;
+    GapQueue queues[kEnvBlock / 32];
+};
 
 template <int V, int MC, int MP>
 __global__ void __launch_bounds__(kEnvBlock, kEnvMinBlocks) k_env_step(const __grid_constant__ EnvArena a, const __grid_constant__ EnvConst c,
                                                                            const __grid_constant__ RngKey key, const __grid_constant__ StepIO io) {
+    extern __shared__ __align__(16) unsigned char step_smem[];
+    StepShared<MC> &sh = *reinterpret_cast<StepShared<MC> *>(step_smem);
     const int64_t n = (int64_t)blockIdx.x * kEnvBlock + threadIdx.x;
+    WarpCtx w;
+    w.mask = __ballot_sync(0xFFFFFFFFu, n < a.N);           // the last warp may own fewer than 32 envs
+    w.q = &sh.queues[threadIdx.x >> 5];
     if (n >= a.N) return;
-    env_step_thread<V, MC, MP>(a, c, key, io, n);
+    env_step_thread<V, MC, MP, kEnvBlock>(a, c, key, io, n, w, sh.cars, (int)threadIdx.x);
 }
 
 template <int V, int MC, int MP>
@@ -42,12 +54,12 @@ __global__ void __launch_bounds__(kEnvBlock) k_env_reset(const __grid_constant__
 
 // ---- instantiation table -----------------------------------------------------------------------
 struct EnvKernelEntry {
-    int variant, mc, mp;
+    int variant, mc, mp, step_smem;
     void (*step)(EnvArena, EnvConst, RngKey, StepIO);
     void (*reset)(EnvArena, EnvConst, RngKey, const uint8_t *, mhppo_view);
 };
 
-#define MHPPO_ENV_ENTRY(V, MC, MP) { V, MC, MP, k_env_step<V, MC, MP>, k_env_reset<V, MC, MP> }
+#define MHPPO_ENV_ENTRY(V, MC, MP) { V, MC, MP, (int)sizeof(StepShared<MC>), k_env_step<V, MC, MP>, k_env_reset<V, MC, MP> }
 
 // each env_inst_*.cu defines one of these
 const EnvKernelEntry *env_table_stop(int *n);

@@ -3,20 +3,24 @@
 // Replaces Crosswalk_hybrid_multi_*.step (SC:789-878 and siblings) + in-kernel auto-reset.
 //
 // Shape of the computation (chosen for the SM, not copied from the Python control flow):
-//  * cars live in registers (slots fully unrolled); pedestrians are STREAMED: one rolled loop
-//    loads pedestrian j from HBM, runs its state machine, its danger detection against every car,
-//    its contribution to the wait rewards and its observation row, and stores it back.  The
-//    reference runs these as four separate passes over all pedestrians (SC:808-809, 841-846,
-//    849-858, 869); the passes only communicate through per-car running min/max and per-pedestrian
-//    fields, so interleaving them per pedestrian is exactly equivalent (DESIGN.md "Step kernel").
-//    It keeps one pedestrian in registers instead of P, and the hot loop body exists once in SASS
-//    (the first version unrolled everything: 28k instructions, instruction-fetch bound).
-//  * bulky paths are single out-of-line copies: the sin walking profile (fp64 sincos), the
+//  * the kernel is bound by instruction issue, not by HBM: ~8k mostly-fp64 instructions per env
+//    step against 976 bytes.  What limits the issue rate is (a) how many warps an SM can hold
+//    (registers) and (b) how much SASS a warp walks per step (instruction-cache misses were the
+//    second-largest stall of the unrolled versions, profiles/round1_env_step_r1d_summary.txt).
+//    So the CARS of a CTA live in shared memory ([field][slot][thread], conflict-free) and every
+//    loop over cars is ROLLED: one copy of each (pedestrian, car) body in SASS, few live
+//    registers, 5 CTAs per SM instead of 3;
+//  * pedestrians are STREAMED: one rolled loop loads pedestrian j from HBM, runs its state
+//    machine, its danger detection against every car, its contribution to the wait rewards and
+//    its observation row, and stores it back.  The reference runs these as four separate passes
+//    over all pedestrians (SC:808-809, 841-846, 849-858, 869); the passes only communicate through
+//    per-car running min/max and per-pedestrian fields, so interleaving them per pedestrian is
+//    exactly equivalent (DESIGN.md "Step kernel");
+//  * bulky rare paths are single out-of-line copies: the sin walking profile (fp64 sincos), the
 //    episode reset, and the exact fp64 critical gap.  The gap-acceptance decision
 //    `choix_pedestrian` runs every step for a waiting pedestrian, so its log10/pow/normal-draw
-//    comparison is a filtered predicate: fp32 with an error bound, fp64 only when undecidable.
-//  * geometry predicates is_in_front / is_crossing_in_front are evaluated once per (ped, car)
-//    into bit masks and reused by detection, rewards and the observation.
+//    comparison is a filtered predicate (fp32 with an error bound, fp64 only when undecidable), and
+//    the judgements of all lanes of a warp are evaluated side by side (choix_coop);
 //  * reward-shaping exponentials feed only fp32 outputs: their argument is formed in fp64 and the
 //    exponential itself is exp2f (DESIGN.md "Precision"); everything that feeds state or a
 //    threshold stays fp64 in the reference's operation order.
@@ -51,84 +55,176 @@ static MH_NOINLINE double cg_exact(double v0y, int gender, int age, double size,
 
 // `car_time + light < CG` of SC:167-170, bit-exact at fp32 cost: the comparison is first evaluated
 // in fp32 with a conservative error bound (filtered predicate); only an undecidable case recomputes
-// both sides in fp64 exactly as the reference does.  One Philox block per call, like CG_score.
-// Returns (new_ctr << 1) | refused.  Out of line (one copy): a few of these run per waiting pedestrian.
-static MH_NOINLINE uint64_t gap_refused_ol(double Spx, double v0y, int dlines, int gender, int age, bool crossing,
-                                           double Sc, double Vc, double light, double cross, Rng rng) {
-    const double dx = Sc - Spx, vden = Vc + 10e-3;
-    bool refused;
-    if (!crossing) refused = (fabs(dx / vden) + light) < 0.0;                        // CG = 0., no draw (SC:427-428)
-    else {
-        const PhiloxBlock b = rng.next();
-        const double u1 = u53(b.w0, b.w1), u2 = u53(b.w2, b.w3);
-        const double size = fabs((double)dlines) * cross;
-        const double pden = fabs(v0y + 10e-3);
-        // fp32 estimate: CG = size/|v0y+.01| * 10^(0.09 + gender/age terms + 0.09*z)
-        const float adj = 0.09f + ((gender == 1) ? 0.0369f : 0.f) + ((age == 0) ? -0.0355f : ((age == 1) ? -0.0221f : -0.1810f));
+// both sides in fp64 exactly as the reference does.  `ctr` is the Philox block of this decision's
+// normal draw (one block per CG_score call).  Out of line: one copy, two callers.
+static MH_NOINLINE bool gap_eval(double dx, double vden, double light, double size, double v0y, int gender, int age,
+                                 uint32_t ctr, uint32_t env_lo, uint32_t env_hi, uint32_t k0, uint32_t k1) {
+    const PhiloxBlock b = philox4x32_10(ctr, 0u, env_lo, env_hi, k0, k1);
+    const double u1 = u53(b.w0, b.w1), u2 = u53(b.w2, b.w3);
+    const double pden = fabs(v0y + 10e-3);
+    // fp32 estimate: CG = size/|v0y+.01| * 10^(0.09 + gender/age terms + 0.09*z)
+    const float adj = 0.09f + ((gender == 1) ? 0.0369f : 0.f) + ((age == 0) ? -0.0355f : ((age == 1) ? -0.0221f : -0.1810f));
 #ifdef __CUDA_ARCH__
-        const float cz = cospif(2.0f * (float)u2);
+    const float cz = cospif(2.0f * (float)u2);
 #else
-        const float cz = cosf(6.2831853f * (float)u2);
+    const float cz = cosf(6.2831853f * (float)u2);
 #endif
-        const float z = sqrtf(-2.0f * logf((float)(1.0 - u1))) * cz;
-        const float cg = ((float)size / (float)pden) * exp2f(3.3219280948873623f * (adj + 0.09f * z));
-        const float lhs = fabsf((float)dx / (float)vden) + (float)light;
-        const float tol = 2e-4f * (fabsf(lhs) + cg) + 1e-30f;
-        if (fabsf(lhs - cg) > tol) refused = lhs < cg;
-        else refused = (fabs(dx / vden) + light) < cg_exact(v0y, gender, age, size, u1, u2);
-    }
-    return ((uint64_t)rng.ctr << 1) | (refused ? 1u : 0u);
+    const float z = sqrtf(-2.0f * logf((float)(1.0 - u1))) * cz;
+    const float cg = ((float)size / (float)pden) * exp2f(3.3219280948873623f * (adj + 0.09f * z));
+    const float lhs = fabsf((float)dx / (float)vden) + (float)light;
+    const float tol = 2e-4f * (fabsf(lhs) + cg) + 1e-30f;
+    if (fabsf(lhs - cg) > tol) return lhs < cg;
+    return (fabs(dx / vden) + light) < cg_exact(v0y, gender, age, size, u1, u2);
 }
-MH_HD bool gap_refused(const PedR &p, const CarR &k, double cross, Rng &rng) {
-    const uint64_t r = gap_refused_ol(p.Spx, p.v0y, p.lpos - k.line, p.gender, p.age, (p.fl & PF_CROSSING) != 0, k.Sc, k.Vc,
-                                      k.light, cross, rng);
-    rng.ctr = (uint32_t)(r >> 1);
-    return (r & 1u) != 0;
+
+// ---------------------------------------------------------------------------------------------
+// The cars of NT envs (one CTA; NT = 1 in the host build), [field][slot][thread].  Positions and
+// speeds are the fp64 values after this step's move (they are rounded to fp32 only when stored);
+// brake = Vc^2/(2b) and rVc = 1/Vc are the two per-car quotients every (pedestrian, car) pair reuses.
+template <int MC, int NT>
+struct CarSlots {
+    double Sc[MC][NT], Vc[MC][NT], brake[MC][NT], rVc[MC][NT];
+    float prevSc[MC][NT], light[MC][NT], pa[MC][NT], es[MC][NT], Ts[MC][NT], rl[MC][NT], wmin[MC][NT];
+    uint32_t bits[MC][NT];                                      // line | exist << 8
+};
+#define MH_LINE(S, i, t) ((int)((S).bits[i][t] & 255u))
+MH_HD int ctz32(uint32_t m) {
+#ifdef __CUDA_ARCH__
+    return __ffs((int)m) - 1;
+#else
+    return __builtin_ctz(m);
+#endif
 }
 
 // pedestrian.choix_pedestrian, SC:139-174 / NA:138-177.  `seen` = slots handed to pedestrian.step
 // (existing cars in scalable SC:803-806, leaders+followers in 4cars C4:796-799, all otherwise).
-template <int V, int MC>
-MH_HD bool choix_fast(const Geo &g, const PedR &p, const CarR (&car)[MC], uint32_t seen, Rng &rng) {
+//
+// The decision is split in two: choix_plan does everything that needs no normal draw (geometry,
+// the follower rules, the shuffle's draws) and returns either the answer or the ordered list of
+// cars whose gap must be judged; the gaps are then judged either one after the other (choix_fast)
+// or by the whole warp at once (choix_coop).  SC:162-173 walks the cars in front in ascending order:
+// a car standing on the crosswalk answers False, an upstream car answers False if its gap is
+// refused; the two cases exclude each other (on the crosswalk means Sc > Sp_x), so the walk is
+// "judge the upstream cars that come before the first car on the crosswalk, in order; False at the
+// first refusal, else False if there was a car on the crosswalk, else True".
+struct ChoixPlan { uint32_t gaps; int answer; bool tail_false; };   // answer: -1 = needs the gaps, else 0 / 1
+template <int V, int MC, int NT>
+MH_HD ChoixPlan choix_plan(const EnvConst &c, const Geo &g, const PedR &p, const CarSlots<MC, NT> &S, int t, uint32_t seen, Rng &rng) {
     typedef VT<V> T;
+    ChoixPlan pl; pl.gaps = 0; pl.answer = -1; pl.tail_false = false;
     const int nseen = __builtin_popcount(seen);
-    // per-car predicates of this decision
     uint32_t inf1 = 0, on_cross = 0, behind = 0, blocked = 0;
-#pragma unroll
-    for (int i = 0; i < MC; ++i) {
-        if (!((seen >> i) & 1u)) continue;
-        const bool f1 = in_front(g, p, car[i].line, 1.0);
-        const bool over = (car[i].Sc < 4.0 + p.Spx) && (car[i].Sc > p.Spx);          // car body on the crosswalk
-        if (f1) inf1 |= 1u << i;
-        if (over) on_cross |= 1u << i;
-        if (car[i].Sc < p.Spx) behind |= 1u << i;
-        if (over && f1 && crossing_in_front(g, p, car[i].line, 0.5)) blocked |= 1u << i;
+#pragma unroll 1
+    for (int i = 0; i < c.nC; ++i) {
+        const double Sc = S.Sc[i][t];
+        const int line = MH_LINE(S, i, t);
+        const bool f1 = in_front(g, p, line, 1.0);
+        const bool over = (Sc < 4.0 + p.Spx) && (Sc > p.Spx);                        // car body on the crosswalk
+        inf1 |= (f1 ? 1u : 0u) << i;
+        on_cross |= (over ? 1u : 0u) << i;
+        behind |= ((Sc < p.Spx) ? 1u : 0u) << i;
+        if (over && f1 && crossing_in_front(g, p, line, 0.5)) blocked |= 1u << i;
     }
+    inf1 &= seen; on_cross &= seen; behind &= seen; blocked &= seen;
     if (p.fl & PF_FOLLOW) {
-        if (T::naif) {
-            // NA:151 shuffles the visiting order for real, but both loops below only ever return False
-            // (NA:153-158), so the order cannot change the outcome: only the n-1 draws are consumed
-            if (nseen > 1) rng.skip(nseen - 1);
-            if (blocked) return false;                                               // NA:153-155
-#pragma unroll
-            for (int i = 0; i < MC; ++i)                                             // NA:156-158
-                if (((seen & behind) >> i) & 1u) { if (car[i].light < 0.0) return false; }
-        } else {
-            if (T::burn_shuffle && nseen > 1) rng.skip(nseen - 1);                   // SC:152-153: shuffles a temporary
-            if (blocked) return false;                                               // SC:154-158
-#pragma unroll
-            for (int i = 0; i < MC; ++i)                                             // SC:159-161: first upstream car with a light
-                if (((seen & behind) >> i) & 1u) { if (car[i].light != 0.0) return car[i].light > 0.0; }
+        // NA:151 shuffles the visiting order for real, but both loops of NA:153-158 only ever return
+        // False, so the order cannot change the outcome: only the n-1 draws are consumed.  SC:152-153
+        // shuffles a temporary.
+        if ((T::naif || T::burn_shuffle) && nseen > 1) rng.skip(nseen - 1);
+        if (blocked) { pl.answer = 0; return pl; }                                   // SC:154-158 / NA:153-155
+        for (uint32_t m = behind; m; m &= m - 1u) {                                  // ascending slots
+            const float light = S.light[ctz32(m)][t];
+            if (T::naif) { if (light < 0.f) { pl.answer = 0; return pl; } }          // NA:156-158
+            else if (light != 0.f) { pl.answer = light > 0.f ? 1 : 0; return pl; }   // SC:159-161: first upstream car with a light
         }
     }
-#pragma unroll
-    for (int i = 0; i < MC; ++i) {                                                   // SC:162-173
-        if (!(((seen & inf1) >> i) & 1u)) continue;
-        if ((on_cross >> i) & 1u) return false;
-        if ((behind >> i) & 1u) { if (gap_refused(p, car[i], g.cross, rng)) return false; }
-    }
-    return true;
+    const uint32_t oc = inf1 & on_cross;                                             // SC:162-173
+    const uint32_t before = oc ? ((oc & (0u - oc)) - 1u) : 0xFFFFFFFFu;              // slots below the first car on the crosswalk
+    pl.gaps = inf1 & behind & before;
+    pl.tail_false = oc != 0;
+    if (!pl.gaps) pl.answer = pl.tail_false ? 0 : 1;
+    return pl;
 }
+// one judgement, sequential form: a pedestrian handed to choix_pedestrian is always `crossing`, so
+// CG_score always draws (the CG = 0 branch of SC:427-428 is unreachable from here)
+template <int MC, int NT>
+MH_HD bool gap_refused(const Geo &g, const PedR &p, const CarSlots<MC, NT> &S, int t, int i, Rng &rng) {
+    const double size = fabs((double)(p.lpos - MH_LINE(S, i, t))) * g.cross;
+    const uint32_t ctr = rng.ctr++;
+    return gap_eval(S.Sc[i][t] - p.Spx, S.Vc[i][t] + 10e-3, (double)S.light[i][t], size, p.v0y, p.gender, p.age, ctr,
+                    rng.env_lo, rng.env_hi, rng.k0, rng.k1);
+}
+template <int V, int MC, int NT>
+MH_HD bool choix_fast(const EnvConst &c, const Geo &g, const PedR &p, const CarSlots<MC, NT> &S, int t, uint32_t seen, Rng &rng) {
+    const ChoixPlan pl = choix_plan<V, MC, NT>(c, g, p, S, t, seen, rng);
+    if (pl.answer >= 0) return pl.answer != 0;
+    for (uint32_t m = pl.gaps; m; m &= m - 1u)
+        if (gap_refused<MC, NT>(g, p, S, t, ctz32(m), rng)) return false;
+    return !pl.tail_false;
+}
+
+// ---- warp-cooperative form of the kerb decision ---------------------------------------------------
+// A pedestrian waiting at the kerb re-takes the decision every step (SC:311-318), so in a warp of
+// 32 envs a handful of lanes need one to four gap judgements each while the rest idle: executed in
+// place that is ~100 Philox + ~100 math instructions per judgement with two lanes active, a third of
+// the step's issue slots.  Instead every lane queues its judgements in shared memory and the warp
+// evaluates all of them side by side, one item per lane; because the generator is counter-based,
+// judgement number k of a lane uses block ctr+k whether or not an earlier one already refused, and
+// the lane afterwards advances its cursor only past the ones the sequential walk would have drawn.
+struct GapItem { double dx, vden, size; float light, v0y; uint32_t ctr, env_lo, env_hi, ga; };
+constexpr int kGapQ = 32;                                        // queue slots per warp per pass
+struct GapQueue { GapItem item[kGapQ]; uint8_t refused[kGapQ]; };
+struct WarpCtx { unsigned mask; GapQueue *q; };                  // mask: lanes of this warp that own an env
+
+#ifdef __CUDACC__
+template <int V, int MC, int NT>
+__device__ __forceinline__ bool choix_coop(const EnvConst &c, const Geo &g, const PedR &p, const CarSlots<MC, NT> &S, int t,
+                                           uint32_t seen, Rng &rng, bool need, const WarpCtx &w) {
+    const int lane = (int)(threadIdx.x & 31u);
+    ChoixPlan pl; pl.gaps = 0; pl.answer = 1; pl.tail_false = false;
+    if (need) pl = choix_plan<V, MC, NT>(c, g, p, S, t, seen, rng);
+    const uint32_t gm = (pl.answer < 0) ? pl.gaps : 0u;
+    const int cnt = __popc(gm);
+    int incl = cnt;                                              // inclusive scan of the item counts over the warp
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(w.mask, incl, d); if (lane >= d) incl += v; }
+    const int nlanes = __popc(w.mask);                           // the owning lanes are 0 .. nlanes-1 (kernel tail)
+    const int total = __shfl_sync(w.mask, incl, nlanes - 1);
+    const int base = incl - cnt;
+    uint32_t rb = 0;                                             // bit k: judgement k of this lane refused
+    for (int pass0 = 0; pass0 < total; pass0 += kGapQ) {         // warp-uniform; one pass unless > kGapQ judgements are queued
+        int rank = 0;
+        for (uint32_t m = gm; m; m &= m - 1u, ++rank) {
+            const int slot = base + rank - pass0;
+            if (slot < 0 || slot >= kGapQ) continue;
+            const int i = __ffs((int)m) - 1;
+            GapItem it;
+            it.dx = S.Sc[i][t] - p.Spx; it.vden = S.Vc[i][t] + 10e-3; it.size = fabs((double)(p.lpos - MH_LINE(S, i, t))) * g.cross;
+            it.light = S.light[i][t]; it.v0y = (float)p.v0y;                 // v0y is fp32 state, exact
+            it.ctr = rng.ctr + (uint32_t)rank; it.env_lo = rng.env_lo; it.env_hi = rng.env_hi;
+            it.ga = (uint32_t)p.gender | ((uint32_t)p.age << 8);
+            w.q->item[slot] = it;
+        }
+        __syncwarp(w.mask);
+        const int m_items = (total - pass0 < kGapQ) ? (total - pass0) : kGapQ;
+        for (int s = lane; s < m_items; s += nlanes) {
+            const GapItem it = w.q->item[s];
+            w.q->refused[s] = gap_eval(it.dx, it.vden, (double)it.light, it.size, (double)it.v0y, (int)(it.ga & 255u), (int)(it.ga >> 8),
+                                       it.ctr, it.env_lo, it.env_hi, rng.k0, rng.k1) ? 1 : 0;
+        }
+        __syncwarp(w.mask);
+        for (int k = 0; k < cnt; ++k) {
+            const int slot = base + k - pass0;
+            if (slot >= 0 && slot < kGapQ) rb |= (uint32_t)w.q->refused[slot] << k;
+        }
+        __syncwarp(w.mask);
+    }
+    if (pl.answer >= 0) return pl.answer != 0;
+    if (rb) { rng.ctr += (uint32_t)__ffs((int)rb); return false; }           // draws up to and including the first refusal
+    rng.ctr += (uint32_t)cnt;
+    return !pl.tail_false;
+}
+#endif
 
 struct WalkOut { double pos, spd; };
 // pedestrian.new_pedestrian_sin_y, SC:436-443 with the parameters of SC:94-102
@@ -177,18 +273,25 @@ MH_HD float exp_f32(double x) {   // e^x for output-only terms: fp64 argument, f
 
 // ---------------------------------------------------------------------------------------------
 // pedestrian.step, SC:297-417, for the pedestrian currently held in registers
-template <int V, int MC>
-MH_HD void ped_step_stream(const EnvConst &c, const Geo &g, PedR &p, const CarR (&car)[MC], uint32_t seen, int step, Rng &rng) {
-    typedef VT<V> T;
-    const double dt = c.dt;
-    const double pp_y = p.Spy + p.v0y * dt;                                          // SC:298
-    const double dy = (double)p.dir * p.Spy;                                         // boolean_ped_position SC:266-275
+// boolean_ped_position (SC:266-275); returns whether this step opens with the kerb decision of SC:311-318
+MH_HD bool ped_flags(const Geo &g, PedR &p) {
+    const double dy = (double)p.dir * p.Spy;
     p.fl &= ~(PF_LEFT | PF_IN_CROSS);
     if (dy >= g.Hp) p.fl |= PF_LEFT;
     else if (dy > g.Hn) p.fl |= PF_IN_CROSS;
-    if (!(p.fl & PF_CROSSING)) return;                                               // SC:308
+    return (p.fl & PF_CROSSING) && !(p.fl & PF_DECISION) && (p.fl & PF_AT_CROSSING);
+}
 
-    auto choix = [&]() -> bool { return choix_fast<V, MC>(g, p, car, seen, rng); };
+// `kerb_choice`: the outcome of choix_pedestrian for a pedestrian whose step opens with the kerb decision
+// (already taken by the caller, draws already consumed); ignored otherwise
+template <int V, int MC, int NT>
+MH_HD void ped_step_stream(const EnvConst &c, const Geo &g, PedR &p, const CarSlots<MC, NT> &S, int t, uint32_t seen, int step,
+                           Rng &rng, bool kerb_choice) {
+    typedef VT<V> T;
+    const double dt = c.dt;
+    const double pp_y = p.Spy + p.v0y * dt;                                          // SC:298
+    const double dy = (double)p.dir * p.Spy;
+    if (!(p.fl & PF_CROSSING)) return;                                               // SC:308
 
     bool choose = true;
     const bool first_decision = !(p.fl & PF_DECISION) && (p.fl & PF_AT_CROSSING);    // SC:311
@@ -201,7 +304,7 @@ MH_HD void ped_step_stream(const EnvConst &c, const Geo &g, PedR &p, const CarR 
     bool walk_try = false;
     if (in_walk_block) {
         if (first_decision) {
-            choose = choix();
+            choose = kerb_choice;
             if (choose) { p.lpos = (p.dir < 0) ? (c.L - 1) : 0; p.fl &= ~PF_AT_CROSSING; }
             p.fl |= PF_DECISION;
             p.t0c = step;
@@ -232,7 +335,7 @@ MH_HD void ped_step_stream(const EnvConst &c, const Geo &g, PedR &p, const CarR 
         dtc += ((double)p.lpos * g.cross) * (double)(p.dir < 0);
         bool new_choice = false;
         if (change_line && (dtc > 0.0 && dtc < g.W)) {                               // SC:353-357
-            new_choice = choix();
+            new_choice = choix_fast<V, MC, NT>(c, g, p, S, t, seen, rng);
             if (new_choice) p.fl &= ~PF_STOP;
         }
         if (p.fl & PF_STOP) {                                                        // SC:363-369
@@ -276,8 +379,9 @@ MH_HD void ped_step_stream(const EnvConst &c, const Geo &g, PedR &p, const CarR 
 }
 
 // ---------------------------------------------------------------------------------------------
-template <int V, int MC, int MP>
-MH_HD void env_step_thread(const EnvArena &a, const EnvConst &c, const RngKey &key, const StepIO &io, int64_t n) {
+template <int V, int MC, int MP, int NT>
+MH_HD void env_step_thread(const EnvArena &a, const EnvConst &c, const RngKey &key, const StepIO &io, int64_t n, const WarpCtx &w,
+                           CarSlots<MC, NT> &S, int t) {
     typedef VT<V> T;
     // ---- env word
     const float4 ee = a.env_e[n];
@@ -291,90 +395,64 @@ MH_HD void env_step_thread(const EnvArena &a, const EnvConst &c, const RngKey &k
         rng.ctr = f2u(ee.w); rng.env_lo = (uint32_t)gid; rng.env_hi = (uint32_t)(gid >> 32); rng.k0 = key.k0; rng.k1 = key.k1;
     }
     const Geo g = make_geo(cross, c.L);
-
-    // ---- cars: load, act (SC:797-802 / C4:791-795 / C42:807-811 / CO:753-755)
-    CarR car[MC];
-    double prevSc[MC];
-    // running min/max shaping accumulators (possible_accident, error_scenario, Ts): kept in fp32.  They
-    // are stored as fp32 and only ever updated by min/max with a new candidate, and rounding is
-    // monotonic, so min(fp32 old, fp32(candidate)) == fp32(min(old, candidate)) bit for bit.
-    float paf[MC], esf[MC], Tsf[MC];
-#pragma unroll
-    for (int i = 0; i < MC; ++i) {
-        if (i >= c.nC) continue;
-        const float4 ka = a.car_a[(int64_t)i * a.N + n], kb = a.car_b[(int64_t)i * a.N + n];
-        CarR &k = car[i];
-        k.Vc = (double)ka.x; k.Sc = (double)ka.y; k.light = (double)ka.z; k.Ac = (double)ka.w;
-        paf[i] = kb.x; esf[i] = kb.y; Tsf[i] = kb.z;
-        const uint32_t b = f2u(kb.w);
-        k.line = (int)(b & 255u); k.exist = (int)((b >> 8) & 1u);
-        prevSc[i] = k.Sc;
-    }
-    {
-        const float *ap = io.actions.ptr + n * io.actions.env_stride;
-        const int half = c.nA / 2;
-        const int64_t cs = io.actions.comp_stride;
-        if (T::scal) {
-#pragma unroll
-            for (int i = 0; i < MC; ++i) {
-                if (i >= c.nC) continue;
-                double acc = (double)ap[(int64_t)i * cs];
-                const double lt = (double)ap[(int64_t)(half + i) * cs];
-                if ((i & 1) && car[i > 0 ? i - 1 : 0].exist && car[i].exist)
-                    acc = dmin(idm(c, car[i], car[i > 0 ? i - 1 : 0].Sc, car[i > 0 ? i - 1 : 0].Vc), acc);
-                else acc = dmin(2.0, acc);
-                car_move<V>(c, car[i], acc, lt);
-            }
-        } else if (T::four) {
-            const int nl = c.nb_car;
-#pragma unroll
-            for (int i = 0; i < MC / 2; ++i) {
-                if (i >= nl) continue;
-                car_move<V>(c, car[i], (double)ap[(int64_t)i * cs], (double)ap[(int64_t)(half + i) * cs]);
-            }
-#pragma unroll
-            for (int i = 0; i < MC / 2; ++i) {
-                if (i >= nl) continue;
-                CarR &f = car[MC / 2 + i];                  // follower of leader i (MC == 2*nb_car for these classes)
-                const double a_idm = idm(c, f, car[i].Sc, car[i].Vc);
-                if (V == V_4CARS2) car_move<V>(c, f, dmin(a_idm, (double)ap[(int64_t)(nl + i) * cs]), (double)ap[(int64_t)(half + nl + i) * cs]);
-                else car_move<V>(c, f, a_idm, car[i].light);
-            }
-        } else {
-#pragma unroll
-            for (int i = 0; i < MC; ++i) {
-                if (i >= c.nC) continue;
-                car_move<V>(c, car[i], (double)ap[(int64_t)i * cs], (double)ap[(int64_t)(half + i) * cs]);
-            }
-        }
-    }
-    // ---- per-car quantities reused by every pedestrian
-    double brake[MC], rVc[MC];
-    uint32_t seen = 0, lead_ok = 0;     // seen: cars handed to pedestrian.step; lead_ok: cars detection may touch
-    double green = 0.0;                 // SC:246
-#pragma unroll
-    for (int i = 0; i < MC; ++i) {
-        if (i >= c.nC) continue;
-        brake[i] = car[i].Vc * car[i].Vc / (-2.0 * c.acc_lo);
-        rVc[i] = 1.0 / car[i].Vc;
-        if (!T::scal || car[i].exist) seen |= 1u << i;
-        if (i < c.nlead && (!T::scal || car[i].exist)) {
-            lead_ok |= 1u << i;
-            if (car[i].light > 0.0) green += 1.0;
-        }
-    }
     const bool done = (step >= c.done_idx) || (ped_traffic <= 0);                    // SC:874
     const bool will_reset = done && io.autoreset;
     const mhppo_view ov = will_reset ? io.term_obs : io.obs;
     float *const op = ov.ptr ? ov.ptr + n * ov.env_stride : nullptr;
     const int64_t ocs = ov.comp_stride;
+
+    // ---- cars: load, act (SC:797-802 / C4:791-795 / C42:807-811 / CO:753-755), observation row
+    // (car.get_data SC:652-655) and position/speed store, one slot at a time.  Leaders come before the
+    // slots that follow them (odd slots in scalable SC:799-801, the second half in 4cars C4:793-795), so a
+    // follower reads its leader's already-moved position from the slots.
+    uint32_t seen = 0, lead_ok = 0, lead_green = 0;   // seen: cars handed to pedestrian.step; lead_ok: cars detection may touch
+    {
+        const float *ap = io.actions.ptr + n * io.actions.env_stride;
+        const int half = c.nA / 2;
+        const int64_t cs = io.actions.comp_stride;
+#pragma unroll 1
+        for (int i = 0; i < c.nC; ++i) {
+            const float4 ka = a.car_a[(int64_t)i * a.N + n], kb = a.car_b[(int64_t)i * a.N + n];
+            CarR k;
+            k.Vc = (double)ka.x; k.Sc = (double)ka.y; k.light = (double)ka.z; k.Ac = (double)ka.w;
+            const uint32_t b = f2u(kb.w);
+            k.line = (int)(b & 255u); k.exist = (int)((b >> 8) & 1u);
+            if (T::scal) {
+                double acc = (double)ap[(int64_t)i * cs];
+                const int l = i > 0 ? i - 1 : 0;
+                if ((i & 1) && ((S.bits[l][t] >> 8) & 1u) && k.exist) acc = dmin(idm(c, k, S.Sc[l][t], S.Vc[l][t]), acc);
+                else acc = dmin(2.0, acc);
+                car_move<V>(c, k, acc, (double)ap[(int64_t)(half + i) * cs]);
+            } else if (T::four && i >= c.nb_car) {
+                const int l = i - c.nb_car;                                          // follower of leader l
+                const double a_idm = idm(c, k, S.Sc[l][t], S.Vc[l][t]);
+                if (V == V_4CARS2) car_move<V>(c, k, dmin(a_idm, (double)ap[(int64_t)i * cs]), (double)ap[(int64_t)(half + i) * cs]);
+                else car_move<V>(c, k, a_idm, (double)S.light[l][t]);
+            } else {
+                car_move<V>(c, k, (double)ap[(int64_t)i * cs], (double)ap[(int64_t)(half + i) * cs]);
+            }
+            S.prevSc[i][t] = ka.y; S.Sc[i][t] = k.Sc; S.Vc[i][t] = k.Vc; S.light[i][t] = (float)k.light;
+            S.brake[i][t] = k.Vc * k.Vc / (-2.0 * c.acc_lo);
+            S.rVc[i][t] = 1.0 / k.Vc;
+            S.pa[i][t] = kb.x; S.es[i][t] = kb.y; S.Ts[i][t] = kb.z; S.rl[i][t] = 0.f; S.wmin[i][t] = 0.f;
+            S.bits[i][t] = b;
+            const bool ex = !T::scal || k.exist;
+            if (ex) seen |= 1u << i;
+            if (i < c.nlead && ex) { lead_ok |= 1u << i; if (k.light > 0.0) lead_green |= 1u << i; }
+            if (op) {
+                float *q = op + (int64_t)(T::car_w * i) * ocs;
+                q[0 * ocs] = ex ? (float)k.Ac : 0.f; q[1 * ocs] = ex ? (float)k.Vc : 0.f;
+                q[2 * ocs] = ex ? (float)(10.0 - k.Vc) : 10.f; q[3 * ocs] = ex ? (float)k.Sc : -1000.f;
+                q[4 * ocs] = ex ? (float)k.light : 0.f; q[5 * ocs] = (float)k.line;
+                if (T::scal) q[6 * ocs] = ex ? 1.f : 0.f;
+            }
+            if (!will_reset) a.car_a[(int64_t)i * a.N + n] = make_float4((float)k.Vc, (float)k.Sc, (float)k.light, (float)k.Ac);
+        }
+    }
+    const float green = (float)__builtin_popcount(lead_green);                       // SC:246
     const int env_w = T::scal ? 4 : 3;
     const int ped_o = T::car_w * c.nC + env_w;
     const double time_braking = -(10.0 / (2.0 * c.acc_lo)) + 1.0;                    // SC:580
-
-    float rl[MC], wmin[MC];
-#pragma unroll
-    for (int i = 0; i < MC; ++i) { rl[i] = 0.f; wmin[i] = 0.f; }
     bool any_exist = false;
 
     // ---- pedestrians, streamed
@@ -391,131 +469,139 @@ MH_HD void env_step_thread(const EnvArena &a, const EnvConst &c, const RngKey &k
             unpack_ped_bits(bits, p);
             if (bits & (PB_Y_KERB | PB_Y_LANE)) p.Spy = (bits & PB_Y_KERB) ? sym_kerb(g, p) : sym_lane(g, p);
         }
-        ped_step_stream<V, MC>(c, g, p, car, seen, step, rng);                       // SC:808-809
-
-        // geometry predicates of this pedestrian against every car lane, and the shared gaps
-        uint32_t inf = 0, cif = 0, behind = 0;    // behind: Sc < Sp_x
-        double raw[MC];                           // |Sc - Sp_x| - Vc^2/(2b)   (SC:527)
-#pragma unroll
-        for (int i = 0; i < MC; ++i) {
-            if (i >= c.nC) continue;
-            if (in_front(g, p, car[i].line, 0.0)) inf |= 1u << i;
-            if (crossing_in_front(g, p, car[i].line, 0.0)) cif |= 1u << i;
-            if (car[i].Sc < p.Spx) behind |= 1u << i;
-            raw[i] = fabs(car[i].Sc - p.Spx) - brake[i];
+        {                                                                            // SC:808-809
+            const bool kerb = ped_flags(g, p);
+#ifdef __CUDA_ARCH__
+            const bool kerb_choice = choix_coop<V, MC, NT>(c, g, p, S, t, seen, rng, kerb, w);
+#else
+            const bool kerb_choice = kerb ? choix_fast<V, MC, NT>(c, g, p, S, t, seen, rng) : true;
+            (void)w;
+#endif
+            ped_step_stream<V, MC, NT>(c, g, p, S, t, seen, step, rng, kerb_choice);
         }
         const bool left = (p.fl & PF_LEFT) != 0;
+        const bool pex = (p.fl & PF_EXIST) != 0;
+
+        // ---- geometry predicates of this pedestrian against every car lane (is_in_front / is_crossing_in_front
+        // evaluated once per pair, reused below), and the observation's running-min gap (pedestrian.get_data
+        // SC:449-460 with delta_l_all SC:508-514 over the cars handed to it: SC:803-806 / C4:796-799)
+        uint32_t inf = 0, cif = 0, behind = 0;    // behind: Sc < Sp_x
+        {
+            double dl = T::far;
+#pragma unroll 1
+            for (int i = 0; i < c.nC; ++i) {
+                const double Sc = S.Sc[i][t];
+                const int line = MH_LINE(S, i, t);
+                const bool f0 = in_front(g, p, line, 0.0);
+                inf |= (f0 ? 1u : 0u) << i;
+                cif |= (crossing_in_front(g, p, line, 0.0) ? 1u : 0u) << i;
+                behind |= ((Sc < p.Spx) ? 1u : 0u) << i;
+                if (((seen >> i) & 1u) && (Sc <= p.Spx) && f0 && !left && (S.light[i][t] >= 0.f))
+                    dl = dmin(dl, (fabs(Sc - p.Spx) - S.brake[i][t]) - 1.0 * S.Vc[i][t]);
+            }
+            if (pex) {
+                const double gate = ((p.fl & PF_CROSSING) && !left) ? 1.0 : 0.0;
+                p.delta = dmin(dl * gate, p.delta);
+            }
+        }
         const double wait_t = (double)p.waitc * c.dt, cross_t = (double)p.crossc * c.dt;
 
         // ---- detection (SC:176-264); placeholders run it too (SC:842-843)
-        double nwait = 0.0;                                                          // SC:206
-#pragma unroll
-        for (int i = 0; i < MC; ++i)
-            if (((lead_ok & behind) >> i) & 1u) { if (car[i].light > 0.0) nwait += 1.0; }
+        const double nwait = (double)__builtin_popcount(lead_green & behind);        // SC:206
         const float ts_new = (float)(T::naif ? (((wait_t + 10.0 * cross_t) - time_braking) + 1.0)
                                              : ((((1.0 + nwait) * wait_t + 2.0 * cross_t) - time_braking) + 1.0));
-        // Written branch-free on purpose: lanes (envs) disagree on every one of these conditions, so
-        // each pair is evaluated once with selects instead of serialising the sides of the branches.
+        // The pair body is written branch-free on purpose: lanes (envs) disagree on every one of these
+        // conditions, so each pair is evaluated once with selects instead of serialising the sides.
+        // The running min/max accumulators (possible_accident, error_scenario, Ts) are fp32: they are stored
+        // as fp32 and only ever updated by min/max with a new candidate, and rounding is monotonic, so
+        // min(fp32 old, fp32(candidate)) == fp32(min(old, candidate)) bit for bit.
         uint32_t fl = p.fl;
-#pragma unroll
-        for (int i = 0; i < MC; ++i) {
-            if (i >= c.nlead) continue;
-            CarR &k = car[i];
+        const bool counts = (p.fl & PF_CROSSING) && (!T::scal || pex);               // SC:844-845
+#pragma unroll 1
+        for (int i = 0; i < c.nlead; ++i) {
+            const double Sc = S.Sc[i][t], Vc = S.Vc[i][t];
+            const float light = S.light[i][t];
             const bool gi = ((lead_ok & inf) >> i) & 1u;                             // SC:180
             const bool bi = (behind >> i) & 1u, ci = (cif >> i) & 1u;
-            const bool ahead = (k.Sc > p.Spx);
-            const double wdl = (ahead || left) ? T::far : raw[i];                    // worst_delta_l SC:522-527
+            const bool ahead = (Sc > p.Spx);
+            const double wdl = (ahead || left) ? T::far : (fabs(Sc - p.Spx) - S.brake[i][t]);   // worst_delta_l SC:522-527
             const bool wneg = wdl < 0.0;
             const bool acc0 = (fl & PF_ACCIDENT) != 0;
             bool wa = (fl & PF_WORST_ACC) != 0;
             const bool ped_accident = T::naif ? (!acc0 && wneg) : (!acc0 && wa);     // SC:181-182 / NA:181-185
             wa = gi ? wneg : wa;
-            const bool hit = gi && ped_accident && ci && (prevSc[i] < p.Spx) && ahead;   // SC:184-185
+            const bool hit = gi && ped_accident && ci && ((double)S.prevSc[i][t] < p.Spx) && ahead;   // SC:184-185
             fl = (fl & ~PF_WORST_ACC) | (wa ? PF_WORST_ACC : 0u) | (hit ? PF_ACCIDENT : 0u);
+            float paf = S.pa[i][t], esf = S.es[i][t], Tsf = S.Ts[i][t];
             {                                                                        // SC:187-201
-                const bool slow = k.Vc < 0.05;
-                const double dl64 = slow ? T::far : wdl * rVc[i];
+                const bool slow = Vc < 0.05;
+                const double dl64 = slow ? T::far : wdl * S.rVc[i][t];
                 const float dl = (float)dl64;
                 const bool pos = slow ? (T::far > 0.0) : (wdl > 0.0);
                 // -dl-1 (ST:197, NA:200) cancels near dl = -1: that one difference is formed in fp64
                 const float lin = T::neg_dl ? (float)(-1.0 * dl64 - 1.0) : (1.0f * dl - 1.0f);
                 const float pa = pos ? -exp2f(-4.0f * 1.4426950408889634f * dl) : lin;
-                paf[i] = (gi && ci) ? fminf(paf[i], pa) : paf[i];
+                paf = (gi && ci) ? fminf(paf, pa) : paf;
             }
-            Tsf[i] = (gi && bi) ? fmaxf(ts_new, Tsf[i]) : Tsf[i];                    // SC:207-208
+            Tsf = (gi && bi) ? fmaxf(ts_new, Tsf) : Tsf;                             // SC:207-208
             {                                                                        // SC:216-237
-                const bool red = k.light < 0.0, grn = k.light > 0.0;
-                const double gap = p.Spx - k.Sc;
+                const bool red = light < 0.f, grn = light > 0.f;
+                const double gap = p.Spx - Sc;
                 const float gapf = (float)gap;
-                const bool use_exp = red ? (Tsf[i] < 0.f) : (gap > 0.0);
-                const float arg = red ? (4.0f * Tsf[i]) : (-4.0f * gapf);
-                const float lin = red ? (-1.0f * (1.0f + Tsf[i])) : (-1.0f - (float)(k.Sc - p.Spx));
+                const bool use_exp = red ? (Tsf < 0.f) : (gap > 0.0);
+                const float arg = red ? (4.0f * Tsf) : (-4.0f * gapf);
+                const float lin = red ? (-1.0f * (1.0f + Tsf)) : (-1.0f - (float)(Sc - p.Spx));
                 const float ne = use_exp ? -exp2f(1.4426950408889634f * arg) : lin;
-                esf[i] = (gi && (red || grn)) ? fminf(ne, esf[i]) : esf[i];
+                esf = (gi && (red || grn)) ? fminf(ne, esf) : esf;
                 if (!T::naif) fl |= (gi && red && ci && bi) ? PF_NOT_WAITING : 0u;
+            }
+            S.pa[i][t] = paf; S.es[i][t] = esf; S.Ts[i][t] = Tsf;
+            if (counts) {                                                            // res: SC:250-263
+                float r = paf + esf;
+                if (T::danger_sign != 0) {
+                    const float extra = ((light < 0.f) && (Tsf > 0.f)) ? 0.5f * green : 0.f;
+                    r = (T::danger_sign > 0) ? (r + extra) : (r - extra);
+                }
+                if (T::scal && !((S.bits[i][t] >> 8) & 1u)) r = 0.f;
+                S.rl[i][t] += r;
             }
         }
         p.fl = fl;
-        if ((p.fl & PF_CROSSING) && (!T::scal || (p.fl & PF_EXIST))) {               // SC:844-845, res: SC:250-263
-#pragma unroll
-            for (int i = 0; i < MC; ++i) {
-                if (i >= c.nlead) continue;
-                float r = paf[i] + esf[i];
-                if (T::danger_sign != 0) {
-                    const float extra = ((car[i].light < 0.0) && (Tsf[i] > 0.f)) ? 0.5f * (float)green : 0.f;
-                    r = (T::danger_sign > 0) ? (r + extra) : (r - extra);
-                }
-                if (T::scal && !car[i].exist) r = 0.f;
-                rl[i] += r;
-            }
-        }
 
         // ---- wait-reward contribution (SC:855-857 with new_reward_wait_safety SC:478-506); the
         // reference loops cars outside / pedestrians inside, but worst_dl is per pedestrian and only
-        // sees the cars in ascending order, which this loop preserves
+        // sees the cars in ascending order, which this loop preserves.  It needs the accident flag
+        // after ALL cars' detection (the reference finishes SC:841-846 before SC:849), hence a second loop.
         {
-            const bool ex = (p.fl & PF_EXIST) != 0;
-            const bool guard_p = ex && !left && (p.fl & PF_CROSSING);
+            const bool guard_p = pex && !left && (p.fl & PF_CROSSING);
             const float acc_pen = (p.fl & PF_ACCIDENT) ? 20.0f : 0.0f;
             float pwdl = (float)p.wdl;
-#pragma unroll
-            for (int i = 0; i < MC; ++i) {
-                if (i >= c.nlead) continue;
-                const CarR &k = car[i];
-                const bool grn = ex && (k.light > 0.0);
+#pragma unroll 1
+            for (int i = 0; i < c.nlead; ++i) {
+                const double Vc = S.Vc[i][t];
+                const bool grn = pex && (S.light[i][t] > 0.f);
                 const bool guard = grn && guard_p && (((behind & inf) >> i) & 1u);
-                const double d = raw[i] - 1.0 * k.Vc;                                // delta_l SC:516-520
-                const float dl = (float)(d * rVc[i]);
+                const double d = (fabs(S.Sc[i][t] - p.Spx) - S.brake[i][t]) - 1.0 * Vc;   // delta_l SC:516-520
+                const float dl = (float)(d * S.rVc[i][t]);
                 const float soft = fmaxf(-20.0f * exp2f(1.4426950408889634f * (-4.0f * dl - 4.0f)), -20.0f);
-                float e = (k.Vc < T::wait_thr) ? 0.0f : ((d >= -k.Vc) ? soft : 20.0f * dl);
+                float e = (Vc < T::wait_thr) ? 0.0f : ((d >= -Vc) ? soft : 20.0f * dl);
                 e = e - acc_pen;
                 pwdl = (guard && e < pwdl) ? e : pwdl;
-                wmin[i] = grn ? ((!any_exist || pwdl < wmin[i]) ? pwdl : wmin[i]) : wmin[i];
+                const float wm = S.wmin[i][t];
+                S.wmin[i][t] = grn ? ((!any_exist || pwdl < wm) ? pwdl : wm) : wm;
             }
             p.wdl = (double)pwdl;
-            any_exist = any_exist || ex;
+            any_exist = any_exist || pex;
         }
 
-        // ---- observation row (pedestrian.get_data SC:449-460, delta_l_all SC:508-514)
-        if (p.fl & PF_EXIST) {
-            double dl = T::far;
-#pragma unroll
-            for (int i = 0; i < MC; ++i) {
-                if (!((seen >> i) & 1u)) continue;                                   // SC:803-806 existing cars / C4:796-799 all
-                if ((car[i].Sc <= p.Spx) && ((inf >> i) & 1u) && !left && (car[i].light >= 0.0))
-                    dl = dmin(dl, raw[i] - 1.0 * car[i].Vc);
-            }
-            const double gate = ((p.fl & PF_CROSSING) && !left) ? 1.0 : 0.0;
-            p.delta = dmin(dl * gate, p.delta);
-        }
+        // ---- observation row
         if (op) {
             float *q = op + (int64_t)(ped_o + 9 * j) * ocs;
-            const bool ex = (p.fl & PF_EXIST) != 0;
-            q[0 * ocs] = ex ? (float)p.Vpx : 0.f; q[1 * ocs] = ex ? (float)p.Vpy : 0.f;
-            q[2 * ocs] = ex ? (float)p.Spx : 0.f; q[3 * ocs] = ex ? (float)p.Spy : 0.f;
-            q[4 * ocs] = ex ? (float)p.delta : 0.f; q[5 * ocs] = (ex && left) ? 1.f : 0.f;
-            q[6 * ocs] = (ex && (p.fl & PF_IN_CROSS)) ? 1.f : 0.f; q[7 * ocs] = ex ? 1.f : 0.f;
-            q[8 * ocs] = ex ? (float)p.dir : 0.f;
+            q[0 * ocs] = pex ? (float)p.Vpx : 0.f; q[1 * ocs] = pex ? (float)p.Vpy : 0.f;
+            q[2 * ocs] = pex ? (float)p.Spx : 0.f; q[3 * ocs] = pex ? (float)p.Spy : 0.f;
+            q[4 * ocs] = pex ? (float)p.delta : 0.f; q[5 * ocs] = (pex && left) ? 1.f : 0.f;
+            q[6 * ocs] = (pex && (p.fl & PF_IN_CROSS)) ? 1.f : 0.f; q[7 * ocs] = pex ? 1.f : 0.f;
+            q[8 * ocs] = pex ? (float)p.dir : 0.f;
         }
         // ---- store pedestrian j
         if (!will_reset) {
@@ -526,34 +612,25 @@ MH_HD void env_step_thread(const EnvArena &a, const EnvConst &c, const RngKey &k
         }
     }
 
-    // ---- rewards (SC:849-858), reward_light (SC:846), done
+    // ---- rewards (SC:849-858), reward_light (SC:846), shaping accumulators back to HBM, done
     {
         float *rp = io.rewards.ptr ? io.rewards.ptr + n * io.rewards.env_stride : nullptr;
         float *lp = io.reward_light.ptr ? io.reward_light.ptr + n * io.reward_light.env_stride : nullptr;
-#pragma unroll
-        for (int i = 0; i < MC; ++i) {
-            if (i >= c.nlead) continue;
-            const double d = car[i].Vc - 10.0;
-            double r = (-10.0 * (d * d)) / 100.0;                                    // SC:657-665
-            if ((car[i].light > 0.0) && any_exist) r += (double)wmin[i];
-            if (rp) rp[(int64_t)i * io.rewards.comp_stride] = (float)r;
-            if (lp) lp[(int64_t)i * io.reward_light.comp_stride] = rl[i];
+#pragma unroll 1
+        for (int i = 0; i < c.nC; ++i) {
+            if (i < c.nlead) {
+                const double d = S.Vc[i][t] - 10.0;
+                double r = (-10.0 * (d * d)) / 100.0;                                // SC:657-665
+                if ((S.light[i][t] > 0.f) && any_exist) r += (double)S.wmin[i][t];
+                if (rp) rp[(int64_t)i * io.rewards.comp_stride] = (float)r;
+                if (lp) lp[(int64_t)i * io.reward_light.comp_stride] = S.rl[i][t];
+            }
+            if (!will_reset) a.car_b[(int64_t)i * a.N + n] = make_float4(S.pa[i][t], S.es[i][t], S.Ts[i][t], u2f(S.bits[i][t]));
         }
         if (io.done) io.done[n] = done ? 1 : 0;
     }
-    // ---- observation: car rows (car.get_data SC:652-655) and env row (SC:871)
+    // ---- observation: env row (SC:871)
     if (op) {
-#pragma unroll
-        for (int i = 0; i < MC; ++i) {
-            if (i >= c.nC) continue;
-            const CarR &k = car[i];
-            float *q = op + (int64_t)(T::car_w * i) * ocs;
-            const bool ex = !T::scal || k.exist;
-            q[0 * ocs] = ex ? (float)k.Ac : 0.f; q[1 * ocs] = ex ? (float)k.Vc : 0.f;
-            q[2 * ocs] = ex ? (float)(10.0 - k.Vc) : 10.f; q[3 * ocs] = ex ? (float)k.Sc : -1000.f;
-            q[4 * ocs] = ex ? (float)k.light : 0.f; q[5 * ocs] = (float)k.line;
-            if (T::scal) q[6 * ocs] = ex ? 1.f : 0.f;
-        }
         float *q = op + (int64_t)(T::car_w * c.nC) * ocs;
         int o = 0;
         q[(o++) * ocs] = (float)(cross * (double)c.L / 2.0);
@@ -565,15 +642,6 @@ MH_HD void env_step_thread(const EnvArena &a, const EnvConst &c, const RngKey &k
     if (will_reset) {                                                                // in-kernel auto-reset
         reset_and_store<V, MC, MP>(a, c, n, rng, io.obs);
         return;
-    }
-    // ---- store cars + env word
-#pragma unroll
-    for (int i = 0; i < MC; ++i) {
-        if (i >= c.nC) continue;
-        const CarR &k = car[i];
-        a.car_a[(int64_t)i * a.N + n] = make_float4((float)k.Vc, (float)k.Sc, (float)k.light, (float)k.Ac);
-        a.car_b[(int64_t)i * a.N + n] = make_float4(paf[i], esf[i], Tsf[i],
-                                                    u2f(((uint32_t)k.line & 255u) | (((uint32_t)k.exist & 1u) << 8)));
     }
     a.env_e[n] = make_float4(ee.x, ee.y, u2f(pack_env_word(step, ped_traffic, car_traffic)), u2f(rng.ctr));
 }

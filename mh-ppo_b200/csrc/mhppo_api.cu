@@ -118,6 +118,7 @@ int mhppo_env_create(const mhppo_env_cfg *cfg, void **handle) {
     }
     if (cfg->device < 0 || cfg->device >= ndev) return fail(MHPPO_EINVAL, "device ordinal out of range");
     CK(cudaSetDevice(cfg->device));
+    CK(cudaFuncSetAttribute((const void *)k->step, cudaFuncAttributeMaxDynamicSharedMemorySize, k->step_smem));
 
     EnvHandle *h = new (std::nothrow) EnvHandle();
     if (!h) return fail(MHPPO_ENOMEM, "host allocation failed");
@@ -208,7 +209,7 @@ int mhppo_env_step(void *handle, mhppo_view actions_dev, mhppo_view obs_dev, mhp
     io.actions = actions_dev; io.obs = obs_dev; io.rewards = rewards_dev; io.reward_light = reward_light_dev;
     io.term_obs = term_obs_dev; io.done = done_dev; io.autoreset = autoreset;
     auto fn = h->k->step;
-    fn<<<grid_for(h->a.N), kEnvBlock, 0, (cudaStream_t)stream>>>(h->a, h->c, h->key, io);
+    fn<<<grid_for(h->a.N), kEnvBlock, h->k->step_smem, (cudaStream_t)stream>>>(h->a, h->c, h->key, io);
     g_launches.fetch_add(1);
     CK(cudaGetLastError());
     return MHPPO_OK;

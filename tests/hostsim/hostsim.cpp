@@ -37,7 +37,8 @@ static void sim_step(Sim *s, mhppo_view actions, mhppo_view obs, mhppo_view rewa
     io.actions = actions; io.obs = obs; io.rewards = rewards; io.reward_light = reward_light; io.term_obs = term_obs;
     io.done = done; io.autoreset = autoreset;
     RngKey key; key.k0 = s->k0; key.k1 = s->k1; key.env_id0 = s->env_id0;
-    for (int64_t n = 0; n < s->a.N; ++n) env_step_thread<V, MC, MP>(s->a, s->c, key, io, n);   // the kernel's thread body
+    CarSlots<MC, 1> cars;
+    for (int64_t n = 0; n < s->a.N; ++n) env_step_thread<V, MC, MP, 1>(s->a, s->c, key, io, n, WarpCtx{0u, nullptr}, cars, 0);   // the kernel's thread body
 }
 
 #define DISPATCH(FN, ...)                                                                          \
