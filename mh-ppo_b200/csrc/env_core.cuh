@@ -93,7 +93,17 @@ struct EnvConst {
     double dt, acc_lo, acc_hi;       // car_b[0,0], car_b[1,0]
     double pb[8];                    // ped_b row-major
     double cross_lo, cross_hi;       // cross_b
+    // derived on the host by env_const_finish (same IEEE double arithmetic as on the device): the three
+    // per-handle constants the reference recomputes on every call
+    double brake_den;                // -2 * acc_lo                      (SC:527, 518: Vc^2 / (2b))
+    double idm_den;                  // 2 * sqrt(-acc_lo * acc_hi)       (SC:611)
+    double time_braking;             // -(10 / (2 * acc_lo)) + 1         (SC:580)
 };
+inline void env_const_finish(EnvConst &c) {
+    c.brake_den = -2.0 * c.acc_lo;
+    c.idm_den = 2.0 * sqrt(-c.acc_lo * c.acc_hi);
+    c.time_braking = -(10.0 / (2.0 * c.acc_lo)) + 1.0;
+}
 
 struct Geo {
     double cross, W, Hn, Hp, Lf;     // Hn = -W/2, Hp = W/2
@@ -104,6 +114,14 @@ MH_HD Geo make_geo(double cross, int L) {
 }
 
 MH_HD double dmin(double a, double b) { return b < a ? b : a; }   // Python min(a, b)
+// x / den for den > 0, bit-identical to the plain quotient.  A zero numerator (a stopped car: Vc = 0, a = 0) sends
+// the device's fp64 division into its out-of-line slow path; a third of the cars stand still at any time, so the
+// quotient is formed from a stand-in numerator and the (signed) zero is passed through instead.
+MH_HD double div_pos(double x, double den) {
+    const bool z = (x == 0.0);
+    const double q = (z ? 1.0 : x) / den;
+    return z ? x : q;
+}
 MH_HD double dmax(double a, double b) { return b > a ? b : a; }   // Python max(a, b)
 
 // pedestrian.is_in_front, SC:463-468
@@ -139,8 +157,8 @@ MH_HD double sigma_lim(double Vc, double a, double dt) {
 MH_HD double idm(const EnvConst &c, const CarR &k, double leadSc, double leadVc) {
     const double dd = leadSc - k.Sc;
     const double dv = k.Vc - leadVc;
-    const double s = (2.0 + (k.Vc * 2.0)) + (k.Vc * dv) / (2.0 * sqrt(-c.acc_lo * c.acc_hi));
-    const double r4 = k.Vc / 10.0, r2 = s / dd;
+    const double s = (2.0 + (k.Vc * 2.0)) + div_pos(k.Vc * dv, c.idm_den);
+    const double r4 = div_pos(k.Vc, 10.0), r2 = s / dd;
     return c.acc_hi * ((1.0 - (r4 * r4) * (r4 * r4)) - r2 * r2);
 }
 // car.step SC:627-650 (ST:599-618 adds the clamp; car_follower.transform C4:79-93)
@@ -201,7 +219,7 @@ MH_HD void write_obs(const EnvConst &c, EnvR<MC, MP> &e, bool at_reset, Out &out
                 const CarR &k = e.car[i];
                 if (T::scal && !at_reset && !k.exist) continue;
                 if ((k.Sc <= p.Spx) && in_front(g, p, k.line, 0.0) && !left && (k.light >= 0.0)) {
-                    const double nd = (fabs(k.Sc - p.Spx) - (k.Vc * k.Vc / (-2.0 * c.acc_lo))) - 1.0 * k.Vc;
+                    const double nd = (fabs(k.Sc - p.Spx) - (k.Vc * k.Vc / c.brake_den)) - 1.0 * k.Vc;
                     dl = dmin(dl, nd);
                 }
             }

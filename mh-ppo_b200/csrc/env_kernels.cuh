@@ -13,17 +13,19 @@
 
 namespace mhppo {
 
-constexpr int kEnvBlock = 128;
+#ifndef MH_ENV_BLOCK
+#define MH_ENV_BLOCK 128
+#endif
+constexpr int kEnvBlock = MH_ENV_BLOCK;
 #ifndef MH_ENV_MIN_BLOCKS
-#define MH_ENV_MIN_BLOCKS 4
+#define MH_ENV_MIN_BLOCKS 5
 #endif
 constexpr int kEnvMinBlocks = MH_ENV_MIN_BLOCKS;   // CTAs per SM the register allocation is capped for
 
-// dynamic shared memory of the step kernel: the CTA's car slots and one gap queue per warp
+// dynamic shared memory of the step kernel: the CTA's car slots
 template <int MC>
 struct StepShared {
     CarSlots<MC, kEnvBlock> cars;
-    GapQueue queues[kEnvBlock / 32];
 };
 
 template <int V, int MC, int MP>
@@ -32,11 +34,8 @@ __global__ void __launch_bounds__(kEnvBlock, kEnvMinBlocks) k_env_step(const __g
     extern __shared__ __align__(16) unsigned char step_smem[];
     StepShared<MC> &sh = *reinterpret_cast<StepShared<MC> *>(step_smem);
     const int64_t n = (int64_t)blockIdx.x * kEnvBlock + threadIdx.x;
-    WarpCtx w;
-    w.mask = __ballot_sync(0xFFFFFFFFu, n < a.N);           // the last warp may own fewer than 32 envs
-    w.q = &sh.queues[threadIdx.x >> 5];
     if (n >= a.N) return;
-    env_step_thread<V, MC, MP, kEnvBlock>(a, c, key, io, n, w, sh.cars, (int)threadIdx.x);
+    env_step_thread<V, MC, MP, kEnvBlock>(a, c, key, io, n, sh.cars, (int)threadIdx.x);
 }
 
 template <int V, int MC, int MP>

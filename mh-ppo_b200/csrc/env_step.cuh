@@ -19,8 +19,9 @@
 //  * bulky rare paths are single out-of-line copies: the sin walking profile (fp64 sincos), the
 //    episode reset, and the exact fp64 critical gap.  The gap-acceptance decision
 //    `choix_pedestrian` runs every step for a waiting pedestrian, so its log10/pow/normal-draw
-//    comparison is a filtered predicate (fp32 with an error bound, fp64 only when undecidable), and
-//    the judgements of all lanes of a warp are evaluated side by side (choix_coop);
+//    comparison is a filtered predicate (fp32 with an error bound, fp64 only when undecidable).
+//    (Tried and dropped: queueing the judgements of a warp in shared memory and evaluating them one
+//    per lane.  With rolled car loops the lanes already meet at a single call site; it was 3 % slower.);
 //  * reward-shaping exponentials feed only fp32 outputs: their argument is formed in fp64 and the
 //    exponential itself is exp2f (DESIGN.md "Precision"); everything that feeds state or a
 //    threshold stays fp64 in the reference's operation order.
@@ -101,8 +102,8 @@ MH_HD int ctz32(uint32_t m) {
 //
 // The decision is split in two: choix_plan does everything that needs no normal draw (geometry,
 // the follower rules, the shuffle's draws) and returns either the answer or the ordered list of
-// cars whose gap must be judged; the gaps are then judged either one after the other (choix_fast)
-// or by the whole warp at once (choix_coop).  SC:162-173 walks the cars in front in ascending order:
+// cars whose gap must be judged (choix_fast then judges them in order; every lane of a warp reaches
+// that one rolled loop, so lanes with work run it together).  SC:162-173 walks the cars in front in ascending order:
 // a car standing on the crosswalk answers False, an upstream car answers False if its gap is
 // refused; the two cases exclude each other (on the crosswalk means Sc > Sp_x), so the walk is
 // "judge the upstream cars that come before the first car on the crosswalk, in order; False at the
@@ -113,17 +114,24 @@ MH_HD ChoixPlan choix_plan(const EnvConst &c, const Geo &g, const PedR &p, const
     typedef VT<V> T;
     ChoixPlan pl; pl.gaps = 0; pl.answer = -1; pl.tail_false = false;
     const int nseen = __builtin_popcount(seen);
+    // is_in_front / is_crossing_in_front depend on the car only through its lane: one evaluation per lane
+    uint32_t inf1_l = 0, cif_l = 0;
+#pragma unroll 1
+    for (int l = 0; l < c.L; ++l) {
+        inf1_l |= (in_front(g, p, l, 1.0) ? 1u : 0u) << l;
+        cif_l |= (crossing_in_front(g, p, l, 0.5) ? 1u : 0u) << l;
+    }
     uint32_t inf1 = 0, on_cross = 0, behind = 0, blocked = 0;
 #pragma unroll 1
     for (int i = 0; i < c.nC; ++i) {
         const double Sc = S.Sc[i][t];
         const int line = MH_LINE(S, i, t);
-        const bool f1 = in_front(g, p, line, 1.0);
-        const bool over = (Sc < 4.0 + p.Spx) && (Sc > p.Spx);                        // car body on the crosswalk
-        inf1 |= (f1 ? 1u : 0u) << i;
-        on_cross |= (over ? 1u : 0u) << i;
+        const uint32_t f1 = (inf1_l >> line) & 1u;
+        const uint32_t over = ((Sc < 4.0 + p.Spx) && (Sc > p.Spx)) ? 1u : 0u;        // car body on the crosswalk
+        inf1 |= f1 << i;
+        on_cross |= over << i;
         behind |= ((Sc < p.Spx) ? 1u : 0u) << i;
-        if (over && f1 && crossing_in_front(g, p, line, 0.5)) blocked |= 1u << i;
+        blocked |= (over & f1 & ((cif_l >> line) & 1u)) << i;
     }
     inf1 &= seen; on_cross &= seen; behind &= seen; blocked &= seen;
     if (p.fl & PF_FOLLOW) {
@@ -162,69 +170,6 @@ MH_HD bool choix_fast(const EnvConst &c, const Geo &g, const PedR &p, const CarS
         if (gap_refused<MC, NT>(g, p, S, t, ctz32(m), rng)) return false;
     return !pl.tail_false;
 }
-
-// ---- warp-cooperative form of the kerb decision ---------------------------------------------------
-// A pedestrian waiting at the kerb re-takes the decision every step (SC:311-318), so in a warp of
-// 32 envs a handful of lanes need one to four gap judgements each while the rest idle: executed in
-// place that is ~100 Philox + ~100 math instructions per judgement with two lanes active, a third of
-// the step's issue slots.  Instead every lane queues its judgements in shared memory and the warp
-// evaluates all of them side by side, one item per lane; because the generator is counter-based,
-// judgement number k of a lane uses block ctr+k whether or not an earlier one already refused, and
-// the lane afterwards advances its cursor only past the ones the sequential walk would have drawn.
-struct GapItem { double dx, vden, size; float light, v0y; uint32_t ctr, env_lo, env_hi, ga; };
-constexpr int kGapQ = 32;                                        // queue slots per warp per pass
-struct GapQueue { GapItem item[kGapQ]; uint8_t refused[kGapQ]; };
-struct WarpCtx { unsigned mask; GapQueue *q; };                  // mask: lanes of this warp that own an env
-
-#ifdef __CUDACC__
-template <int V, int MC, int NT>
-__device__ __forceinline__ bool choix_coop(const EnvConst &c, const Geo &g, const PedR &p, const CarSlots<MC, NT> &S, int t,
-                                           uint32_t seen, Rng &rng, bool need, const WarpCtx &w) {
-    const int lane = (int)(threadIdx.x & 31u);
-    ChoixPlan pl; pl.gaps = 0; pl.answer = 1; pl.tail_false = false;
-    if (need) pl = choix_plan<V, MC, NT>(c, g, p, S, t, seen, rng);
-    const uint32_t gm = (pl.answer < 0) ? pl.gaps : 0u;
-    const int cnt = __popc(gm);
-    int incl = cnt;                                              // inclusive scan of the item counts over the warp
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(w.mask, incl, d); if (lane >= d) incl += v; }
-    const int nlanes = __popc(w.mask);                           // the owning lanes are 0 .. nlanes-1 (kernel tail)
-    const int total = __shfl_sync(w.mask, incl, nlanes - 1);
-    const int base = incl - cnt;
-    uint32_t rb = 0;                                             // bit k: judgement k of this lane refused
-    for (int pass0 = 0; pass0 < total; pass0 += kGapQ) {         // warp-uniform; one pass unless > kGapQ judgements are queued
-        int rank = 0;
-        for (uint32_t m = gm; m; m &= m - 1u, ++rank) {
-            const int slot = base + rank - pass0;
-            if (slot < 0 || slot >= kGapQ) continue;
-            const int i = __ffs((int)m) - 1;
-            GapItem it;
-            it.dx = S.Sc[i][t] - p.Spx; it.vden = S.Vc[i][t] + 10e-3; it.size = fabs((double)(p.lpos - MH_LINE(S, i, t))) * g.cross;
-            it.light = S.light[i][t]; it.v0y = (float)p.v0y;                 // v0y is fp32 state, exact
-            it.ctr = rng.ctr + (uint32_t)rank; it.env_lo = rng.env_lo; it.env_hi = rng.env_hi;
-            it.ga = (uint32_t)p.gender | ((uint32_t)p.age << 8);
-            w.q->item[slot] = it;
-        }
-        __syncwarp(w.mask);
-        const int m_items = (total - pass0 < kGapQ) ? (total - pass0) : kGapQ;
-        for (int s = lane; s < m_items; s += nlanes) {
-            const GapItem it = w.q->item[s];
-            w.q->refused[s] = gap_eval(it.dx, it.vden, (double)it.light, it.size, (double)it.v0y, (int)(it.ga & 255u), (int)(it.ga >> 8),
-                                       it.ctr, it.env_lo, it.env_hi, rng.k0, rng.k1) ? 1 : 0;
-        }
-        __syncwarp(w.mask);
-        for (int k = 0; k < cnt; ++k) {
-            const int slot = base + k - pass0;
-            if (slot >= 0 && slot < kGapQ) rb |= (uint32_t)w.q->refused[slot] << k;
-        }
-        __syncwarp(w.mask);
-    }
-    if (pl.answer >= 0) return pl.answer != 0;
-    if (rb) { rng.ctr += (uint32_t)__ffs((int)rb); return false; }           // draws up to and including the first refusal
-    rng.ctr += (uint32_t)cnt;
-    return !pl.tail_false;
-}
-#endif
 
 struct WalkOut { double pos, spd; };
 // pedestrian.new_pedestrian_sin_y, SC:436-443 with the parameters of SC:94-102
@@ -380,7 +325,7 @@ MH_HD void ped_step_stream(const EnvConst &c, const Geo &g, PedR &p, const CarSl
 
 // ---------------------------------------------------------------------------------------------
 template <int V, int MC, int MP, int NT>
-MH_HD void env_step_thread(const EnvArena &a, const EnvConst &c, const RngKey &key, const StepIO &io, int64_t n, const WarpCtx &w,
+MH_HD void env_step_thread(const EnvArena &a, const EnvConst &c, const RngKey &key, const StepIO &io, int64_t n,
                            CarSlots<MC, NT> &S, int t) {
     typedef VT<V> T;
     // ---- env word
@@ -432,8 +377,10 @@ MH_HD void env_step_thread(const EnvArena &a, const EnvConst &c, const RngKey &k
                 car_move<V>(c, k, (double)ap[(int64_t)i * cs], (double)ap[(int64_t)(half + i) * cs]);
             }
             S.prevSc[i][t] = ka.y; S.Sc[i][t] = k.Sc; S.Vc[i][t] = k.Vc; S.light[i][t] = (float)k.light;
-            S.brake[i][t] = k.Vc * k.Vc / (-2.0 * c.acc_lo);
-            S.rVc[i][t] = 1.0 / k.Vc;
+            S.brake[i][t] = div_pos(k.Vc * k.Vc, c.brake_den);
+            // 1/Vc is only read for Vc >= 0.01 (SC:190 `Vc < 0.05`, SC:482 / ST:478 thresholds); below that a
+            // finite stand-in keeps a stopped car (Vc = 0) out of the division's slow path
+            S.rVc[i][t] = 1.0 / ((k.Vc >= 0.01) ? k.Vc : 1.0);
             S.pa[i][t] = kb.x; S.es[i][t] = kb.y; S.Ts[i][t] = kb.z; S.rl[i][t] = 0.f; S.wmin[i][t] = 0.f;
             S.bits[i][t] = b;
             const bool ex = !T::scal || k.exist;
@@ -452,7 +399,7 @@ MH_HD void env_step_thread(const EnvArena &a, const EnvConst &c, const RngKey &k
     const float green = (float)__builtin_popcount(lead_green);                       // SC:246
     const int env_w = T::scal ? 4 : 3;
     const int ped_o = T::car_w * c.nC + env_w;
-    const double time_braking = -(10.0 / (2.0 * c.acc_lo)) + 1.0;                    // SC:580
+    const double time_braking = c.time_braking;                                      // SC:580
     bool any_exist = false;
 
     // ---- pedestrians, streamed
@@ -471,12 +418,7 @@ MH_HD void env_step_thread(const EnvArena &a, const EnvConst &c, const RngKey &k
         }
         {                                                                            // SC:808-809
             const bool kerb = ped_flags(g, p);
-#ifdef __CUDA_ARCH__
-            const bool kerb_choice = choix_coop<V, MC, NT>(c, g, p, S, t, seen, rng, kerb, w);
-#else
             const bool kerb_choice = kerb ? choix_fast<V, MC, NT>(c, g, p, S, t, seen, rng) : true;
-            (void)w;
-#endif
             ped_step_stream<V, MC, NT>(c, g, p, S, t, seen, step, rng, kerb_choice);
         }
         const bool left = (p.fl & PF_LEFT) != 0;
@@ -487,14 +429,20 @@ MH_HD void env_step_thread(const EnvArena &a, const EnvConst &c, const RngKey &k
         // SC:449-460 with delta_l_all SC:508-514 over the cars handed to it: SC:803-806 / C4:796-799)
         uint32_t inf = 0, cif = 0, behind = 0;    // behind: Sc < Sp_x
         {
+            uint32_t inf_l = 0, cif_l = 0;        // both predicates depend on the car only through its lane
+#pragma unroll 1
+            for (int l = 0; l < c.L; ++l) {
+                inf_l |= (in_front(g, p, l, 0.0) ? 1u : 0u) << l;
+                cif_l |= (crossing_in_front(g, p, l, 0.0) ? 1u : 0u) << l;
+            }
             double dl = T::far;
 #pragma unroll 1
             for (int i = 0; i < c.nC; ++i) {
                 const double Sc = S.Sc[i][t];
                 const int line = MH_LINE(S, i, t);
-                const bool f0 = in_front(g, p, line, 0.0);
-                inf |= (f0 ? 1u : 0u) << i;
-                cif |= (crossing_in_front(g, p, line, 0.0) ? 1u : 0u) << i;
+                const uint32_t f0 = (inf_l >> line) & 1u;
+                inf |= f0 << i;
+                cif |= ((cif_l >> line) & 1u) << i;
                 behind |= ((Sc < p.Spx) ? 1u : 0u) << i;
                 if (((seen >> i) & 1u) && (Sc <= p.Spx) && f0 && !left && (S.light[i][t] >= 0.f))
                     dl = dmin(dl, (fabs(Sc - p.Spx) - S.brake[i][t]) - 1.0 * S.Vc[i][t]);

@@ -119,6 +119,8 @@ int mhppo_env_create(const mhppo_env_cfg *cfg, void **handle) {
     if (cfg->device < 0 || cfg->device >= ndev) return fail(MHPPO_EINVAL, "device ordinal out of range");
     CK(cudaSetDevice(cfg->device));
     CK(cudaFuncSetAttribute((const void *)k->step, cudaFuncAttributeMaxDynamicSharedMemorySize, k->step_smem));
+    // the step kernel streams its global data once (no L1 reuse) and keeps the cars in shared memory
+    CK(cudaFuncSetAttribute((const void *)k->step, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
 
     EnvHandle *h = new (std::nothrow) EnvHandle();
     if (!h) return fail(MHPPO_ENOMEM, "host allocation failed");
@@ -137,6 +139,7 @@ int mhppo_env_create(const mhppo_env_cfg *cfg, void **handle) {
     c.sin_model = cfg->sin_model; c.dt = cfg->dt; c.acc_lo = cfg->car_b[0]; c.acc_hi = cfg->car_b[2];
     for (int i = 0; i < 8; ++i) c.pb[i] = cfg->ped_b[i];
     c.cross_lo = cfg->cross_b[0]; c.cross_hi = cfg->cross_b[1];
+    env_const_finish(c);
     h->key.k0 = (uint32_t)cfg->seed; h->key.k1 = (uint32_t)(cfg->seed >> 32); h->key.env_id0 = cfg->env_id0;
 
     const int64_t N = cfg->n_envs;

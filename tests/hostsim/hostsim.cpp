@@ -38,7 +38,7 @@ static void sim_step(Sim *s, mhppo_view actions, mhppo_view obs, mhppo_view rewa
     io.done = done; io.autoreset = autoreset;
     RngKey key; key.k0 = s->k0; key.k1 = s->k1; key.env_id0 = s->env_id0;
     CarSlots<MC, 1> cars;
-    for (int64_t n = 0; n < s->a.N; ++n) env_step_thread<V, MC, MP, 1>(s->a, s->c, key, io, n, WarpCtx{0u, nullptr}, cars, 0);   // the kernel's thread body
+    for (int64_t n = 0; n < s->a.N; ++n) env_step_thread<V, MC, MP, 1>(s->a, s->c, key, io, n, cars, 0);   // the kernel's thread body
 }
 
 #define DISPATCH(FN, ...)                                                                          \
@@ -66,7 +66,7 @@ extern "C" {
 
 int hs_create(int variant, int mc, int mp, const EnvConst *c, int64_t N, uint64_t seed, int64_t env_id0, void **out) {
     Sim *s = (Sim *)calloc(1, sizeof(Sim));
-    s->variant = variant; s->mc = mc; s->mp = mp; s->c = *c; s->k0 = (uint32_t)seed; s->k1 = (uint32_t)(seed >> 32);
+    s->variant = variant; s->mc = mc; s->mp = mp; s->c = *c; env_const_finish(s->c); s->k0 = (uint32_t)seed; s->k1 = (uint32_t)(seed >> 32);
     s->env_id0 = env_id0; s->a.N = N;
     s->a.car_a = (float4 *)calloc((size_t)N * mc, 16); s->a.car_b = (float4 *)calloc((size_t)N * mc, 16);
     s->a.ped_a = (float4 *)calloc((size_t)N * mp, 16); s->a.ped_b = (float4 *)calloc((size_t)N * mp, 16);
