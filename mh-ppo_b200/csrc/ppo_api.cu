@@ -31,15 +31,14 @@ static int *fail_flag() {
 static size_t smem_tc(int nets) {
     return sizeof(float) * ((size_t)nets * ((tcm::NetTiles<16>::FLOATS + 255) & ~255) + 2 * 128 * H2) + 1024;
 }
+constexpr int kGradGrid = 148;       // k_ppo_grad: one persistent CTA per SM (its tile fills shared memory)
 constexpr int kUpdateGrid = 296;     // gradient partials of the update kernels: 148 SMs x 2 (CTAs of k_value_stats, teams of k_ppo_grad)
 
 template <int KP> static size_t smem_fwd(int nets) {
     return sizeof(float) * ((size_t)nets * ((net_params(KP) + 3) & ~3) + (size_t)kFwdBlock * kRowFwd);
 }
 template <int KP> static size_t smem_grad() {
-    typedef Strides<KP> St;
-    const int ROW = (St::X + St::A1 + St::A2 + St::A3 + OP) | 1;
-    return sizeof(float) * ((size_t)((net_params(KP) + 3) & ~3) + H2 * H1 + H3 * H2 + OP * H3 + (size_t)kTeams * kMlpBlock * ROW);
+    return sizeof(float) * GradCfg<KP>::smem_floats;
 }
 static RolloutDims dims_of(const mhppo_rollout_cfg *c) {
     RolloutDims d;
@@ -70,9 +69,9 @@ using namespace mhppo;
 template <int KP>
 static int launch_grad(int head, const SampleSet &ss, const float *net, const LossArgs &la, const Workspace &w, cudaStream_t s) {
     const size_t sm = smem_grad<KP>();
-    if (head == 0) { SET_SMEM((k_ppo_grad<KP, 0>), sm); k_ppo_grad<KP, 0><<<kUpdateGrid / kTeams, kMlpBlock * kTeams, sm, s>>>(ss, net, la, w.gpartial, w.lpartial); }
-    else if (head == 1) { SET_SMEM((k_ppo_grad<KP, 1>), sm); k_ppo_grad<KP, 1><<<kUpdateGrid / kTeams, kMlpBlock * kTeams, sm, s>>>(ss, net, la, w.gpartial, w.lpartial); }
-    else { SET_SMEM((k_ppo_grad<KP, 2>), sm); k_ppo_grad<KP, 2><<<kUpdateGrid / kTeams, kMlpBlock * kTeams, sm, s>>>(ss, net, la, w.gpartial, w.lpartial); }
+    if (head == 0) { SET_SMEM((k_ppo_grad<KP, 0>), sm); k_ppo_grad<KP, 0><<<kGradGrid, kMlpBlock, sm, s>>>(ss, net, la, w.gpartial, w.lpartial); }
+    else if (head == 1) { SET_SMEM((k_ppo_grad<KP, 1>), sm); k_ppo_grad<KP, 1><<<kGradGrid, kMlpBlock, sm, s>>>(ss, net, la, w.gpartial, w.lpartial); }
+    else { SET_SMEM((k_ppo_grad<KP, 2>), sm); k_ppo_grad<KP, 2><<<kGradGrid, kMlpBlock, sm, s>>>(ss, net, la, w.gpartial, w.lpartial); }
     api_count_launch();
     return ck(cudaGetLastError(), "k_ppo_grad");
 }
@@ -189,8 +188,8 @@ int mhppo_ppo_grad(int32_t n_in, int32_t head, const float *x, int32_t D, int64_
     int rc = (kp == 16) ? launch_grad<16>(head, ss, net, la, w, s) : ((kp == 32) ? launch_grad<32>(head, ss, net, la, w, s) : launch_grad<56>(head, ss, net, la, w, s));
     if (rc) return rc;
     const int npar = net_params(kp);
-    k_reduce_partials<<<(npar + 255) / 256, 256, 0, s>>>(w.gpartial, kUpdateGrid, npar, grad);
-    k_reduce_scalars<<<1, 32, 0, s>>>(w.lpartial, kUpdateGrid, 1, loss);
+    k_reduce_partials<<<(npar + 255) / 256, 256, 0, s>>>(w.gpartial, kGradGrid, npar, grad);
+    k_reduce_scalars<<<1, 32, 0, s>>>(w.lpartial, kGradGrid, 1, loss);
     api_count_launch(); api_count_launch();
     return ck(cudaGetLastError(), "k_reduce_partials");
 }

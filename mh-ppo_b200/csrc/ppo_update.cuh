@@ -9,11 +9,11 @@
 //   4. k_reduce      : fixed-order sum of the CTA partials -> flat gradient (deterministic)
 //   5. (multi-GPU: one NCCL all-reduce of the flat gradient buffer)       6. k_adam
 //
-// Execution model: thread = sample for forward and backward-data (activations of the CTA's 128
-// samples sit in shared memory as [sample][feature], deltas overwrite activations in place), then the
-// same 128 threads switch roles and each owns a strip of every weight matrix for the weight
-// gradient dWt[k][j] += sum_s in[s][k] * delta[s][j], accumulated in registers across all tiles
-// of a persistent CTA.
+// Execution model: thread = sample(s) for forward and backward-data (activations of the CTA's tile sit
+// in shared memory as [sample][feature], deltas overwrite activations in place), then the same 128
+// threads switch roles and each owns a register tile of every weight matrix for the weight
+// gradient dWt[k][j] += sum_s in[s][k] * delta[s][j], accumulated across all tiles of a
+// persistent CTA (one per SM).
 #pragma once
 #include "mlp.cuh"
 
@@ -91,60 +91,145 @@ struct LossArgs {
     float f0, f1;                              // choice only: fraction of samples whose action is 0 / 1 (PY:834-842 broadcast)
 };
 
-// backward-data for this thread's sample: din[k] = relu'(ain[k]) * sum_j dout[j] * W[j][k], written over ain
-template <int K, int J>
-__device__ __forceinline__ void dense_bwd_data(float *__restrict__ ain_din, const float *__restrict__ dout, const float *__restrict__ W /* [J][K] */) {
-    float acc[K];
+// ---- register-tiled dense layers for the fused kernel -------------------------------------------------
+// The first version read one weight per FFMA from shared memory (a 128-bit broadcast load feeds 4 FFMAs of
+// one sample) and the weight-gradient strips read one delta per FFMA: 3 shared-memory wavefront cycles per
+// FFMA issue cycle, FMA pipe 27 % busy (profiles/round1_ppo_kernels_summary.txt).  Here every thread owns R
+// samples (rows tid, tid + 128, ...) so a weight load feeds R x 4 FFMAs, every row access is a 128-bit
+// load/store (rows are 16-byte aligned, row stride = 4 mod 32 words: 8 lanes x 16 B per wavefront, conflict-free),
+// and the weight gradient is a 4 x 8 register tile per thread.
+template <int KP>
+struct GradCfg {
+    static constexpr int R = (KP <= 16) ? 2 : 1;                    // samples per thread (shared memory bounds it)
+    static constexpr int TILE = kMlpBlock * R;                      // samples per CTA tile
+    static constexpr int X = 0, A1 = KP, A2 = KP + H1, A3 = KP + H1 + H2, D4 = KP + H1 + H2 + H3, RAW = D4 + OP;
+    static constexpr int ROW = ((RAW - 4 + 31) / 32) * 32 + 4;      // >= RAW and = 4 (mod 32)
+    static constexpr int NPAR = net_params(KP), NP4 = (NPAR + 3) & ~3;
+    static constexpr size_t smem_floats = (size_t)NP4 + H2 * H1 + H3 * H2 + OP * H3 + (size_t)TILE * ROW;
+};
+
+__device__ __forceinline__ float4 ld4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
+__device__ __forceinline__ void st4(float *p, float4 v) { *reinterpret_cast<float4 *>(p) = v; }
+
+// out[r][j] = act(b[j] + sum_k in[r][k] * Wt[k][j]) for the R rows of this thread; rows are `rs` floats apart
+template <int K, int J, bool RELU, int R>
+__device__ __forceinline__ void dense_fwd_t(const float *in, float *out, int rs, const float *__restrict__ Wt, const float *__restrict__ b) {
+    constexpr int JC = (J < 32) ? J : 32;
+#pragma unroll 1
+    for (int jc = 0; jc < J; jc += JC) {
+        float acc[R][JC];
 #pragma unroll
-    for (int k = 0; k < K; ++k) acc[k] = 0.f;
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int j = 0; j < JC; ++j) acc[r][j] = b[jc + j];
 #pragma unroll 2
-    for (int j = 0; j < J; ++j) {
-        const float dj = dout[j];
-        const float4 *w = reinterpret_cast<const float4 *>(W + j * K);
+        for (int k = 0; k < K; k += 4) {
+            float a[R][4];
 #pragma unroll
-        for (int k4 = 0; k4 < K / 4; ++k4) {
-            const float4 ww = w[k4];
-            acc[4 * k4 + 0] = fmaf(dj, ww.x, acc[4 * k4 + 0]); acc[4 * k4 + 1] = fmaf(dj, ww.y, acc[4 * k4 + 1]);
-            acc[4 * k4 + 2] = fmaf(dj, ww.z, acc[4 * k4 + 2]); acc[4 * k4 + 3] = fmaf(dj, ww.w, acc[4 * k4 + 3]);
+            for (int r = 0; r < R; ++r) { const float4 v = ld4(in + r * rs + k); a[r][0] = v.x; a[r][1] = v.y; a[r][2] = v.z; a[r][3] = v.w; }
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+                for (int j4 = 0; j4 < JC / 4; ++j4) {
+                    const float4 w = ld4(Wt + (k + kk) * J + jc + 4 * j4);
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        acc[r][4 * j4 + 0] = fmaf(a[r][kk], w.x, acc[r][4 * j4 + 0]); acc[r][4 * j4 + 1] = fmaf(a[r][kk], w.y, acc[r][4 * j4 + 1]);
+                        acc[r][4 * j4 + 2] = fmaf(a[r][kk], w.z, acc[r][4 * j4 + 2]); acc[r][4 * j4 + 3] = fmaf(a[r][kk], w.w, acc[r][4 * j4 + 3]);
+                    }
+                }
         }
-    }
 #pragma unroll
-    for (int k = 0; k < K; ++k) ain_din[k] = (ain_din[k] > 0.f) ? acc[k] : 0.f;
-}
-
-// weight-gradient strip owned by this thread: NJ consecutive outputs j0.. of input row kk, summed over the tile
-template <int NJ>
-__device__ __forceinline__ void wgrad_strip(float (&acc)[NJ], const float *__restrict__ in, int in_stride, int kk,
-                                            const float *__restrict__ dl, int dl_stride, int j0, bool active) {
-    if (!active) return;
-#pragma unroll 4
-    for (int s = 0; s < kMlpBlock; ++s) {
-        const float a = in[s * in_stride + kk];
-        const float *dr = dl + s * dl_stride + j0;
+        for (int r = 0; r < R; ++r)
 #pragma unroll
-        for (int j = 0; j < NJ; ++j) acc[j] = fmaf(a, dr[j], acc[j]);
+            for (int j4 = 0; j4 < JC / 4; ++j4) {
+                float4 o = make_float4(acc[r][4 * j4], acc[r][4 * j4 + 1], acc[r][4 * j4 + 2], acc[r][4 * j4 + 3]);
+                if (RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                st4(out + r * rs + jc + 4 * j4, o);
+            }
     }
 }
 
-// HEAD: 0 = critic (MSE), 1 = Gaussian actor (clipped surrogate), 2 = categorical actor with the (M,M) broadcast
-// A CTA holds kTeams independent 128-thread teams that share the staged weights; each team walks its own tiles and
-// synchronises on its own named barrier, so two tiles are in flight per SM (shared memory allows one 128-row tile set
-// per team, registers allow 256 threads).
+// backward-data for the R rows of this thread: din[k] = relu'(ain[k]) * sum_j dout[j] * W[j][k], written over ain
+template <int K, int J, int R>
+__device__ __forceinline__ void dense_bwd_t(float *ain_din, const float *dout, int rs, const float *__restrict__ W /* [J][K] */) {
+    constexpr int KC = (K < 32) ? K : 32;
+#pragma unroll 1
+    for (int kc = 0; kc < K; kc += KC) {
+        float acc[R][KC];
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int k = 0; k < KC; ++k) acc[r][k] = 0.f;
+#pragma unroll 2
+        for (int j = 0; j < J; j += 4) {
+            float d[R][4];
+#pragma unroll
+            for (int r = 0; r < R; ++r) { const float4 v = ld4(dout + r * rs + j); d[r][0] = v.x; d[r][1] = v.y; d[r][2] = v.z; d[r][3] = v.w; }
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+                for (int k4 = 0; k4 < KC / 4; ++k4) {
+                    const float4 w = ld4(W + (j + jj) * K + kc + 4 * k4);
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        acc[r][4 * k4 + 0] = fmaf(d[r][jj], w.x, acc[r][4 * k4 + 0]); acc[r][4 * k4 + 1] = fmaf(d[r][jj], w.y, acc[r][4 * k4 + 1]);
+                        acc[r][4 * k4 + 2] = fmaf(d[r][jj], w.z, acc[r][4 * k4 + 2]); acc[r][4 * k4 + 3] = fmaf(d[r][jj], w.w, acc[r][4 * k4 + 3]);
+                    }
+                }
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int k4 = 0; k4 < KC / 4; ++k4) {
+                float *q = ain_din + r * rs + kc + 4 * k4;
+                const float4 av = ld4(q);
+                st4(q, make_float4(av.x > 0.f ? acc[r][4 * k4] : 0.f, av.y > 0.f ? acc[r][4 * k4 + 1] : 0.f,
+                                   av.z > 0.f ? acc[r][4 * k4 + 2] : 0.f, av.w > 0.f ? acc[r][4 * k4 + 3] : 0.f));
+            }
+    }
+}
+
+// weight-gradient register tile: acc[kk][j] += in[s][k0 + kk] * delta[s][j0 + j] over the rows [s0, s0 + ns) of the tile
+template <int TJ>
+__device__ __forceinline__ void wgrad_tile(float (&acc)[4][TJ], const float *__restrict__ rows, int row, int in_off, int dl_off, int s0, int ns) {
+#pragma unroll 2
+    for (int s = s0; s < s0 + ns; ++s) {
+        const float *r = rows + (size_t)s * row;
+        const float4 av = ld4(r + in_off);
+        const float a[4] = {av.x, av.y, av.z, av.w};
+        float d[TJ];
+        if (TJ == 2) { const float2 v = *reinterpret_cast<const float2 *>(r + dl_off); d[0] = v.x; d[1] = v.y; }
+        else {
+#pragma unroll
+            for (int j4 = 0; j4 < TJ / 4; ++j4) { const float4 v = ld4(r + dl_off + 4 * j4); d[4 * j4] = v.x; d[4 * j4 + 1] = v.y; d[4 * j4 + 2] = v.z; d[4 * j4 + 3] = v.w; }
+        }
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+            for (int j = 0; j < TJ; ++j) acc[kk][j] = fmaf(a[kk], d[j], acc[kk][j]);
+    }
+}
+
+// HEAD: 0 = critic (MSE), 1 = Gaussian actor (clipped surrogate), 2 = categorical actor with the (M,M) broadcast.
+// Per tile: [thread = sample] forward + loss + dz; then, layer by layer from the top, [tiles] weight gradient from
+// (input activation, delta) and [thread = sample] backward-data which overwrites the activation with its delta.
+// For the weight gradient the CTA splits into two halves of 64 threads; each half sums over half of the tile's rows
+// and every thread of a half owns a 4 x TJ tile of every matrix; the halves are added once, after the last tile.
 constexpr int kTeams = 1;
 template <int KP, int HEAD>
-__global__ void __launch_bounds__(kMlpBlock * kTeams) k_ppo_grad(SampleSet ss, const float *__restrict__ net, LossArgs la,
-                                                        float *__restrict__ gpartial /* [grid][net_params] */,
-                                                        double *__restrict__ lpartial /* [grid] */) {
+__global__ void __launch_bounds__(kMlpBlock, 1) k_ppo_grad(SampleSet ss, const float *__restrict__ net, LossArgs la,
+                                                           float *__restrict__ gpartial /* [grid][net_params] */,
+                                                           double *__restrict__ lpartial /* [grid] */) {
     extern __shared__ __align__(16) float smem[];
-    typedef Strides<KP> St;
-    constexpr int NPAR = net_params(KP), NP4 = (NPAR + 3) & ~3;
+    typedef GradCfg<KP> G;
+    constexpr int R = G::R, ROW = G::ROW, NPAR = G::NPAR;
     float *sw = smem;                                  // flat net (transposed weights)
-    float *W2 = sw + NP4;                              // [H2][H1] original orientation, for backward-data
+    float *W2 = sw + G::NP4;                           // [H2][H1] original orientation, for backward-data
     float *W3 = W2 + H2 * H1;                          // [H3][H2]
     float *W4 = W3 + H3 * H2;                          // [OP][H3]
     float *rows = W4 + OP * H3;
-    constexpr int ROW = (St::X + St::A1 + St::A2 + St::A3 + OP) | 1;   // odd row stride: lane = sample is conflict-free
-    __shared__ double red_all[kTeams][kMlpBlock / 32];
+    __shared__ double red[kMlpBlock / 32];
     stage_net<KP>(sw, net);
     __syncthreads();
     for (int i = threadIdx.x; i < H1 * H2; i += blockDim.x) { const int k = i / H2, j = i % H2; W2[j * H1 + k] = sw[off_w2(KP) + i]; }
@@ -152,136 +237,159 @@ __global__ void __launch_bounds__(kMlpBlock * kTeams) k_ppo_grad(SampleSet ss, c
     for (int i = threadIdx.x; i < H3 * OP; i += blockDim.x) { const int k = i / OP, j = i % OP; W4[j * H3 + k] = sw[off_w4(KP) + i]; }
     __syncthreads();
 
-    const int team = threadIdx.x / kMlpBlock, tid = threadIdx.x % kMlpBlock, bar = team + 1;
-    const int unit = blockIdx.x * kTeams + team, nunits = gridDim.x * kTeams;
-    rows += (size_t)team * kMlpBlock * ROW;
-    double *red = red_all[team];
-#define TEAM_SYNC() team_sync(bar, kMlpBlock)
-    float *x = rows + (size_t)tid * ROW, *a1 = x + St::X, *a2 = a1 + St::A1, *a3 = a2 + St::A2, *d4 = a3 + St::A3;
-    // weight-gradient strips of this thread (persist over all tiles of this CTA)
-    constexpr int NJ1 = (KP <= 16) ? 4 : ((KP <= 32) ? 8 : 16);
-    constexpr int KK1 = (KP <= 16) ? 16 : ((KP <= 32) ? 32 : 64);       // threads along k for layer 1
-    float g1[NJ1], g2[16], g3[16], g4 = 0.f, gb = 0.f, gbias = 0.f;
-    // bias gradients b3 | b2 | b1: 32 + 64 + 32 = 128 columns, one per thread
-    const int bias_off = (tid < 32) ? (St::X + St::A1 + St::A2 + tid) : ((tid < 96) ? (St::X + St::A1 + (tid - 32)) : (St::X + (tid - 96)));
+    const int tid = threadIdx.x, half = tid >> 6, lt = tid & 63;
+    float *my = rows + (size_t)tid * ROW;              // row of this thread's first sample; the r-th is kMlpBlock rows further
+    constexpr int RS = kMlpBlock * ROW;
+    // weight-gradient tiles of this thread (persist over all tiles of this CTA)
+    constexpr int NKG1 = KP / 4;                                        // k-groups of layer 1
+    constexpr int JG1 = (NKG1 <= 4) ? 16 : ((NKG1 <= 8) ? 8 : 4);       // j-groups of layer 1 (NKG1 * JG1 <= 64 threads)
+    constexpr int TJ1 = H1 / JG1;
+    float g1[4][TJ1], g2[4][8], g3[4][8], g4[2] = {0.f, 0.f}, gb4[2] = {0.f, 0.f}, gbias[2] = {0.f, 0.f};
 #pragma unroll
-    for (int j = 0; j < NJ1; ++j) g1[j] = 0.f;
+    for (int kk = 0; kk < 4; ++kk) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) { g2[j] = 0.f; g3[j] = 0.f; }
+        for (int j = 0; j < TJ1; ++j) g1[kk][j] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { g2[kk][j] = 0.f; g3[kk][j] = 0.f; }
+    }
+    const bool l1_on = lt < NKG1 * JG1;
+    const int k1 = (lt % NKG1) * 4, j1 = (lt / NKG1) * TJ1;             // dW1t[k < KP][j < 32]
+    const int k2 = (lt & 7) * 4, j2 = (lt >> 3) * 8;                    // dW2t[k < 32][j < 64]
+    const int k3 = (lt & 15) * 4, j3 = (lt >> 4) * 8;                   // dW3t[k < 64][j < 32]
+    const int k4 = lt & 31, j4 = (lt >> 5) * 2;                         // dW4t[k < 32][j < 4]
+    constexpr int HALF = G::TILE / 2;
+    const int s0 = half * HALF;
     double loss = 0.0;
 
-    for (int64_t base = (int64_t)unit * kMlpBlock; base < ss.Q; base += (int64_t)nunits * kMlpBlock) {
-        int64_t s = 0;
-        const bool sel = map_sample(ss, base + tid, s);
-        float dz[OP] = {0.f, 0.f, 0.f, 0.f};
-        if (sel) {
-            load_row<KP>(ss, s, x);
-            const float4 o = mlp_fwd_rows<KP>(sw, x, a1, a2, a3);
-            if (HEAD == 0) {                                           // critic_loss = MSE(V, rtg), PY:808-809
-                const float e = o.x - la.rtg[s];
-                loss += (double)e * (double)e * (double)la.inv_n;
-                dz[0] = 2.0f * e * la.inv_n;
-            } else {
-                const float An = ((la.rtg[s] - la.V[s]) - la.adv_mean) * la.adv_inv_std;     // PY:786-787
-                if (HEAD == 1) {
-                    const float th = tanhf(o.x), mu = th * 3.0f + (-1.0f);
-                    const float a = la.act[s];
-                    const float lp = -((a - mu) * (a - mu)) - 0.57236494292470008f;          // MVN(mu, .5 I).log_prob, PY:795-800
-                    const float ratio = expf(lp - la.logp_old[s]);                           // PY:803
-                    const float s1 = ratio * An, s2 = fminf(fmaxf(ratio, 0.8f), 1.2f) * An;   // PY:804-805
-                    loss += (double)(-fminf(s1, s2)) * (double)la.inv_n;                     // PY:806
-                    if (s1 <= s2) dz[0] = -la.inv_n * An * ratio * (2.0f * (a - mu)) * (3.0f * (1.0f - th * th));
+    for (int64_t base = (int64_t)blockIdx.x * G::TILE; base < ss.Q; base += (int64_t)gridDim.x * G::TILE) {
+        bool sel[R];
+        int64_t sidx[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            sidx[r] = 0;
+            sel[r] = map_sample(ss, base + tid + r * kMlpBlock, sidx[r]);
+            float *x = my + r * RS;
+#pragma unroll
+            for (int k = 0; k < KP; k += 4) {
+                float4 v;
+                v.x = (sel[r] && k + 0 < ss.D) ? ss.x[(int64_t)(k + 0) * ss.S + sidx[r]] : 0.f;
+                v.y = (sel[r] && k + 1 < ss.D) ? ss.x[(int64_t)(k + 1) * ss.S + sidx[r]] : 0.f;
+                v.z = (sel[r] && k + 2 < ss.D) ? ss.x[(int64_t)(k + 2) * ss.S + sidx[r]] : 0.f;
+                v.w = (sel[r] && k + 3 < ss.D) ? ss.x[(int64_t)(k + 3) * ss.S + sidx[r]] : 0.f;
+                st4(x + k, v);
+            }
+        }
+        dense_fwd_t<KP, H1, true, R>(my + G::X, my + G::A1, RS, sw, sw + off_b1(KP));
+        dense_fwd_t<H1, H2, true, R>(my + G::A1, my + G::A2, RS, sw + off_w2(KP), sw + off_b2(KP));
+        dense_fwd_t<H2, H3, true, R>(my + G::A2, my + G::A3, RS, sw + off_w3(KP), sw + off_b3(KP));
+        dense_fwd_t<H3, OP, false, R>(my + G::A3, my + G::D4, RS, sw + off_w4(KP), sw + off_b4(KP));
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            float *row = my + r * RS;
+            const float4 o = ld4(row + G::D4);
+            const int64_t s = sidx[r];
+            float dz[OP] = {0.f, 0.f, 0.f, 0.f};
+            if (sel[r]) {
+                if (HEAD == 0) {                                           // critic_loss = MSE(V, rtg), PY:808-809
+                    const float e = o.x - la.rtg[s];
+                    loss += (double)e * (double)e * (double)la.inv_n;
+                    dz[0] = 2.0f * e * la.inv_n;
                 } else {
-                    // Categorical(probs [M,2]).log_prob(actions [M,1]) broadcasts to (M,M): lp[i,j] = log p_j(a_i)
-                    // (PY:834-842).  With two actions the mean over i collapses to the action frequencies f0, f1.
-                    const float m = fmaxf(o.x, o.y), e0 = expf(o.x - m), e1 = expf(o.y - m);
-                    const float p0 = e0 / (e0 + e1), p1 = e1 / (e0 + e1);
-                    const float inv_old = expf(-la.logp_old[s]);
-                    float dp0 = 0.f, dp1 = 0.f;
-                    {
-                        const float r = p0 * inv_old, s1 = r * An, s2 = fminf(fmaxf(r, 0.8f), 1.2f) * An;
-                        loss += (double)(-fminf(s1, s2)) * (double)(la.f0 * la.inv_n);
-                        if (s1 <= s2) dp0 = -la.inv_n * la.f0 * An * inv_old;
+                    const float An = ((la.rtg[s] - la.V[s]) - la.adv_mean) * la.adv_inv_std;     // PY:786-787
+                    if (HEAD == 1) {
+                        const float th = tanhf(o.x), mu = th * 3.0f + (-1.0f);
+                        const float a = la.act[s];
+                        const float lp = -((a - mu) * (a - mu)) - 0.57236494292470008f;          // MVN(mu, .5 I).log_prob, PY:795-800
+                        const float ratio = expf(lp - la.logp_old[s]);                           // PY:803
+                        const float s1 = ratio * An, s2 = fminf(fmaxf(ratio, 0.8f), 1.2f) * An;   // PY:804-805
+                        loss += (double)(-fminf(s1, s2)) * (double)la.inv_n;                     // PY:806
+                        if (s1 <= s2) dz[0] = -la.inv_n * An * ratio * (2.0f * (a - mu)) * (3.0f * (1.0f - th * th));
+                    } else {
+                        // Categorical(probs [M,2]).log_prob(actions [M,1]) broadcasts to (M,M): lp[i,j] = log p_j(a_i)
+                        // (PY:834-842).  With two actions the mean over i collapses to the action frequencies f0, f1.
+                        const float m = fmaxf(o.x, o.y), e0 = expf(o.x - m), e1 = expf(o.y - m);
+                        const float p0 = e0 / (e0 + e1), p1 = e1 / (e0 + e1);
+                        const float inv_old = expf(-la.logp_old[s]);
+                        float dp0 = 0.f, dp1 = 0.f;
+                        {
+                            const float rr = p0 * inv_old, s1 = rr * An, s2 = fminf(fmaxf(rr, 0.8f), 1.2f) * An;
+                            loss += (double)(-fminf(s1, s2)) * (double)(la.f0 * la.inv_n);
+                            if (s1 <= s2) dp0 = -la.inv_n * la.f0 * An * inv_old;
+                        }
+                        {
+                            const float rr = p1 * inv_old, s1 = rr * An, s2 = fminf(fmaxf(rr, 0.8f), 1.2f) * An;
+                            loss += (double)(-fminf(s1, s2)) * (double)(la.f1 * la.inv_n);
+                            if (s1 <= s2) dp1 = -la.inv_n * la.f1 * An * inv_old;
+                        }
+                        // softmax backward: dz_a = p_a * (dp_a - sum_b p_b dp_b)
+                        const float dot = p0 * dp0 + p1 * dp1;
+                        dz[0] = p0 * (dp0 - dot); dz[1] = p1 * (dp1 - dot);
                     }
-                    {
-                        const float r = p1 * inv_old, s1 = r * An, s2 = fminf(fmaxf(r, 0.8f), 1.2f) * An;
-                        loss += (double)(-fminf(s1, s2)) * (double)(la.f1 * la.inv_n);
-                        if (s1 <= s2) dp1 = -la.inv_n * la.f1 * An * inv_old;
-                    }
-                    // softmax backward: dz_a = p_a * (dp_a - sum_b p_b dp_b)
-                    const float dot = p0 * dp0 + p1 * dp1;
-                    dz[0] = p0 * (dp0 - dot); dz[1] = p1 * (dp1 - dot);
                 }
             }
-        } else {
-#pragma unroll
-            for (int k = 0; k < KP; ++k) x[k] = 0.f;
-            for (int k = 0; k < H1; ++k) a1[k] = 0.f;
-            for (int k = 0; k < H2; ++k) a2[k] = 0.f;
-            for (int k = 0; k < H3; ++k) a3[k] = 0.f;
+            // an unselected row has x = 0 but its activations are relu(bias) != 0: its dz = 0 keeps every gradient term zero
+            st4(row + G::D4, make_float4(dz[0], dz[1], dz[2], dz[3]));
         }
+        __syncthreads();
+        // layer 4: dW4t[k][j], b4[j]
+        for (int s = s0; s < s0 + HALF; ++s) {
+            const float *r = rows + (size_t)s * ROW;
+            const float a = r[G::A3 + k4];
+            const float2 d = *reinterpret_cast<const float2 *>(r + G::D4 + j4);
+            g4[0] = fmaf(a, d.x, g4[0]); g4[1] = fmaf(a, d.y, g4[1]);
+            gb4[0] += d.x; gb4[1] += d.y;
+        }
+        __syncthreads();
+        dense_bwd_t<H3, OP, R>(my + G::A3, my + G::D4, RS, W4);           // a3 now holds delta3
+        __syncthreads();
+        wgrad_tile<8>(g3, rows, ROW, G::A2 + k3, G::A3 + j3, s0, HALF);
+        __syncthreads();
+        dense_bwd_t<H2, H3, R>(my + G::A2, my + G::A3, RS, W3);           // a2 now holds delta2
+        __syncthreads();
+        wgrad_tile<8>(g2, rows, ROW, G::A1 + k2, G::A2 + j2, s0, HALF);
+        __syncthreads();
+        dense_bwd_t<H1, H2, R>(my + G::A1, my + G::A2, RS, W2);           // a1 now holds delta1
+        __syncthreads();
+        if (l1_on) wgrad_tile<TJ1>(g1, rows, ROW, G::X + k1, G::A1 + j1, s0, HALF);
+        // bias gradients b1 | b2 | b3: the deltas now sit in a1, a2, a3 of every row (128 consecutive columns)
+        for (int s = s0; s < s0 + HALF; ++s) {
+            const float2 d = *reinterpret_cast<const float2 *>(rows + (size_t)s * ROW + G::A1 + 2 * lt);
+            gbias[0] += d.x; gbias[1] += d.y;
+        }
+        __syncthreads();
+    }
+    // ---- add the two halves and emit this CTA's partial gradient
+    float *scratch = rows;                              // NPAR floats, the tile rows are dead now
+    auto emit = [&](float *dst, bool add) {
+        if (l1_on)
 #pragma unroll
-        for (int j = 0; j < OP; ++j) d4[j] = dz[j];
-        TEAM_SYNC();
-        // layer-4 weight / bias gradient: thread (k = tid % 32, j = tid / 32), 32*4 = 128 entries
-        {
-            const int kk = tid & 31, j = tid >> 5;
-            float acc = 0.f, accb = 0.f;
-            for (int s2 = 0; s2 < kMlpBlock; ++s2) {
-                const float dd = rows[s2 * ROW + (St::X + St::A1 + St::A2 + St::A3) + j];
-                acc = fmaf(rows[s2 * ROW + (St::X + St::A1 + St::A2) + kk], dd, acc);
-                accb += dd;
+            for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+                for (int j = 0; j < TJ1; ++j) { float &q = dst[(k1 + kk) * H1 + j1 + j]; q = add ? q + g1[kk][j] : g1[kk][j]; }
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float &q2 = dst[off_w2(KP) + (k2 + kk) * H2 + j2 + j]; q2 = add ? q2 + g2[kk][j] : g2[kk][j];
+                float &q3 = dst[off_w3(KP) + (k3 + kk) * H3 + j3 + j]; q3 = add ? q3 + g3[kk][j] : g3[kk][j];
             }
-            g4 += acc;
-            if (kk == 0) gb += accb;          // b4[j]
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            float &q4 = dst[off_w4(KP) + k4 * OP + j4 + j]; q4 = add ? q4 + g4[j] : g4[j];
+            if (k4 == 0) { float &qb = dst[off_b4(KP) + j4 + j]; qb = add ? qb + gb4[j] : gb4[j]; }
+            const int c = 2 * lt + j;                   // column of (b1 | b2 | b3)
+            const int o = (c < H1) ? (off_b1(KP) + c) : ((c < H1 + H2) ? (off_b2(KP) + c - H1) : (off_b3(KP) + c - H1 - H2));
+            float &qq = dst[o]; qq = add ? qq + gbias[j] : gbias[j];
         }
-        TEAM_SYNC();
-        dense_bwd_data<H3, OP>(a3, d4, W4);                            // a3 now holds delta3
-        TEAM_SYNC();
-        wgrad_strip<16>(g3, rows + St::X + St::A1, ROW, tid & 63, rows + St::X + St::A1 + St::A2, ROW, (tid >> 6) * 16, true);   // dW3t[k<64][j<32]
-        TEAM_SYNC();
-        dense_bwd_data<H2, H3>(a2, a3, W3);                            // a2 now holds delta2
-        TEAM_SYNC();
-        wgrad_strip<16>(g2, rows + St::X, ROW, tid & 31, rows + St::X + St::A1, ROW, (tid >> 5) * 16, true);                      // dW2t[k<32][j<64]
-        TEAM_SYNC();
-        dense_bwd_data<H1, H2>(a1, a2, W2);                            // a1 now holds delta1
-        TEAM_SYNC();
-        wgrad_strip<NJ1>(g1, rows, ROW, tid % KK1, rows + St::X, ROW, (tid / KK1) * NJ1, (tid % KK1) < KP);                        // dW1t[k<KP][j<32]
-        // bias gradients b3, b2, b1: the deltas now sit in a3, a2, a1 of every row
-        {
-            float acc = 0.f;
-#pragma unroll 4
-            for (int s2 = 0; s2 < kMlpBlock; ++s2) acc += rows[s2 * ROW + bias_off];
-            gbias += acc;
-        }
-        TEAM_SYNC();
-    }
-    float *gp = gpartial + (size_t)unit * NPAR;
-    {
-        const int kk = tid % KK1, j0 = (tid / KK1) * NJ1;
-        if (kk < KP)
-#pragma unroll
-            for (int j = 0; j < NJ1; ++j) gp[kk * H1 + j0 + j] = g1[j];
-    }
-    {
-        const int kk = tid & 31, j0 = (tid >> 5) * 16;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) gp[off_w2(KP) + kk * H2 + j0 + j] = g2[j];
-    }
-    {
-        const int kk = tid & 63, j0 = (tid >> 6) * 16;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) gp[off_w3(KP) + kk * H3 + j0 + j] = g3[j];
-    }
-    {
-        const int kk = tid & 31, j = tid >> 5;
-        gp[off_w4(KP) + kk * OP + j] = g4;
-        if (kk == 0) gp[off_b4(KP) + j] = gb;
-    }
-    gp[(tid < 32) ? (off_b3(KP) + tid) : ((tid < 96) ? (off_b2(KP) + tid - 32) : (off_b1(KP) + tid - 96))] = gbias;
-    const double lt = team_sum(loss, red, tid, kMlpBlock, bar);
-    if (tid == 0) lpartial[unit] = lt;
-#undef TEAM_SYNC
+    };
+    if (half == 1) emit(scratch, false);
+    __syncthreads();
+    if (half == 0) emit(scratch, true);
+    __syncthreads();
+    float *gp = gpartial + (size_t)blockIdx.x * NPAR;
+    for (int i = tid; i < NPAR; i += kMlpBlock) gp[i] = scratch[i];
+    const double lt_sum = team_sum(loss, red, tid, kMlpBlock, 0);
+    if (tid == 0) lpartial[blockIdx.x] = lt_sum;
 }
 
 // ---- 4. deterministic reduction of the per-CTA partials ----------------------------------------------
