@@ -210,6 +210,7 @@ def main():
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
     ap.add_argument("--ppo-envs", type=int, default=131072, help="envs per GPU of the PPO samples/s section (0 = skip)")
     ap.add_argument("--ppo-iters", type=int, default=2)
+    ap.add_argument("--row-major-actions", action="store_true", help="device-resident actions as a contiguous [N, A] tensor (gym layout)")
     args = ap.parse_args()
     wl = list(WORKLOADS[args.workload])
     if args.envs:
@@ -240,7 +241,8 @@ def main():
     g = torch.Generator(device=dev).manual_seed(1000 + rank)
     pool = []
     for _ in range(4):   # synthetic actions resident in HBM: acc ~ U(-4,2), light in {-1,+1}
-        a = torch.empty(n_envs, A, device=dev)
+        # [N, A] view of a component-major buffer: the layout the rollout kernels hand to env.step (coalesced reads)
+        a = torch.empty(n_envs, A, device=dev) if args.row_major_actions else torch.empty(A, n_envs, device=dev).t()
         a[:, :A // 2] = torch.rand(n_envs, A // 2, device=dev, generator=g) * 6 - 4
         a[:, A // 2:] = (torch.rand(n_envs, A // 2, device=dev, generator=g) < 0.5).float() * 2 - 1
         pool.append(a)
