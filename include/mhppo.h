@@ -156,6 +156,17 @@ int mhppo_choice_act(const mhppo_rollout_cfg *cfg, const float *obs_dev, const f
 int mhppo_policy_act(const mhppo_rollout_cfg *cfg, const float *obs_dev, const float *net_cross_dev, const float *net_wait_dev,
                      const int8_t *action_d_dev, const float *light_dev, int32_t t, uint32_t iteration, float *actions_dev,
                      float *obs_c_dev, float *act_dev, float *logp_dev, void *stream);
+/* deterministic evaluation rollout, Env_rollout.iterations (PY:152-252).
+ * choice_eval: argmax of the choice net per (car, ped) (PY:177-192) for the envs that re-decide: all when force != 0 (first
+ *   step of an episode), else those whose state has ped_traffic != nb_ped (PY:222-224); other envs keep action_d.
+ * policy_eval: per car, min over ALL pedestrian slots of {net output | speed-recovery clip((speed_limit - v)/dt, acc_lo,
+ *   acc_hi) when the pedestrian has left the lane}, capped by (10 - v)/dt (PY:195-214); writes the env's action buffer
+ *   [2C][N] (lights = the first C entries of action_d, PY:192/216) and optionally the accelerations act_dev [C][N]. */
+int mhppo_choice_eval(const mhppo_rollout_cfg *cfg, const float *obs_dev, const float *net_choice_dev, int32_t force,
+                      int8_t *action_d_dev, void *stream);
+int mhppo_policy_eval(const mhppo_rollout_cfg *cfg, const float *obs_dev, const float *net_cross_dev, const float *net_wait_dev,
+                      const int8_t *action_d_dev, float dt, float speed_limit, float acc_lo, float acc_hi, float *actions_dev,
+                      float *act_dev, void *stream);
 /* Env_rollout.futur_rewards (PY:658-684): reverse scan rtg_t = r_t + gamma*rtg_{t+1}, zero bootstrap; and the
  * episodic choice reward min(0, min_t reward_light) (PY:461).  CN = C*N */
 int mhppo_returns(const float *rew_dev, const float *rl_dev, int32_t T, int64_t CN, double gamma, float *rtg_dev,

@@ -118,6 +118,36 @@ int mhppo_policy_act(const mhppo_rollout_cfg *cfg, const float *obs, const float
     return ck(cudaGetLastError(), "k_policy_act");
 }
 
+int mhppo_choice_eval(const mhppo_rollout_cfg *cfg, const float *obs, const float *net, int32_t force, int8_t *action_d, void *stream) {
+    if (!cfg || !obs || !net || !action_d) return api_fail(MHPPO_EINVAL, "null argument");
+    const RolloutDims d = dims_of(cfg);
+    const int kp = padded_in(d.D);
+    if (kp < 0) return api_fail(MHPPO_EUNSUPPORTED, "choice features wider than 56 (nb_lines > 4)");
+    const dim3 grid((unsigned)((d.N + kFwdBlock - 1) / kFwdBlock), (unsigned)d.C);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (kp == 16) { SET_SMEM(k_choice_eval<16>, smem_fwd<16>(1)); k_choice_eval<16><<<grid, kFwdBlock, smem_fwd<16>(1), s>>>(d, obs, net, force, action_d); }
+    else if (kp == 32) { SET_SMEM(k_choice_eval<32>, smem_fwd<32>(1)); k_choice_eval<32><<<grid, kFwdBlock, smem_fwd<32>(1), s>>>(d, obs, net, force, action_d); }
+    else { SET_SMEM(k_choice_eval<56>, smem_fwd<56>(1)); k_choice_eval<56><<<grid, kFwdBlock, smem_fwd<56>(1), s>>>(d, obs, net, force, action_d); }
+    api_count_launch();
+    return ck(cudaGetLastError(), "k_choice_eval");
+}
+
+int mhppo_policy_eval(const mhppo_rollout_cfg *cfg, const float *obs, const float *net_cross, const float *net_wait,
+                      const int8_t *action_d, float dt, float speed_limit, float acc_lo, float acc_hi, float *actions, float *act,
+                      void *stream) {
+    if (!cfg || !obs || !net_cross || !net_wait || !action_d || !actions) return api_fail(MHPPO_EINVAL, "null argument");
+    if (!(dt > 0.f)) return api_fail(MHPPO_EINVAL, "dt must be > 0");
+    const RolloutDims d = dims_of(cfg);
+    if (d.P < 1 || (int64_t)d.C * d.P < d.C) return api_fail(MHPPO_EINVAL, "needs at least one pedestrian slot");
+    EvalIO io; io.obs = obs; io.action_d = action_d; io.actions = actions; io.act = act;
+    io.dt = dt; io.speed_limit = speed_limit; io.acc_lo = acc_lo; io.acc_hi = acc_hi;
+    const dim3 grid((unsigned)((d.N + kFwdBlock - 1) / kFwdBlock), (unsigned)d.C);
+    SET_SMEM(k_policy_eval, smem_fwd<16>(2));
+    k_policy_eval<<<grid, kFwdBlock, smem_fwd<16>(2), (cudaStream_t)stream>>>(d, net_cross, net_wait, io);
+    api_count_launch();
+    return ck(cudaGetLastError(), "k_policy_eval");
+}
+
 int mhppo_returns(const float *rew, const float *rl, int32_t T, int64_t CN, double gamma, float *rtg, float *rew_d, void *stream) {
     if (!rew || !rl || !rtg || !rew_d) return api_fail(MHPPO_EINVAL, "null argument");
     k_returns<<<(unsigned)((CN + 255) / 256), 256, 0, (cudaStream_t)stream>>>(rew, rl, T, CN, gamma, rtg, rew_d);

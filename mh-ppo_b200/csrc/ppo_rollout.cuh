@@ -183,6 +183,83 @@ __global__ void __launch_bounds__(kFwdBlock, 2) k_policy_act(RolloutDims d, cons
     io.act[s] = a; io.logp[s] = lp;
 }
 
+// ---- deterministic evaluation rollout (Env_rollout.iterations, PY:152-252): thread = (env, car) ---------
+// Decisions: argmax of the choice net per (car, pedestrian), taken at the first step of an episode (`force`) and again
+// whenever the state says ped_traffic != nb_ped (PY:222-224); otherwise the stored decisions stay.
+template <int KP>
+__global__ void __launch_bounds__(kFwdBlock, 2) k_choice_eval(RolloutDims d, const float *__restrict__ obs, const float *__restrict__ net,
+                                                           int force, int8_t *__restrict__ action_d) {
+    extern __shared__ __align__(16) float smem[];
+    float *sw = smem;
+    float *rows = smem + ((net_params(KP) + 3) & ~3);
+    stage_net<KP>(sw, net);
+    __syncthreads();
+    const int64_t n = (int64_t)blockIdx.x * kFwdBlock + threadIdx.x;
+    const int i = blockIdx.y;
+    if (n >= d.N) return;
+    float *x = rows + (size_t)threadIdx.x * kRowFwd;
+    const ObsView v{obs, d.N, n, 7 * d.C + 4, 7 * d.C};
+    if (!force && v.env(1) == (float)d.P) return;                                  // PY:222: state["env"][1] != nb_ped
+    for (int p = 0; p < d.P; ++p) {
+        for (int k = 0; k < KP; ++k) x[k] = 0.f;
+        feat_d(v, d.C, i, p, x);
+        const float4 o = mlp_fwd_inplace<KP>(sw, x);
+        const float m = fmaxf(o.x, o.y);                                          // softmax over the pair, PY:81-83
+        const float e0 = expf(o.x - m), e1 = expf(o.y - m);
+        const float p0 = e0 / (e0 + e1), p1 = e1 / (e0 + e1);
+        action_d[(int64_t)(i * d.P + p) * d.N + n] = (int8_t)((p1 > p0) ? 1 : -1);   // 2*argmax - 1, first index on a tie (PY:188-192)
+    }
+}
+
+// Accelerations (PY:195-214): every pedestrian slot is visited, existing or not; a pedestrian that has left the car's lane
+// (feature 7) asks for the speed-recovery acceleration clip((speed_limit - v)/dt, acc_lo, acc_hi) instead of a net output;
+// the running min is capped by (10 - v)/dt.  The lights handed to env.step are the FIRST C entries of the per-(car,
+// pedestrian) decision vector: the reference appends the whole vector and the env reads actions[C + i] (PY:192, 216).
+struct EvalIO {
+    const float *obs; const int8_t *action_d;
+    float *actions;                 // [2C][N]: acc rows then light rows
+    float *act;                     // [C][N] record of the accelerations of this step, or null
+    float dt, speed_limit, acc_lo, acc_hi;
+};
+__global__ void __launch_bounds__(kFwdBlock, 2) k_policy_eval(RolloutDims d, const float *__restrict__ net_cross,
+                                                           const float *__restrict__ net_wait, EvalIO io) {
+    constexpr int KP = 16;
+    extern __shared__ __align__(16) float smem[];
+    constexpr int NP = (net_params(KP) + 3) & ~3;
+    float *sw = smem;
+    float *rows = smem + 2 * NP;
+    stage_net<KP>(sw, net_cross);
+    stage_net<KP>(sw + NP, net_wait);
+    __syncthreads();
+    const int64_t n = (int64_t)blockIdx.x * kFwdBlock + threadIdx.x;
+    const int i = blockIdx.y;
+    if (n >= d.N) return;
+    float *row = rows + (size_t)threadIdx.x * kRowFwd;
+    const ObsView v{io.obs, d.N, n, 7 * d.C + 4, 7 * d.C};
+    float a = io.acc_hi;                                 // car_b[1,0], PY:197
+    float x[13];
+    for (int p = 0; p < d.P; ++p) {
+        feat_c(v, i, p, x);
+        float na;
+        if (x[7] != 0.f) {
+            na = fmaxf(fminf((io.speed_limit - x[0]) / io.dt, io.acc_hi), io.acc_lo);    // PY:200-201
+        } else {
+            const int sel = (io.action_d[(int64_t)(i * d.P + p) * d.N + n] <= 0) ? 0 : 1;   // cross | wait, PY:203-206
+#pragma unroll
+            for (int k = 0; k < 13; ++k) row[k] = x[k];
+            row[13] = row[14] = row[15] = 0.f;
+            const float4 o = mlp_fwd_inplace<KP>(sw + sel * NP, row);
+            na = tanhf(o.x) * 3.0f + (-1.0f);
+        }
+        a = (na < a) ? na : a;                           // PY:209
+        const float cap = (10.0f - x[0]) / io.dt;        // PY:210
+        a = (cap < a) ? cap : a;
+    }
+    io.actions[(int64_t)i * d.N + n] = a;
+    io.actions[(int64_t)(d.C + i) * d.N + n] = (float)io.action_d[(int64_t)i * d.N + n];   // flat index i, PY:192/216
+    if (io.act) io.act[(int64_t)i * d.N + n] = a;
+}
+
 // ---- futur_rewards (PY:658-684) + episodic choice reward (PY:461): thread = (car, env) ---------------
 __global__ void __launch_bounds__(256) k_returns(const float *__restrict__ rew, const float *__restrict__ rl, int T, int64_t CN,
                                                  double gamma, float *__restrict__ rtg, float *__restrict__ rew_d) {

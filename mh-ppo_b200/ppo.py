@@ -182,6 +182,13 @@ class Algo_PPO:
     # -- checkpoints: same file names and state_dict layout as the reference (PY:935-1001) ------------------------
     _PATH = "load_model/weights/pappo-scalable-coop-{name}-{num_algo:02d}-{kind}-step-{epoch:03d}0.pth"
 
+    def evaluate(self, nbr_episodes, choix=False, **kw):
+        """Testing (PY:738-747): the deterministic rollout of every env for `nbr_episodes` episodes.  Returns the dense
+        per-step records of Env_rollout.iterations; `self.rollout.reference_batches(out, n)` gives env n's
+        (state_batch, action_batch, rew_c_batch, rew_d_batch, time_stop_batch) in the reference's shapes."""
+        self.rollout.reset()
+        return self.rollout.iterations(self.actor_net_cross, self.actor_net_wait, self.actor_net_choice, nbr_episodes, choix=choix, **kw)
+
     def _nets(self):
         return [("cross", "actor", self.actor_net_cross), ("wait", "actor", self.actor_net_wait), ("choice", "actor", self.actor_net_choice),
                 ("cross", "critic", self.critic_net_cross), ("wait", "critic", self.critic_net_wait), ("choice", "critic", self.critic_net_choice)]

@@ -76,6 +76,72 @@ class Env_rollout:
         self.route.copy_(torch.where(self.exist != 0, (flat_d > 0).to(torch.int8), torch.full_like(flat_d, -1)))
         self.iteration += 1
 
+    def iterations(self, actor_net_cross, actor_net_wait, actor_net_choice, nbr_episodes, choix=False, record_obs=True,
+                   record_waiting=True):
+        """Deterministic evaluation rollout (PY:152-252): `nbr_episodes` episodes in every env, argmax decisions (re-taken
+        every step while ped_traffic != nb_ped), accelerations = min over all pedestrian slots of the cross / wait net or
+        the speed-recovery action, capped by (10 - v)/dt.  Returns a dict of CUDA tensors, episode-major:
+          obs [E,T,n_obs,N] (state before each step), acts [E,T,C,N], rews [E,T,C,N], reward_light [E,T,C,N],
+          action_d int8 [E,T,C*P,N] (+-1 decisions in force at each step), waiting [E,T,P,N] (pedestrian.waiting_time
+          after each step).  `reference_batches(out, n)` rebuilds the reference's return values for env n."""
+        if choix:
+            raise NotImplementedError("choix_test (PY:128-150) is an analysis helper outside the hot path")
+        env, L, cfg, st = self.env, self._L, self._cfg, self._stream()
+        N, Cn, P, T, dev = self.N, self.C, self.P, self.T, env.device
+        E = int(nbr_episodes)
+        f = lambda *s: torch.zeros(*s, device=dev)
+        out = dict(acts=f(E, T, Cn, N), rews=f(E, T, Cn, N), reward_light=f(E, T, Cn, N),
+                   action_d=torch.zeros(E, T, Cn * P, N, dtype=torch.int8, device=dev))
+        if record_obs:
+            out["obs"] = f(E, T, env.n_obs, N)
+        if record_waiting:
+            out["waiting"] = f(E, T, P, N)
+        was_auto = env.autoreset
+        env.autoreset = False
+        none = View(None, 0, 0)
+        lo, hi = float(env.car_b[0, 0]), float(env.car_b[1, 0])
+        for e in range(E):
+            env.reset()
+            for t in range(T):
+                check(L.mhppo_choice_eval(C.byref(cfg), env._obs.data_ptr(), actor_net_choice.flat.data_ptr(), int(t == 0),
+                                          self.action_d.data_ptr(), st))
+                if record_obs:
+                    out["obs"][e, t].copy_(env._obs)
+                out["action_d"][e, t].copy_(self.action_d)
+                check(L.mhppo_policy_eval(C.byref(cfg), env._obs.data_ptr(), actor_net_cross.flat.data_ptr(),
+                                          actor_net_wait.flat.data_ptr(), self.action_d.data_ptr(), float(self.dt),
+                                          float(env.speed_limit), lo, hi, self.actions.data_ptr(), out["acts"][e, t].data_ptr(), st))
+                check(L.mhppo_env_step(env._h, View(self.actions.data_ptr(), 1, N), View(env._obs.data_ptr(), 1, N),
+                                       View(out["rews"][e, t].data_ptr(), 1, N), View(out["reward_light"][e, t].data_ptr(), 1, N),
+                                       env._done.data_ptr(), 0, none, st))
+                if record_waiting:
+                    out["waiting"][e, t].copy_(env.ped_waiting_time.t())
+        env.autoreset = was_auto
+        return out
+
+    def reference_batches(self, out, n):
+        """The reference's return values of `iterations` (PY:238-252) for env `n`, rebuilt from the dense records:
+        (t_batch_obs, t_batch_acts, t_batch_rews_c, t_batch_rews_d, t_batch_waiting_time) as CPU tensors.  The reference
+        closes a batch after every step while ped_traffic != nb_ped (episodic reward = min(0, reward_light) of that one
+        step, PY:222-235) and once per episode otherwise (min over the episode)."""
+        E, T = out["acts"].shape[:2]
+        Cn, P = self.C, self.P
+        obs = out["obs"][:, :, :, n].reshape(E * T, -1).cpu()
+        acts = out["acts"][:, :, :, n].reshape(E * T, Cn).cpu()
+        rews_c = out["rews"][:, :, :, n].reshape(E * T, Cn).cpu()
+        rl = out["reward_light"][:, :, :, n].cpu()
+        wait = out["waiting"][:, :, :, n].cpu()
+        rews_d, wt = [], []
+        for e in range(E):
+            per_step = float(out["obs"][e, 0, 7 * Cn + 1, n]) != float(P)           # ped_traffic is fixed during an episode
+            if per_step:
+                rews_d.append(torch.minimum(rl[e], torch.zeros_like(rl[e])))
+                wt.append(wait[e].reshape(-1))
+            else:
+                rews_d.append(torch.minimum(rl[e].min(dim=0).values, torch.zeros(Cn))[None])
+                wt.append(wait[e, T - 1])
+        return obs, acts, rews_c, torch.cat(rews_d), torch.cat(wt)
+
     def futur_rewards(self):
         """Expected future rewards (PY:658-684) for every trajectory + the episodic choice reward (PY:461, 504)."""
         check(self._L.mhppo_returns(self.rew.data_ptr(), self.rl.data_ptr(), self.T, self.M, 0.99, self.rtg.data_ptr(),

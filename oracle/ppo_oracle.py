@@ -175,6 +175,77 @@ def discrete_step(obs, sd_choice, u, nb_ped, nb_lines):
     return acts, logps, feats, acts[rows, idx], logps[rows, idx], feats[rows, idx], closest
 
 
+def eval_discrete(obs, sd_choice, nb_ped, nb_lines):
+    """Deterministic decisions of Env_rollout.iterations, PY:177-190: argmax of the choice net per (car, pedestrian).
+    Returns action_all_d [N, C*P] in {0, 1} (torch.argmax: the first index on a tie)."""
+    obs = np.asarray(obs, F32)
+    C, P = 2 * nb_lines, nb_ped
+    acts = np.zeros((obs.shape[0], C * P), np.int64)
+    for i in range(C):
+        for p in range(P):
+            f, _ = obs_car_ped_d(obs, i, p, nb_ped, nb_lines)
+            with torch.no_grad():
+                pr = mlp_forward(sd_choice, f, 2)
+            acts[:, i * P + p] = torch.argmax(pr, dim=1).numpy()
+    return acts
+
+
+def eval_continuous(obs, action_d, sd_cross, sd_wait, nb_ped, nb_lines, dt=0.3, speed_limit=10.0, acc_lo=-4.0, acc_hi=2.0):
+    """Deterministic accelerations of Env_rollout.iterations, PY:195-214, fp32 like the reference's numpy scalars
+    (NumPy >= 2 promotion: float32 op python-float stays float32).  Every pedestrian slot is visited, existing or not;
+    a pedestrian that has left the car's lane (feature 7, end_cross) asks for the speed-recovery acceleration
+    clip((speed_limit - v) / dt, acc_lo, acc_hi) instead of a net output; the running min is also capped by (10 - v) / dt."""
+    obs = np.asarray(obs, F32)
+    N = obs.shape[0]
+    C, P = 2 * nb_lines, nb_ped
+    out = np.zeros((N, C), F32)
+    for i in range(C):
+        a = np.full(N, acc_hi, F32)
+        for p in range(P):
+            f, _ = obs_car_ped(obs, i, p, nb_ped, nb_lines)
+            with torch.no_grad():
+                m_cross = mlp_forward(sd_cross, f, 1).numpy()[:, 0]
+                m_wait = mlp_forward(sd_wait, f, 1).numpy()[:, 0]
+            net = np.where(action_d[:, i * P + p] <= 0, m_cross, m_wait).astype(F32)
+            rec = np.maximum(np.minimum((F32(speed_limit) - f[:, 0]) / F32(dt), F32(acc_hi)), F32(acc_lo)).astype(F32)
+            new = np.where(f[:, 7] != 0, rec, net)
+            a = np.where(new < a, new, a)                               # python min(a, new)
+            cap = ((F32(10.0) - f[:, 0]) / F32(dt)).astype(F32)
+            a = np.where(cap < a, cap, a)
+        out[:, i] = a
+    return out
+
+
+def eval_episode(env, sd_cross, sd_wait, sd_choice, nb_ped, nb_lines, T=80, dt=0.3):
+    """One deterministic evaluation episode per env of Env_rollout.iterations (PY:152-252) on a vectorised env oracle.
+    The decisions are taken at step 0 and again before every step whose state has ped_traffic != nb_ped (PY:222-224);
+    the lights handed to env.step are the FIRST C entries of the per-(car, pedestrian) decision vector (PY:192, 216:
+    `action_d_light = 2*action_all_d - 1` is appended whole and the env reads actions[C + i]).
+    Returns obs [T,N,n_obs] (state before each step), acts [T,N,C], rew [T,N,C], rl [T,N,C], action_d [T,N,C*P],
+    waiting [T,N,P] (pedestrian.waiting_time after each step), done [N]."""
+    C, P = 2 * nb_lines, nb_ped
+    obs = np.asarray(env.reset(), F32)
+    N = obs.shape[0]
+    need = np.ones(N, bool)
+    acts_d = np.zeros((N, C * P), np.int64)
+    out = dict(obs=[], acts=[], rew=[], rl=[], action_d=[], waiting=[])
+    done = None
+    for t in range(T):
+        new_d = eval_discrete(obs, sd_choice, nb_ped, nb_lines)
+        acts_d = np.where(need[:, None], new_d, acts_d)
+        action_d = (2 * acts_d - 1).astype(np.float64)
+        a = eval_continuous(obs, action_d, sd_cross, sd_wait, nb_ped, nb_lines, dt=dt)
+        out["obs"].append(obs.copy()); out["acts"].append(a.copy()); out["action_d"].append(action_d.copy())
+        obs, rew, rl, done = env.step(np.concatenate([a.astype(np.float64), action_d[:, :C]], axis=1), autoreset=False)
+        obs = np.asarray(obs, F32)
+        out["rew"].append(np.asarray(rew).copy()); out["rl"].append(np.asarray(rl).copy())
+        out["waiting"].append(env.get_state()["ped_i"][:, :, 1].astype(np.float64) * dt)   # waiting_time is a multiple of dt
+        need = obs[:, 7 * C + 1] != F32(P)
+    res = {k: np.stack(v) for k, v in out.items()}
+    res["done"] = np.asarray(done)
+    return res
+
+
 def reward_to_go(rews, gamma=0.99):
     """futur_rewards, PY:658-684: rews [T, ...] -> discounted reward-to-go with zero bootstrap (fp64 like the reference)."""
     rews = np.asarray(rews, np.float64)

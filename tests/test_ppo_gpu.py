@@ -107,6 +107,55 @@ def test_rollout_matches_oracle_batch(mh, oracle_mod):
     np.testing.assert_allclose(r.rtg.view(T, C, N).cpu().numpy(), PO.reward_to_go(b["rew"]), rtol=1e-4 if mh.mlp_mode != "tc" else 2e-3, atol=5e-3 if mh.mlp_mode != "tc" else 5e-2)
 
 
+def test_eval_rollout_matches_reference_golden(mh):
+    """Deterministic evaluation rollout (Algo_PPO.evaluate -> Env_rollout.iterations, PY:152-252, 738-747) on the GPU vs
+    whole episodes recorded from the reference, incl. the reference-shaped return values."""
+    z = np.load(os.path.join(GOLDEN_DIR, "ppo_eval_432.npz"))
+    tol = dict(rtol=1e-4, atol=1e-4) if mh.mlp_mode != "tc" else dict(rtol=2e-3, atol=5e-3)
+    for e, (seed, env_id) in enumerate(z["streams"]):
+        algo, env = _algo(mh, 1, int(seed), int(env_id), z)
+        # (Algo_PPO.evaluate resets once more before the rollout's own reset, PY:744 + 168, like the reference; the golden
+        # episodes were recorded from `iterations` on a fresh stream)
+        out = algo.rollout.iterations(algo.actor_net_cross, algo.actor_net_wait, algo.actor_net_choice, 1)
+        want = {k.split(".", 1)[1]: z[k] for k in z.files if k.startswith("ep%d." % e)}
+        np.testing.assert_array_equal(out["action_d"][0, :, :, 0].cpu().numpy(), want["actions"][:, 4:])
+        np.testing.assert_allclose(out["obs"][0, :, :, 0].cpu().numpy(), want["obs"], **tol)
+        np.testing.assert_allclose(out["acts"][0, :, :, 0].cpu().numpy(), want["acts"], **tol)
+        np.testing.assert_allclose(out["rews"][0, :, :, 0].cpu().numpy(), want["rew"], **tol)
+        np.testing.assert_allclose(out["reward_light"][0, :, :, 0].cpu().numpy(), want["rl"], **tol)
+        np.testing.assert_allclose(out["waiting"][0, :, :, 0].cpu().numpy(), want["waiting"], rtol=1e-6, atol=1e-6)
+        obs, acts, rews_c, rews_d, wt = algo.rollout.reference_batches(out, 0)
+        assert rews_d.shape == want["rews_d"].shape and wt.shape == want["waiting_batch"].shape
+        np.testing.assert_allclose(rews_c.numpy(), want["rews_c"], **tol)
+        np.testing.assert_allclose(rews_d.numpy(), want["rews_d"], **tol)
+        np.testing.assert_allclose(wt.numpy(), want["waiting_batch"], rtol=1e-6, atol=1e-6)
+
+
+def test_eval_rollout_matches_oracle_batch(mh, oracle_mod):
+    """512 envs, one evaluation episode: decisions bit-exact, values within the free-running tolerance."""
+    from oracle import ppo_oracle as PO
+    N, seed, id0 = 512, 77, 9000
+    algo, env = _algo(mh, N, seed, id0)
+    sds = [{k: v.clone() for k, v in n.state_dict().items()} for n in (algo.actor_net_cross, algo.actor_net_wait, algo.actor_net_choice)]
+    out = algo.rollout.iterations(algo.actor_net_cross, algo.actor_net_wait, algo.actor_net_choice, 1)
+    venv = oracle_mod.OracleVecEnv("coop_scalable", N, 4, 3, 2, seed=seed, env_id0=id0, store_f32=True)
+    b = PO.eval_episode(venv, *sds, 3, 2)
+    g = lambda k: out[k][0].permute(0, 2, 1).cpu().numpy()       # [T, N, width]
+    # an argmax between two nearly equal probabilities is rounding noise in the reference too: tolerate rare flips, and
+    # compare the values only for envs whose decisions agree over the whole episode
+    same = (g("action_d") == b["action_d"]).all(axis=(0, 2))
+    assert same.mean() > 0.99, same.mean()
+    tol = dict(rtol=1e-4, atol=5e-4) if mh.mlp_mode != "tc" else dict(rtol=2e-3, atol=5e-3)
+    np.testing.assert_allclose(g("acts")[:, same], b["acts"][:, same], **tol)
+    np.testing.assert_allclose(g("rews")[:, same], b["rew"][:, same], **tol)
+    np.testing.assert_allclose(g("reward_light")[:, same], b["rl"][:, same], **tol)
+    np.testing.assert_allclose(g("waiting")[:, same], b["waiting"][:, same], rtol=1e-6, atol=1e-6)   # count * dt in fp32
+    assert not (g("action_d")[0] == 0).any()                       # every (car, pedestrian) pair decided at step 0
+    out2 = algo.evaluate(2, record_obs=False)                      # Algo_PPO.evaluate, PY:738-747: two more episodes
+    assert out2["acts"].shape == (2, 80, 4, N) and "obs" not in out2
+    assert torch.isfinite(out2["rews"]).all()
+
+
 def test_returns_kernel(mh):
     import ctypes as C
     from oracle import ppo_oracle as PO

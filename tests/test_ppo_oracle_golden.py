@@ -35,6 +35,23 @@ def test_rollout_oracle_reproduces_reference_episodes(oracle_mod):
         np.testing.assert_allclose(np.array([b["rew_d"][i, 0] for i in cars]), want["rews_choice"], rtol=1e-6, atol=1e-9)
 
 
+def test_eval_rollout_oracle_reproduces_reference_episodes(oracle_mod):
+    from oracle import ppo_oracle as PO
+    z = np.load(os.path.join(GOLDEN_DIR, "ppo_eval_432.npz"))
+    sds = [_sd(z, n) for n in ("cross", "wait", "choice")]
+    for e, (seed, env_id) in enumerate(z["streams"]):
+        seed, env_id = int(seed), int(env_id)
+        venv = oracle_mod.OracleVecEnv("coop_scalable", 1, 4, 3, 2, seed=seed, env_id0=env_id, store_f32=False, n_threads=1)
+        b = PO.eval_episode(venv, *sds, 3, 2)
+        want = {k.split(".", 1)[1]: z[k] for k in z.files if k.startswith("ep%d." % e)}
+        np.testing.assert_allclose(b["obs"][:, 0], want["obs"], rtol=2e-5, atol=2e-5)
+        np.testing.assert_allclose(b["acts"][:, 0], want["acts"], rtol=2e-5, atol=2e-5)
+        np.testing.assert_array_equal(b["action_d"][:, 0], want["actions"][:, 4:])
+        np.testing.assert_allclose(b["rew"][:, 0], want["rew"], rtol=2e-5, atol=2e-5)
+        np.testing.assert_allclose(b["rl"][:, 0], want["rl"], rtol=2e-5, atol=2e-5)
+        np.testing.assert_allclose(b["waiting"][:, 0], want["waiting"], rtol=0, atol=1e-9)
+
+
 def test_train_step_oracle_reproduces_reference():
     from oracle import ppo_oracle as PO
     for kind, n_in, n_out, mt in (("c", 13, 1, 1), ("d", 30, 2, 2)):

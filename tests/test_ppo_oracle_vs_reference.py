@@ -129,3 +129,26 @@ def test_rollout_episode_matches_reference(ref):
         np.testing.assert_array_equal(np.array([b["act_d"][i, 0] for i in cars]), want["acts_choice"])
         np.testing.assert_allclose(np.array([b["logp_d"][i, 0] for i in cars]), want["logp_choice"], rtol=1e-5, atol=1e-6)
         np.testing.assert_allclose(np.array([b["rew_d"][i, 0] for i in cars]), want["rews_choice"], rtol=1e-6, atol=1e-9)
+
+
+def test_eval_rollout_matches_reference(ref):
+    """Deterministic evaluation rollout: reference Env_rollout.iterations (env.step wrapped to record what it receives and
+    returns) vs PO.eval_episode, both decision regimes (ped_traffic == nb_ped: decided once; < nb_ped: every step)."""
+    import ref_rollout
+    from oracle import oracle as O
+    from oracle import ppo_oracle as PO
+    ns, algo, env = ref
+    sds = [_sd(n) for n in (algo.actor_net_cross, algo.actor_net_wait, algo.actor_net_choice)]
+    regimes = set()
+    for seed, env_id in [(777, 5), (778, 9), (901, 123), (7, 3), (8, 4)]:
+        want = ref_rollout.reference_eval_episode(ns, algo, env, seed, env_id)
+        venv = O.OracleVecEnv("coop_scalable", 1, 4, 3, 2, seed=seed, env_id0=env_id, store_f32=False, n_threads=1)
+        b = PO.eval_episode(venv, *sds, 3, 2)
+        regimes.add(want["rews_d"].shape[0])
+        np.testing.assert_allclose(b["obs"][:, 0], want["obs"], rtol=2e-5, atol=2e-5)
+        np.testing.assert_allclose(b["acts"][:, 0], want["acts"], rtol=2e-5, atol=2e-5)
+        np.testing.assert_array_equal(b["action_d"][:, 0], want["actions"][:, 4:])       # the whole decision vector is appended (PY:216)
+        np.testing.assert_allclose(b["rew"][:, 0], want["rew"], rtol=2e-5, atol=2e-5)
+        np.testing.assert_allclose(b["rl"][:, 0], want["rl"], rtol=2e-5, atol=2e-5)
+        np.testing.assert_allclose(b["waiting"][:, 0], want["waiting"], rtol=0, atol=1e-9)
+    assert regimes == {1, 80}

@@ -2,6 +2,8 @@
 
   ppo_rollout_432.npz : whole-episode rollout buffers of Env_rollout.iterations_rand (sampling noise injected through
                         the policy-noise contract, tools/ref_rollout.py) for a few (seed, env_id) streams + the nets used
+  ppo_eval_432.npz    : whole episodes of the deterministic evaluation rollout Env_rollout.iterations (env.step wrapped to
+                        record actions / rewards / reward_light / waiting times) + the nets used
   ppo_train_{c,d}.npz : Algo_PPO.train_model_c / train_model_d on a synthetic batch: nets before, nets after 1..4 epochs
 Re-run:  python tools/gen_golden_ppo.py
 """
@@ -36,6 +38,16 @@ def main():
         for k, v in w.items():
             out["ep%d.%s" % (e, k)] = v
     np.savez_compressed(os.path.join(OUT, "ppo_rollout_432.npz"), **out)
+
+    # deterministic evaluation rollout (Env_rollout.iterations): both regimes (ped_traffic == nb_ped and < nb_ped)
+    ev = {k: v for k, v in out.items() if k.split(".")[0] in ("cross", "wait", "choice")}
+    streams = [(777, 5), (901, 123), (7, 3), (8, 4)]
+    ev["streams"] = np.array(streams, np.int64)
+    for e, (seed, env_id) in enumerate(streams):
+        w = ref_rollout.reference_eval_episode(ns, algo, env, seed, env_id)
+        for k, v in w.items():
+            ev["ep%d.%s" % (e, k)] = v
+    np.savez_compressed(os.path.join(OUT, "ppo_eval_432.npz"), **ev)
 
     for kind in ("c", "d"):
         g = torch.Generator().manual_seed(11)

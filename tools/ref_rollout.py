@@ -97,3 +97,30 @@ def reference_episode(ns, algo, env, seed, env_id, iteration=0):
         return out
     finally:
         ns["MultivariateNormal"], ns["Categorical"] = real
+
+
+def reference_eval_episode(ns, algo, env, seed, env_id):
+    """One episode of the reference's deterministic evaluation rollout (Env_rollout.iterations, PY:152-252) on stream
+    (seed, env_id).  `iterations` keeps nothing per step but its return values, so env.step is wrapped to record the
+    actions it receives, the rewards, reward_light and the pedestrians' waiting times."""
+    r = algo.rollout
+    env._mh_rng.set_stream(seed, env_id, 0)
+    rec = dict(actions=[], rew=[], rl=[], waiting=[])
+    real_step = env.step
+
+    def step(a):
+        out = real_step(a)
+        rec["actions"].append(np.array(a, np.float64)); rec["rew"].append(np.array(out[1], np.float64))
+        rec["rl"].append(np.array(env.reward_light, np.float64))
+        rec["waiting"].append(np.array([p.waiting_time for p in env.pedestrian], np.float64))
+        return out
+
+    env.step = step
+    try:
+        obs, acts, rews_c, rews_d, wt = r.iterations(algo.actor_net_cross, algo.actor_net_wait, algo.actor_net_choice, 1)
+    finally:
+        del env.step
+    out = {k: np.stack(v) for k, v in rec.items()}
+    out.update(obs=obs.numpy(), acts=acts.numpy(), rews_c=rews_c.numpy().reshape(len(rec["rew"]), -1), rews_d=rews_d.numpy(),
+               waiting_batch=wt.numpy())
+    return out
