@@ -160,8 +160,11 @@ class Algo_PPO:
         for _ in range(epochs):
             self.train_model_d(self.actor_net_choice, self.critic_net_choice, self.optimizer_actor_choice, self.optimizer_critic_choice)
 
-    def train(self, nb_loop, verbose=False):
-        """Training loop (PY:854-917)."""
+    _TRACE = "load_model/parameters/pappo-scalable-coop-{num_algo:02d}-{name}-step-{epoch:03d}000.npy"
+
+    def train(self, nb_loop, verbose=False, root=".", save_traces=True):
+        """Training loop (PY:854-917); ends by writing the four learning-curve traces with the reference's file names
+        (PY:908-916) under `root`, so a run can be laid next to the reference's load_model/parameters/*.npy."""
         for ep in range(nb_loop):
             self.rollout.iterations_rand(self.actor_net_cross, self.actor_net_wait, self.actor_net_choice)
             self.update()
@@ -178,6 +181,14 @@ class Algo_PPO:
                 print("Episode * {} * cross {:.4f} wait {:.4f} choice {:.4f}  (#cross {} #wait {})".format(
                     ep, np.mean(self.ep_reward_cross[-10:] or [0]), np.mean(self.ep_reward_wait[-10:] or [0]),
                     np.mean(self.ep_reward_choice[-10:]), nc, nw))
+        d = _dist()
+        if save_traces and (d is None or d.get_rank() == 0):
+            for name, arr in (("reward_cross", np.array(self.ep_reward_cross)), ("reward_wait", np.array(self.ep_reward_wait)),
+                              ("reward_choice", np.array(self.ep_reward_choice)),
+                              ("scenario_balance", np.array(self.ep_scenario_balance).reshape((-1, 2)))):
+                path = os.path.join(root, self._TRACE.format(num_algo=self.num_algo, epoch=int(self.total_loop / 1000), name=name))
+                os.makedirs(os.path.dirname(path), exist_ok=True)
+                np.save(path, arr)
 
     # -- checkpoints: same file names and state_dict layout as the reference (PY:935-1001) ------------------------
     _PATH = "load_model/weights/pappo-scalable-coop-{name}-{num_algo:02d}-{kind}-step-{epoch:03d}0.pth"

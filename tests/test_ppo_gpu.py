@@ -244,3 +244,20 @@ def test_gradients_match_autograd(mh):
         got = net.grad.cpu().numpy()
         scale = np.abs(want).max()
         np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-5 * scale)
+
+
+def test_train_loop_writes_reference_named_traces_and_checkpoints(mh, tmp_path):
+    """Algo_PPO.train / saving / loading (PY:854-917, 935-1001): learning-curve traces and checkpoints use the reference's
+    file names and layouts, and a saved run reloads into identical nets."""
+    algo, env = _algo(mh, 256, 3, 100)
+    algo.train(2, root=str(tmp_path))
+    par = tmp_path / "load_model" / "parameters"
+    for name, shape in (("reward_choice", (2,)), ("scenario_balance", (2, 2))):
+        a = np.load(par / ("pappo-scalable-coop-%02d-%s-step-000000.npy" % (algo.num_algo, name)))
+        assert a.shape == shape and np.isfinite(a).all()
+    assert (par / ("pappo-scalable-coop-%02d-reward_cross-step-000000.npy" % algo.num_algo)).exists()
+    algo.saving(root=str(tmp_path))
+    algo2, _ = _algo(mh, 256, 3, 100)
+    algo2.loading(algo.num_algo, algo.total_loop, root=str(tmp_path))
+    for (_, _, a), (_, _, b) in zip(algo._nets(), algo2._nets()):
+        assert torch.equal(a.flat, b.flat)
