@@ -16,8 +16,9 @@
 //    over all pedestrians (SC:808-809, 841-846, 849-858, 869); the passes only communicate through
 //    per-car running min/max and per-pedestrian fields, so interleaving them per pedestrian is
 //    exactly equivalent (DESIGN.md "Step kernel");
-//  * bulky rare paths are single out-of-line copies: the sin walking profile (fp64 sincos), the
-//    episode reset, and the exact fp64 critical gap.  The gap-acceptance decision
+//  * the coldest paths are single out-of-line copies: the episode reset, the Philox block function and
+//    the exact fp64 critical gap (the sin walking profile and the gap judgement are inlined: with rolled
+//    loops they have one or two call sites and the call's register shuffling cost more than it saved).  The gap-acceptance decision
 //    `choix_pedestrian` runs every step for a waiting pedestrian, so its log10/pow/normal-draw
 //    comparison is a filtered predicate (fp32 with an error bound, fp64 only when undecidable).
 //    (Tried and dropped: queueing the judgements of a warp in shared memory and evaluating them one
@@ -57,8 +58,9 @@ static MH_NOINLINE double cg_exact(double v0y, int gender, int age, double size,
 // `car_time + light < CG` of SC:167-170, bit-exact at fp32 cost: the comparison is first evaluated
 // in fp32 with a conservative error bound (filtered predicate); only an undecidable case recomputes
 // both sides in fp64 exactly as the reference does.  `ctr` is the Philox block of this decision's
-// normal draw (one block per CG_score call).  Out of line: one copy, two callers.
-static MH_NOINLINE bool gap_eval(double dx, double vden, double light, double size, double v0y, int gender, int age,
+// normal draw (one block per CG_score call).  Inlined at its two call sites (3 % faster than one out-of-line copy:
+// a 12-argument call costs more register moves than the body's second copy costs in instruction cache).
+MH_HD bool gap_eval(double dx, double vden, double light, double size, double v0y, int gender, int age,
                                  uint32_t ctr, uint32_t env_lo, uint32_t env_hi, uint32_t k0, uint32_t k1) {
     const PhiloxBlock b = philox4x32_10(ctr, 0u, env_lo, env_hi, k0, k1);
     const double u1 = u53(b.w0, b.w1), u2 = u53(b.w2, b.w3);
@@ -177,7 +179,7 @@ MH_HD bool choix_fast(const EnvConst &c, const Geo &g, const PedR &p, const CarS
 
 struct WalkOut { double pos, spd; };
 // pedestrian.new_pedestrian_sin_y, SC:436-443 with the parameters of SC:94-102
-static MH_NOINLINE WalkOut walk_sin(double W, double v0y, double Spy, double dt, int step, int t0c, int dir) {
+MH_HD WalkOut walk_sin(double W, double v0y, double Spy, double dt, int step, int t0c, int dir) {
     const double PI_ = 3.141592653589793, Vm = 2.5;
     const double av = fabs(v0y);
     const double T = W / (av + 10e-3);

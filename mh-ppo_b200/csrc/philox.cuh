@@ -23,7 +23,9 @@
 #endif
 
 // one out-of-line copy on the device: ~80 integer instructions per block, called from many places
-#ifdef __CUDACC__
+#if defined(__CUDACC__) && defined(MH_INLINE_PHILOX)
+#define MH_PHILOX static __host__ __device__ __forceinline__
+#elif defined(__CUDACC__)
 #define MH_PHILOX static __host__ __device__ __noinline__
 #else
 #define MH_PHILOX static inline
