@@ -1,4 +1,4 @@
-// env_core.cuh -- one crosswalk env advanced by one thread, state held in registers.
+// env_core.cuh -- one crosswalk env advanced by one thread.
 //
 // This is the device-side semantics of `Crosswalk_hybrid_multi_{stop,naif,coop,coop_4cars,
 // coop_4cars2,coop_scalable}.step/reset` (reference: Environments/Env_hybrid_multi_*.py; citation
@@ -6,9 +6,9 @@
 // classes; the behavioural deltas between the files are compile-time switches (`VT<V>`).
 //
 // Design (B200-first, not a translation of the Python object graph):
-//  * thread = env, lane = env inside a warp; car slots are unrolled register arrays, so the
-//    reference's filtered Python lists become bit masks over slots (order preserved); the step
-//    itself (env_step.cuh) streams the pedestrians through one rolled loop;
+//  * thread = env, lane = env inside a warp; the reference's filtered Python lists become bit masks
+//    over car slots (order preserved); the step itself (env_step.cuh) keeps the cars of a CTA in
+//    shared memory and streams the pedestrians through one rolled loop;
 //  * persisted state is fp32 / packed integers in HBM (env_state.cuh), arithmetic is fp64 in the
 //    reference's operation order (compile with -fmad=false) so threshold flags are bit-exact and
 //    values differ from the fp64 reference only by the final fp32 rounding;

@@ -4,8 +4,8 @@
 // Replaces Crosswalk_hybrid_multi_*.step / .reset of the reference (SC:789-946 and siblings) for
 // n_envs environments at once.  Grid: one thread per env, 128-thread CTAs; a warp touches 32
 // consecutive envs so every state group is one coalesced 512 B float4 access (env_state.cuh).
-// Bound: HBM (state is read and written once per step) as long as the fp64 issue rate keeps up;
-// DESIGN.md "Kernels" has the byte accounting and the measured roofline fraction.
+// Roofline: HBM (state is read and written once per step); the measured limiter is instruction issue
+// (DESIGN.md "Kernels" has the byte accounting, the measured roofline fraction and the stall breakdown).
 #pragma once
 #include <cuda_runtime.h>
 
