@@ -195,10 +195,32 @@ def run_reference(args, wl):
             "note": "the reference is single-process Python (one env, global RNG, GIL) and is not shippable to the GPU box; "
                     "this arm is its pinned C restatement on all host threads, far faster than the Python original "
                     "(3.4k env-steps/s/core, BASELINE.md section 2)"}
-    print(json.dumps(line))
+    emit(line)
+
+
+_JSON_FD = None
+
+
+def claim_stdout():
+    """Libraries (NCCL's version banner, torchrun) write to file descriptor 1; the contract is ONE JSON line on stdout.
+    Everything else is sent to stderr and the line is written to the original descriptor at the end."""
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_JSON_FD, data)
 
 
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=160)
@@ -343,7 +365,7 @@ def main():
             line["cpu_baseline"] = {"value": rate * act_cpu, "unit": "agent-steps/s", "cores": cores, "kind": "port",
                                     "sample": "%d envs x %d steps of the same workload, C oracle port on all host threads (%.1f s)" % (ns, ks, dt),
                                     "env_steps_per_s": rate}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
