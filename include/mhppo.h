@@ -185,6 +185,13 @@ int mhppo_ppo_grad(int32_t n_in, int32_t head, const float *x_dev, int32_t D, in
                    int64_t CN, const float *net_dev, const float *act_dev, const float *logp_old_dev, const float *rtg_dev,
                    const float *V_dev, float adv_mean, float adv_inv_std, float inv_n, float f0, float f1, float *grad_dev,
                    double *loss_dev, void *workspace_dev, void *stream);
+/* critic pass of one epoch in a single kernel: ppo_grad with head 0 that also returns V = critic(s) (PY:785) and the
+ * advantage statistics (sum A, sum A^2, n) of A = rtg - V, so an epoch is critic_grad_stats -> [all-reduce stats] ->
+ * ppo_grad (actor) -> [all-reduce grads] -> adam, adam; V and the statistics are those of the critic before its step,
+ * as in the reference (the actor and critic steps of PY:810-815 act on different networks).  inv_n = 1 / global count */
+int mhppo_critic_grad_stats(int32_t n_in, const float *x_dev, int32_t D, int64_t S, const int32_t *idx_dev, int64_t K, int64_t CN,
+                            const float *critic_dev, const float *rtg_dev, float inv_n, float *grad_dev, double *loss_dev,
+                            float *V_dev, double *stats3_dev, void *workspace_dev, void *stream);
 /* torch.optim.Adam defaults (PY:719-724); step counts from 1; grad_scale multiplies the gradient first */
 int mhppo_adam(float *param_dev, const float *grad_dev, float *m_dev, float *v_dev, int32_t n, float lr, float beta1,
                float beta2, float eps, int32_t step, float grad_scale, void *stream);

@@ -62,6 +62,8 @@ SYMBOLS = {
     "mhppo_returns": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mhppo_update_workspace_bytes": (C.c_int64, [C.c_int32]),
     "mhppo_value_stats": (C.c_int, [C.c_int32, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_int64, C.c_int64] + [C.c_void_p] * 6),
+    "mhppo_critic_grad_stats": (C.c_int, [C.c_int32, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
+                                          C.c_float] + [C.c_void_p] * 6),
     "mhppo_ppo_grad": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_int64, C.c_int64]
                        + [C.c_void_p] * 5 + [C.c_float] * 5 + [C.c_void_p] * 4),
     "mhppo_tc_failures": (C.c_int, []),

@@ -201,9 +201,10 @@ int mhppo_value_stats(int32_t n_in, const float *x, int32_t D, int64_t S, const 
     return ck(cudaGetLastError(), "k_reduce_scalars");
 }
 
-int mhppo_ppo_grad(int32_t n_in, int32_t head, const float *x, int32_t D, int64_t S, const int32_t *idx, int64_t K, int64_t CN,
-                   const float *net, const float *act, const float *logp_old, const float *rtg, const float *V, float adv_mean,
-                   float adv_inv_std, float inv_n, float f0, float f1, float *grad, double *loss, void *workspace, void *stream) {
+static int ppo_grad_impl(int32_t n_in, int32_t head, const float *x, int32_t D, int64_t S, const int32_t *idx, int64_t K, int64_t CN,
+                         const float *net, const float *act, const float *logp_old, const float *rtg, const float *V, float adv_mean,
+                         float adv_inv_std, float inv_n, float f0, float f1, float *grad, double *loss, float *V_out, double *stats3,
+                         void *workspace, void *stream) {
     if (!x || !net || !rtg || !grad || !loss || !workspace) return api_fail(MHPPO_EINVAL, "null argument");
     if (head < 0 || head > 2) return api_fail(MHPPO_EINVAL, "head must be 0, 1 or 2");
     if (head != 0 && (!act || !logp_old || !V)) return api_fail(MHPPO_EINVAL, "actor heads need act, logp_old and V");
@@ -211,9 +212,9 @@ int mhppo_ppo_grad(int32_t n_in, int32_t head, const float *x, int32_t D, int64_
     if (kp < 0 || D > kp) return api_fail(MHPPO_EUNSUPPORTED, "unsupported input width");
     SampleSet ss;
     { const int rc0 = make_set(ss, x, D, S, idx, K, CN); if (rc0) return rc0; }
-    LossArgs la; la.act = act; la.logp_old = logp_old; la.rtg = rtg; la.V = V; la.adv_mean = adv_mean; la.adv_inv_std = adv_inv_std;
-    la.inv_n = inv_n; la.f0 = f0; la.f1 = f1;
     const Workspace w = carve(workspace, kp);
+    LossArgs la; la.act = act; la.logp_old = logp_old; la.rtg = rtg; la.V = V; la.adv_mean = adv_mean; la.adv_inv_std = adv_inv_std;
+    la.inv_n = inv_n; la.f0 = f0; la.f1 = f1; la.V_out = V_out; la.spartial = stats3 ? w.spartial : nullptr;
     cudaStream_t s = (cudaStream_t)stream;
     int rc = (kp == 16) ? launch_grad<16>(head, ss, net, la, w, s) : ((kp == 32) ? launch_grad<32>(head, ss, net, la, w, s) : launch_grad<56>(head, ss, net, la, w, s));
     if (rc) return rc;
@@ -221,7 +222,23 @@ int mhppo_ppo_grad(int32_t n_in, int32_t head, const float *x, int32_t D, int64_
     k_reduce_partials<<<(npar + 255) / 256, 256, 0, s>>>(w.gpartial, kGradGrid, npar, grad);
     k_reduce_scalars<<<1, 32, 0, s>>>(w.lpartial, kGradGrid, 1, loss);
     api_count_launch(); api_count_launch();
+    if (stats3) { k_reduce_scalars<<<1, 32, 0, s>>>(w.spartial, kGradGrid, 3, stats3); api_count_launch(); }
     return ck(cudaGetLastError(), "k_reduce_partials");
+}
+
+int mhppo_ppo_grad(int32_t n_in, int32_t head, const float *x, int32_t D, int64_t S, const int32_t *idx, int64_t K, int64_t CN,
+                   const float *net, const float *act, const float *logp_old, const float *rtg, const float *V, float adv_mean,
+                   float adv_inv_std, float inv_n, float f0, float f1, float *grad, double *loss, void *workspace, void *stream) {
+    return ppo_grad_impl(n_in, head, x, D, S, idx, K, CN, net, act, logp_old, rtg, V, adv_mean, adv_inv_std, inv_n, f0, f1, grad, loss,
+                         nullptr, nullptr, workspace, stream);
+}
+
+int mhppo_critic_grad_stats(int32_t n_in, const float *x, int32_t D, int64_t S, const int32_t *idx, int64_t K, int64_t CN,
+                            const float *critic, const float *rtg, float inv_n, float *grad, double *loss, float *V, double *stats3,
+                            void *workspace, void *stream) {
+    if (!V || !stats3) return api_fail(MHPPO_EINVAL, "null argument");
+    return ppo_grad_impl(n_in, 0, x, D, S, idx, K, CN, critic, nullptr, nullptr, rtg, nullptr, 0.f, 0.f, inv_n, 0.f, 0.f, grad, loss, V,
+                         stats3, workspace, stream);
 }
 
 int mhppo_adam(float *p, const float *g, float *m, float *v, int32_t n, float lr, float beta1, float beta2, float eps, int32_t step,

@@ -89,6 +89,8 @@ struct LossArgs {
     float adv_mean, adv_inv_std;               // (A - mean) * inv_std, inv_std = 1 / (std_unbiased + 1e-10)  (PY:787)
     float inv_n;                               // 1 / (global sample count)
     float f0, f1;                              // choice only: fraction of samples whose action is 0 / 1 (PY:834-842 broadcast)
+    float *V_out;                              // critic only, optional: V[s] of this forward pass and the advantage statistics
+    double *spartial;                          //   [grid][3] partial (sum A, sum A^2, n) with A = rtg - V (replaces k_value_stats)
 };
 
 // ---- register-tiled dense layers for the fused kernel -------------------------------------------------
@@ -259,7 +261,7 @@ __global__ void __launch_bounds__(kMlpBlock, 1) k_ppo_grad(SampleSet ss, const f
     const int k4 = lt & 31, j4 = (lt >> 5) * 2;                         // dW4t[k < 32][j < 4]
     constexpr int HALF = G::TILE / 2;
     const int s0 = half * HALF;
-    double loss = 0.0;
+    double loss = 0.0, sA = 0.0, sAA = 0.0, cnt = 0.0;
 
     for (int64_t base = (int64_t)blockIdx.x * G::TILE; base < ss.Q; base += (int64_t)gridDim.x * G::TILE) {
         bool sel[R];
@@ -294,6 +296,11 @@ __global__ void __launch_bounds__(kMlpBlock, 1) k_ppo_grad(SampleSet ss, const f
                     const float e = o.x - la.rtg[s];
                     loss += (double)e * (double)e * (double)la.inv_n;
                     dz[0] = 2.0f * e * la.inv_n;
+                    if (la.V_out) {                                        // V = critic(s), A = rtgs - V (PY:785-786)
+                        la.V_out[s] = o.x;
+                        const double A = (double)(la.rtg[s] - o.x);
+                        sA += A; sAA += A * A; cnt += 1.0;
+                    }
                 } else {
                     const float An = ((la.rtg[s] - la.V[s]) - la.adv_mean) * la.adv_inv_std;     // PY:786-787
                     if (HEAD == 1) {
@@ -390,6 +397,10 @@ __global__ void __launch_bounds__(kMlpBlock, 1) k_ppo_grad(SampleSet ss, const f
     for (int i = tid; i < NPAR; i += kMlpBlock) gp[i] = scratch[i];
     const double lt_sum = team_sum(loss, red, tid, kMlpBlock, 0);
     if (tid == 0) lpartial[blockIdx.x] = lt_sum;
+    if (HEAD == 0 && la.spartial) {
+        const double t0 = team_sum(sA, red, tid, kMlpBlock, 0), t1 = team_sum(sAA, red, tid, kMlpBlock, 0), t2 = team_sum(cnt, red, tid, kMlpBlock, 0);
+        if (tid == 0) { la.spartial[blockIdx.x * 3 + 0] = t0; la.spartial[blockIdx.x * 3 + 1] = t1; la.spartial[blockIdx.x * 3 + 2] = t2; }
+    }
 }
 
 // ---- 4. deterministic reduction of the per-CTA partials ----------------------------------------------

@@ -108,21 +108,31 @@ class Algo_PPO:
             self._sel_cache[want] = (sel if sel.numel() else torch.zeros(1, dtype=torch.int32, device=mask.device), sel.numel())
         return self._sel_cache[want]
 
+    def _global_count(self, want, local):
+        """Samples of this buffer over all ranks (the denominators of the losses, PY:806-809); the selection is fixed for
+        the 10 epochs of an update, so the all-reduce happens once per buffer."""
+        k = ("n", want)
+        if k not in self._sel_cache:
+            t = torch.tensor([float(local)], dtype=torch.float64, device=self.rollout.route.device)
+            self._sel_cache[k] = int(allreduce_sum_(t).item())
+        return self._sel_cache[k]
+
     def train_model_c(self, actor, critic, opti_actor, opti_critic, want):
         r, L, st = self.rollout, _lib.lib(), self._stream()
         ws = self._ws.data_ptr()
         idx, K = self._selection(want)                                      # K == 0 still runs (zero partials): other ranks may have samples
-        check(L.mhppo_value_stats(13, r.obs_c.data_ptr(), 13, r.S, idx.data_ptr(), K, r.M, critic.flat.data_ptr(),
-                                  r.rtg.data_ptr(), r.V.data_ptr(), self._stats.data_ptr(), ws, st))
-        mean, inv_std, n = combine_stats(allreduce_sum_(self._stats).cpu())
+        n = self._global_count(want, K * (r.S // r.M))             # sample slots: S = T * M, M = C * N columns
         if n < 1:
             return False                                     # PY:869/874: the net is skipped when its buffer is empty
+        # critic pass first: its forward is V = critic(s) of PY:785, so the same kernel returns V and the advantage statistics
+        check(L.mhppo_critic_grad_stats(13, r.obs_c.data_ptr(), 13, r.S, idx.data_ptr(), K, r.M, critic.flat.data_ptr(),
+                                        r.rtg.data_ptr(), 1.0 / n, critic.grad.data_ptr(), self._loss.data_ptr() + 8,
+                                        r.V.data_ptr(), self._stats.data_ptr(), ws, st))
+        mean, inv_std, n2 = combine_stats(allreduce_sum_(self._stats).cpu())
+        assert n2 == n, (n2, n)
         check(L.mhppo_ppo_grad(13, 1, r.obs_c.data_ptr(), 13, r.S, idx.data_ptr(), K, r.M, actor.flat.data_ptr(),
                                r.act.data_ptr(), r.logp.data_ptr(), r.rtg.data_ptr(), r.V.data_ptr(), mean, inv_std, 1.0 / n,
                                0.0, 0.0, actor.grad.data_ptr(), self._loss.data_ptr(), ws, st))
-        check(L.mhppo_ppo_grad(13, 0, r.obs_c.data_ptr(), 13, r.S, idx.data_ptr(), K, r.M, critic.flat.data_ptr(),
-                               None, None, r.rtg.data_ptr(), None, 0.0, 0.0, 1.0 / n, 0.0, 0.0, critic.grad.data_ptr(),
-                               self._loss.data_ptr() + 8, ws, st))
         allreduce_sum_(actor.grad); allreduce_sum_(critic.grad)
         opti_actor.step(); opti_critic.step()
         return True
@@ -132,21 +142,21 @@ class Algo_PPO:
         r, L, st = self.rollout, _lib.lib(), self._stream()
         ws, D = self._ws.data_ptr(), r.shape_env_d
         idx, K = self._selection(None)
-        check(L.mhppo_value_stats(D, r.obs_d.data_ptr(), D, r.M, idx.data_ptr(), K, r.M, critic.flat.data_ptr(),
-                                  r.rew_d.data_ptr(), r.V_d.data_ptr(), self._stats.data_ptr(), ws, st))
-        ex = r.exist.view(-1) != 0
-        cnt = torch.stack([(ex & (r.act_d == 0)).sum(), (ex & (r.act_d == 1)).sum()]).double()
-        mean, inv_std, n = combine_stats(allreduce_sum_(self._stats).cpu())
-        cnt = allreduce_sum_(cnt).cpu()
+        n = self._global_count(None, K)
         if n < 1:
             return False
+        check(L.mhppo_critic_grad_stats(D, r.obs_d.data_ptr(), D, r.M, idx.data_ptr(), K, r.M, critic.flat.data_ptr(),
+                                        r.rew_d.data_ptr(), 1.0 / n, critic.grad.data_ptr(), self._loss.data_ptr() + 8,
+                                        r.V_d.data_ptr(), self._stats.data_ptr(), ws, st))
+        ex = r.exist.view(-1) != 0
+        cnt = torch.stack([(ex & (r.act_d == 0)).sum(), (ex & (r.act_d == 1)).sum()]).double()
+        mean, inv_std, n2 = combine_stats(allreduce_sum_(self._stats).cpu())
+        assert n2 == n, (n2, n)
+        cnt = allreduce_sum_(cnt).cpu()
         f0, f1 = float(cnt[0]) / n, float(cnt[1]) / n
         check(L.mhppo_ppo_grad(D, 2, r.obs_d.data_ptr(), D, r.M, idx.data_ptr(), K, r.M, actor.flat.data_ptr(),
                                r.act_d.data_ptr(), r.logp_d.data_ptr(), r.rew_d.data_ptr(), r.V_d.data_ptr(), mean, inv_std,
                                1.0 / n, f0, f1, actor.grad.data_ptr(), self._loss.data_ptr(), ws, st))
-        check(L.mhppo_ppo_grad(D, 0, r.obs_d.data_ptr(), D, r.M, idx.data_ptr(), K, r.M, critic.flat.data_ptr(),
-                               None, None, r.rew_d.data_ptr(), None, 0.0, 0.0, 1.0 / n, 0.0, 0.0, critic.grad.data_ptr(),
-                               self._loss.data_ptr() + 8, ws, st))
         allreduce_sum_(actor.grad); allreduce_sum_(critic.grad)
         opti_actor.step(); opti_critic.step()
         return True

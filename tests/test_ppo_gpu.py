@@ -237,6 +237,16 @@ def test_gradients_match_autograd(mh):
     assert algo.train_model_c(actor, critic, algo.optimizer_actor_wait, algo.optimizer_critic_wait, 1)
     torch.cuda.synchronize()
     np.testing.assert_allclose(algo._loss.cpu().numpy(), [float(la), float(lc)], rtol=1e-5)
+    # the critic pass also returns V = critic(s) of the not yet updated critic (mhppo_critic_grad_stats) ...
+    np.testing.assert_allclose(r.V.cpu()[sel].numpy(), V.detach().numpy(), rtol=1e-5, atol=1e-5)
+    # ... and the same statistics as the stand-alone critic forward (mhppo_value_stats)
+    from mhppo_b200._lib import check
+    idx, K = algo._selection(1)
+    st2, V2 = torch.zeros(3, dtype=torch.float64, device="cuda"), torch.zeros_like(r.V)
+    check(mh.lib().mhppo_value_stats(13, r.obs_c.data_ptr(), 13, r.S, idx.data_ptr(), K, r.M, before_c.data_ptr(), r.rtg.data_ptr(),
+                                     V2.data_ptr(), st2.data_ptr(), algo._ws.data_ptr(), None))
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(algo._stats.cpu().numpy(), st2.cpu().numpy(), rtol=1e-5 if mh.mlp_mode == "ffma" else 1e-4)
     for net, grads, ref in ((actor, ga, a_o), (critic, gc, c_o)):
         tmp = mh.Model_PPO(13, 1, net.model_type, device="cpu")
         tmp.load_state_dict({k: gg for (k, _), gg in zip(ref.named_parameters(), grads)})
