@@ -6,6 +6,12 @@ ALL_CONFIGS = [
     ("coop", 2, 1, 2), ("coop", 3, 3, 3), ("stop", 1, 2, 1), ("stop", 2, 3, 2), ("naif", 1, 2, 1), ("naif", 3, 3, 2),
     ("coop_4cars", 2, 2, 2), ("coop_4cars", 1, 1, 1), ("coop_4cars2", 2, 2, 2), ("coop_4cars2", 3, 2, 3),
 ]
+# one more config per remaining (variant, car slots, pedestrian slots) kernel instantiation (csrc/env_inst_*.cu)
+EXTRA_CONFIGS = [
+    ("coop_scalable", 2, 4, 1), ("coop_scalable", 3, 4, 2), ("coop", 2, 3, 2), ("coop", 6, 4, 3), ("stop", 3, 4, 2), ("stop", 5, 3, 3),
+    ("naif", 2, 4, 2), ("naif", 7, 2, 4), ("coop_4cars", 2, 3, 2), ("coop_4cars", 3, 4, 3), ("coop_4cars", 4, 2, 4),
+    ("coop_4cars2", 2, 4, 2), ("coop_4cars2", 4, 3, 2),
+]
 INT_KEYS = ("car_i", "ped_i", "env_i")
 FLT_KEYS = ("car_f", "ped_f", "env_f")
 

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-from common import ALL_CONFIGS, ATOL_F32, FLT_KEYS, INT_KEYS, assert_close, assert_equal, compare_vec_envs, random_actions
+from common import ALL_CONFIGS, ATOL_F32, EXTRA_CONFIGS, FLT_KEYS, INT_KEYS, assert_close, assert_equal, compare_vec_envs, random_actions
 from conftest import golden_files, load_golden
 
 pytestmark = pytest.mark.gpu
@@ -28,6 +28,17 @@ def test_cuda_matches_oracle(oracle_mod, cuda_env_cls, cfg):
     ref = oracle_mod.OracleVecEnv(v, N, c, p, l, seed=42, env_id0=5000, store_f32=True)
     got = cuda_env_cls(v, N, c, p, l, seed=42, env_id0=5000)
     compare_vec_envs(ref, got, 165, np.random.default_rng(3), rtol=RTOL, check_state_every=4)
+
+
+@pytest.mark.parametrize("cfg", EXTRA_CONFIGS, ids=lambda c: "%s_%d%d%d" % c)
+def test_every_kernel_instantiation_matches_oracle(oracle_mod, cuda_env_cls, cfg):
+    """The configs above leave some (variant, car slots, pedestrian slots) instantiations untouched: one config each,
+    a ragged env count (tail CTA), one full episode with auto-reset."""
+    v, c, p, l = cfg
+    N = 300
+    ref = oracle_mod.OracleVecEnv(v, N, c, p, l, seed=9, env_id0=77, store_f32=True)
+    got = cuda_env_cls(v, N, c, p, l, seed=9, env_id0=77)
+    compare_vec_envs(ref, got, 85, np.random.default_rng(5), rtol=RTOL, check_state_every=5)
 
 
 @pytest.mark.parametrize("path", golden_files(), ids=lambda p: p.split("/")[-1][:-4])
