@@ -7,6 +7,7 @@
 #include "ppo_rollout.cuh"
 #include "ppo_update.cuh"
 #include "tc_kernels.cuh"
+#include "tc_grad.cuh"
 #include <cstdlib>
 
 namespace mhppo {
@@ -66,8 +67,18 @@ using namespace mhppo;
         if (rc_) return rc_;                                                                                         \
     } while (0)
 
+// 13-input nets, heads 0 / 1: forward and backward-data on the tensor cores (tc_grad.cuh) unless MHPPO_MLP=ffma
+static int launch_grad_tc(int head, const SampleSet &ss, const float *net, const LossArgs &la, const Workspace &w, cudaStream_t s) {
+    const size_t sm = sizeof(float) * kTcGradSmemFloats;
+    if (head == 0) { SET_SMEM((k_ppo_grad_tc<0>), sm); k_ppo_grad_tc<0><<<kGradGrid, kMlpBlock, sm, s>>>(ss, net, la, w.gpartial, w.lpartial, fail_flag()); }
+    else { SET_SMEM((k_ppo_grad_tc<1>), sm); k_ppo_grad_tc<1><<<kGradGrid, kMlpBlock, sm, s>>>(ss, net, la, w.gpartial, w.lpartial, fail_flag()); }
+    api_count_launch();
+    return ck(cudaGetLastError(), "k_ppo_grad_tc");
+}
+
 template <int KP>
 static int launch_grad(int head, const SampleSet &ss, const float *net, const LossArgs &la, const Workspace &w, cudaStream_t s) {
+    if (KP == 16 && head != 2 && use_tc(false)) return launch_grad_tc(head, ss, net, la, w, s);
     const size_t sm = smem_grad<KP>();
     if (head == 0) { SET_SMEM((k_ppo_grad<KP, 0>), sm); k_ppo_grad<KP, 0><<<kGradGrid, kMlpBlock, sm, s>>>(ss, net, la, w.gpartial, w.lpartial); }
     else if (head == 1) { SET_SMEM((k_ppo_grad<KP, 1>), sm); k_ppo_grad<KP, 1><<<kGradGrid, kMlpBlock, sm, s>>>(ss, net, la, w.gpartial, w.lpartial); }

@@ -213,11 +213,152 @@ __device__ __forceinline__ void wgrad_tile(float (&acc)[4][TJ], const float *__r
     }
 }
 
+// ---- loss epilogue of one sample (shared by the FFMA and the tensor-core kernel) ------------------------
 // HEAD: 0 = critic (MSE), 1 = Gaussian actor (clipped surrogate), 2 = categorical actor with the (M,M) broadcast.
-// Per tile: [thread = sample] forward + loss + dz; then, layer by layer from the top, [tiles] weight gradient from
-// (input activation, delta) and [thread = sample] backward-data which overwrites the activation with its delta.
-// For the weight gradient the CTA splits into two halves of 64 threads; each half sums over half of the tile's rows
-// and every thread of a half owns a 4 x TJ tile of every matrix; the halves are added once, after the last tile.
+// o: raw outputs of the net; returns dLoss/dz (4 padded outputs) and accumulates the loss and, for the critic,
+// the advantage statistics.
+struct LossAcc { double loss = 0.0, sA = 0.0, sAA = 0.0, cnt = 0.0; };
+template <int HEAD>
+__device__ __forceinline__ void ppo_loss(const LossArgs &la, int64_t s, float4 o, float (&dz)[OP], LossAcc &acc) {
+    if (HEAD == 0) {                                           // critic_loss = MSE(V, rtg), PY:808-809
+        const float e = o.x - la.rtg[s];
+        acc.loss += (double)e * (double)e * (double)la.inv_n;
+        dz[0] = 2.0f * e * la.inv_n;
+        if (la.V_out) {                                        // V = critic(s), A = rtgs - V (PY:785-786)
+            la.V_out[s] = o.x;
+            const double A = (double)(la.rtg[s] - o.x);
+            acc.sA += A; acc.sAA += A * A; acc.cnt += 1.0;
+        }
+        return;
+    }
+    const float An = ((la.rtg[s] - la.V[s]) - la.adv_mean) * la.adv_inv_std;     // PY:786-787
+    if (HEAD == 1) {
+        const float th = tanhf(o.x), mu = th * 3.0f + (-1.0f);
+        const float a = la.act[s];
+        const float lp = -((a - mu) * (a - mu)) - 0.57236494292470008f;          // MVN(mu, .5 I).log_prob, PY:795-800
+        const float ratio = expf(lp - la.logp_old[s]);                           // PY:803
+        const float s1 = ratio * An, s2 = fminf(fmaxf(ratio, 0.8f), 1.2f) * An;   // PY:804-805
+        acc.loss += (double)(-fminf(s1, s2)) * (double)la.inv_n;                 // PY:806
+        if (s1 <= s2) dz[0] = -la.inv_n * An * ratio * (2.0f * (a - mu)) * (3.0f * (1.0f - th * th));
+    } else {
+        // Categorical(probs [M,2]).log_prob(actions [M,1]) broadcasts to (M,M): lp[i,j] = log p_j(a_i)
+        // (PY:834-842).  With two actions the mean over i collapses to the action frequencies f0, f1.
+        const float m = fmaxf(o.x, o.y), e0 = expf(o.x - m), e1 = expf(o.y - m);
+        const float p0 = e0 / (e0 + e1), p1 = e1 / (e0 + e1);
+        const float inv_old = expf(-la.logp_old[s]);
+        float dp0 = 0.f, dp1 = 0.f;
+        {
+            const float rr = p0 * inv_old, s1 = rr * An, s2 = fminf(fmaxf(rr, 0.8f), 1.2f) * An;
+            acc.loss += (double)(-fminf(s1, s2)) * (double)(la.f0 * la.inv_n);
+            if (s1 <= s2) dp0 = -la.inv_n * la.f0 * An * inv_old;
+        }
+        {
+            const float rr = p1 * inv_old, s1 = rr * An, s2 = fminf(fmaxf(rr, 0.8f), 1.2f) * An;
+            acc.loss += (double)(-fminf(s1, s2)) * (double)(la.f1 * la.inv_n);
+            if (s1 <= s2) dp1 = -la.inv_n * la.f1 * An * inv_old;
+        }
+        // softmax backward: dz_a = p_a * (dp_a - sum_b p_b dp_b)
+        const float dot = p0 * dp0 + p1 * dp1;
+        dz[0] = p0 * (dp0 - dot); dz[1] = p1 * (dp1 - dot);
+    }
+}
+
+// ---- the weight-gradient register tiles of one thread (persist over all tiles of a CTA) ------------------
+// The CTA's 128 threads split into two halves of 64; each half sums over half of the tile's rows and every thread of a
+// half owns a 4 x TJ tile of every matrix; the halves are added once, after the last tile (finish).
+// Row layout: [x KP | a1/delta1 32 | a2/delta2 64 | a3/delta3 32 | dz 4], `row` floats apart.
+template <int KP>
+struct WgradAcc {
+    static constexpr int NKG1 = KP / 4;                                        // k-groups of layer 1
+    static constexpr int JG1 = (NKG1 <= 4) ? 16 : ((NKG1 <= 8) ? 8 : 4);       // j-groups of layer 1 (NKG1 * JG1 <= 64 threads)
+    static constexpr int TJ1 = H1 / JG1;
+    static constexpr int X = 0, A1 = KP, A2 = KP + H1, A3 = KP + H1 + H2, D4 = KP + H1 + H2 + H3;
+    float g1[4][TJ1], g2[4][8], g3[4][8], g4[2], gb4[2], gbias[2];
+    int half, lt, k1, j1, k2, j2, k3, j3, k4, j4;
+    bool l1_on;
+    __device__ __forceinline__ void init(int tid) {
+        half = tid >> 6; lt = tid & 63;
+        l1_on = lt < NKG1 * JG1;
+        k1 = (lt % NKG1) * 4; j1 = (lt / NKG1) * TJ1;                          // dW1t[k < KP][j < 32]
+        k2 = (lt & 7) * 4; j2 = (lt >> 3) * 8;                                 // dW2t[k < 32][j < 64]
+        k3 = (lt & 15) * 4; j3 = (lt >> 4) * 8;                                // dW3t[k < 64][j < 32]
+        k4 = lt & 31; j4 = (lt >> 5) * 2;                                      // dW4t[k < 32][j < 4]
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+            for (int j = 0; j < TJ1; ++j) g1[kk][j] = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { g2[kk][j] = 0.f; g3[kk][j] = 0.f; }
+        }
+        g4[0] = g4[1] = gb4[0] = gb4[1] = gbias[0] = gbias[1] = 0.f;
+    }
+    // layer 4: dW4t[k][j], b4[j] from (a3, dz) of the rows [s0, s0 + ns)
+    __device__ __forceinline__ void layer4(const float *__restrict__ rows, int row, int s0, int ns) {
+        for (int s = s0; s < s0 + ns; ++s) {
+            const float *r = rows + (size_t)s * row;
+            const float a = r[A3 + k4];
+            const float2 d = *reinterpret_cast<const float2 *>(r + D4 + j4);
+            g4[0] = fmaf(a, d.x, g4[0]); g4[1] = fmaf(a, d.y, g4[1]);
+            gb4[0] += d.x; gb4[1] += d.y;
+        }
+    }
+    __device__ __forceinline__ void layer3(const float *rows, int row, int s0, int ns) { wgrad_tile<8>(g3, rows, row, A2 + k3, A3 + j3, s0, ns); }
+    __device__ __forceinline__ void layer2(const float *rows, int row, int s0, int ns) { wgrad_tile<8>(g2, rows, row, A1 + k2, A2 + j2, s0, ns); }
+    // layer 1 and the bias gradients b1 | b2 | b3 (the deltas sit in a1, a2, a3 of every row: 128 consecutive columns)
+    __device__ __forceinline__ void layer1_and_biases(const float *__restrict__ rows, int row, int s0, int ns) {
+        if (l1_on) wgrad_tile<TJ1>(g1, rows, row, X + k1, A1 + j1, s0, ns);
+        for (int s = s0; s < s0 + ns; ++s) {
+            const float2 d = *reinterpret_cast<const float2 *>(rows + (size_t)s * row + A1 + 2 * lt);
+            gbias[0] += d.x; gbias[1] += d.y;
+        }
+    }
+    __device__ __forceinline__ void emit(float *dst, bool add) const {
+        if (l1_on)
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+                for (int j = 0; j < TJ1; ++j) { float &q = dst[(k1 + kk) * H1 + j1 + j]; q = add ? q + g1[kk][j] : g1[kk][j]; }
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float &q2 = dst[off_w2(KP) + (k2 + kk) * H2 + j2 + j]; q2 = add ? q2 + g2[kk][j] : g2[kk][j];
+                float &q3 = dst[off_w3(KP) + (k3 + kk) * H3 + j3 + j]; q3 = add ? q3 + g3[kk][j] : g3[kk][j];
+            }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            float &q4 = dst[off_w4(KP) + k4 * OP + j4 + j]; q4 = add ? q4 + g4[j] : g4[j];
+            if (k4 == 0) { float &qb = dst[off_b4(KP) + j4 + j]; qb = add ? qb + gb4[j] : gb4[j]; }
+            const int c = 2 * lt + j;                   // column of (b1 | b2 | b3)
+            const int o = (c < H1) ? (off_b1(KP) + c) : ((c < H1 + H2) ? (off_b2(KP) + c - H1) : (off_b3(KP) + c - H1 - H2));
+            float &qq = dst[o]; qq = add ? qq + gbias[j] : gbias[j];
+        }
+    }
+    // add the two halves through `scratch` (>= net_params floats of shared memory no longer in use) and write the CTA's
+    // partial gradient, loss and (critic) advantage statistics
+    template <int HEAD>
+    __device__ __forceinline__ void finish(float *scratch, float *__restrict__ gpartial, double *__restrict__ lpartial, const LossArgs &la,
+                                           const LossAcc &acc, double *red) const {
+        constexpr int NPAR = net_params(KP);
+        const int tid = threadIdx.x;
+        if (half == 1) emit(scratch, false);
+        __syncthreads();
+        if (half == 0) emit(scratch, true);
+        __syncthreads();
+        float *gp = gpartial + (size_t)blockIdx.x * NPAR;
+        for (int i = tid; i < NPAR; i += kMlpBlock) gp[i] = scratch[i];
+        const double lt_sum = team_sum(acc.loss, red, tid, kMlpBlock, 0);
+        if (tid == 0) lpartial[blockIdx.x] = lt_sum;
+        if (HEAD == 0 && la.spartial) {
+            const double t0 = team_sum(acc.sA, red, tid, kMlpBlock, 0), t1 = team_sum(acc.sAA, red, tid, kMlpBlock, 0),
+                         t2 = team_sum(acc.cnt, red, tid, kMlpBlock, 0);
+            if (tid == 0) { la.spartial[blockIdx.x * 3 + 0] = t0; la.spartial[blockIdx.x * 3 + 1] = t1; la.spartial[blockIdx.x * 3 + 2] = t2; }
+        }
+    }
+};
+
+// Per tile: [thread = R samples] forward + loss + dz; then, layer by layer from the top, [register tiles] weight gradient from
+// (input activation, delta) and [thread = R samples] backward-data which overwrites the activation with its delta.
 constexpr int kTeams = 1;
 template <int KP, int HEAD>
 __global__ void __launch_bounds__(kMlpBlock, 1) k_ppo_grad(SampleSet ss, const float *__restrict__ net, LossArgs la,
@@ -225,7 +366,7 @@ __global__ void __launch_bounds__(kMlpBlock, 1) k_ppo_grad(SampleSet ss, const f
                                                            double *__restrict__ lpartial /* [grid] */) {
     extern __shared__ __align__(16) float smem[];
     typedef GradCfg<KP> G;
-    constexpr int R = G::R, ROW = G::ROW, NPAR = G::NPAR;
+    constexpr int R = G::R, ROW = G::ROW;
     float *sw = smem;                                  // flat net (transposed weights)
     float *W2 = sw + G::NP4;                           // [H2][H1] original orientation, for backward-data
     float *W3 = W2 + H2 * H1;                          // [H3][H2]
@@ -239,29 +380,14 @@ __global__ void __launch_bounds__(kMlpBlock, 1) k_ppo_grad(SampleSet ss, const f
     for (int i = threadIdx.x; i < H3 * OP; i += blockDim.x) { const int k = i / OP, j = i % OP; W4[j * H3 + k] = sw[off_w4(KP) + i]; }
     __syncthreads();
 
-    const int tid = threadIdx.x, half = tid >> 6, lt = tid & 63;
+    const int tid = threadIdx.x;
     float *my = rows + (size_t)tid * ROW;              // row of this thread's first sample; the r-th is kMlpBlock rows further
     constexpr int RS = kMlpBlock * ROW;
-    // weight-gradient tiles of this thread (persist over all tiles of this CTA)
-    constexpr int NKG1 = KP / 4;                                        // k-groups of layer 1
-    constexpr int JG1 = (NKG1 <= 4) ? 16 : ((NKG1 <= 8) ? 8 : 4);       // j-groups of layer 1 (NKG1 * JG1 <= 64 threads)
-    constexpr int TJ1 = H1 / JG1;
-    float g1[4][TJ1], g2[4][8], g3[4][8], g4[2] = {0.f, 0.f}, gb4[2] = {0.f, 0.f}, gbias[2] = {0.f, 0.f};
-#pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
-#pragma unroll
-        for (int j = 0; j < TJ1; ++j) g1[kk][j] = 0.f;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { g2[kk][j] = 0.f; g3[kk][j] = 0.f; }
-    }
-    const bool l1_on = lt < NKG1 * JG1;
-    const int k1 = (lt % NKG1) * 4, j1 = (lt / NKG1) * TJ1;             // dW1t[k < KP][j < 32]
-    const int k2 = (lt & 7) * 4, j2 = (lt >> 3) * 8;                    // dW2t[k < 32][j < 64]
-    const int k3 = (lt & 15) * 4, j3 = (lt >> 4) * 8;                   // dW3t[k < 64][j < 32]
-    const int k4 = lt & 31, j4 = (lt >> 5) * 2;                         // dW4t[k < 32][j < 4]
+    WgradAcc<KP> wg;
+    wg.init(tid);
     constexpr int HALF = G::TILE / 2;
-    const int s0 = half * HALF;
-    double loss = 0.0, sA = 0.0, sAA = 0.0, cnt = 0.0;
+    const int s0 = wg.half * HALF;
+    LossAcc acc;
 
     for (int64_t base = (int64_t)blockIdx.x * G::TILE; base < ss.Q; base += (int64_t)gridDim.x * G::TILE) {
         bool sel[R];
@@ -288,119 +414,28 @@ __global__ void __launch_bounds__(kMlpBlock, 1) k_ppo_grad(SampleSet ss, const f
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             float *row = my + r * RS;
-            const float4 o = ld4(row + G::D4);
-            const int64_t s = sidx[r];
             float dz[OP] = {0.f, 0.f, 0.f, 0.f};
-            if (sel[r]) {
-                if (HEAD == 0) {                                           // critic_loss = MSE(V, rtg), PY:808-809
-                    const float e = o.x - la.rtg[s];
-                    loss += (double)e * (double)e * (double)la.inv_n;
-                    dz[0] = 2.0f * e * la.inv_n;
-                    if (la.V_out) {                                        // V = critic(s), A = rtgs - V (PY:785-786)
-                        la.V_out[s] = o.x;
-                        const double A = (double)(la.rtg[s] - o.x);
-                        sA += A; sAA += A * A; cnt += 1.0;
-                    }
-                } else {
-                    const float An = ((la.rtg[s] - la.V[s]) - la.adv_mean) * la.adv_inv_std;     // PY:786-787
-                    if (HEAD == 1) {
-                        const float th = tanhf(o.x), mu = th * 3.0f + (-1.0f);
-                        const float a = la.act[s];
-                        const float lp = -((a - mu) * (a - mu)) - 0.57236494292470008f;          // MVN(mu, .5 I).log_prob, PY:795-800
-                        const float ratio = expf(lp - la.logp_old[s]);                           // PY:803
-                        const float s1 = ratio * An, s2 = fminf(fmaxf(ratio, 0.8f), 1.2f) * An;   // PY:804-805
-                        loss += (double)(-fminf(s1, s2)) * (double)la.inv_n;                     // PY:806
-                        if (s1 <= s2) dz[0] = -la.inv_n * An * ratio * (2.0f * (a - mu)) * (3.0f * (1.0f - th * th));
-                    } else {
-                        // Categorical(probs [M,2]).log_prob(actions [M,1]) broadcasts to (M,M): lp[i,j] = log p_j(a_i)
-                        // (PY:834-842).  With two actions the mean over i collapses to the action frequencies f0, f1.
-                        const float m = fmaxf(o.x, o.y), e0 = expf(o.x - m), e1 = expf(o.y - m);
-                        const float p0 = e0 / (e0 + e1), p1 = e1 / (e0 + e1);
-                        const float inv_old = expf(-la.logp_old[s]);
-                        float dp0 = 0.f, dp1 = 0.f;
-                        {
-                            const float rr = p0 * inv_old, s1 = rr * An, s2 = fminf(fmaxf(rr, 0.8f), 1.2f) * An;
-                            loss += (double)(-fminf(s1, s2)) * (double)(la.f0 * la.inv_n);
-                            if (s1 <= s2) dp0 = -la.inv_n * la.f0 * An * inv_old;
-                        }
-                        {
-                            const float rr = p1 * inv_old, s1 = rr * An, s2 = fminf(fmaxf(rr, 0.8f), 1.2f) * An;
-                            loss += (double)(-fminf(s1, s2)) * (double)(la.f1 * la.inv_n);
-                            if (s1 <= s2) dp1 = -la.inv_n * la.f1 * An * inv_old;
-                        }
-                        // softmax backward: dz_a = p_a * (dp_a - sum_b p_b dp_b)
-                        const float dot = p0 * dp0 + p1 * dp1;
-                        dz[0] = p0 * (dp0 - dot); dz[1] = p1 * (dp1 - dot);
-                    }
-                }
-            }
+            if (sel[r]) ppo_loss<HEAD>(la, sidx[r], ld4(row + G::D4), dz, acc);
             // an unselected row has x = 0 but its activations are relu(bias) != 0: its dz = 0 keeps every gradient term zero
             st4(row + G::D4, make_float4(dz[0], dz[1], dz[2], dz[3]));
         }
         __syncthreads();
-        // layer 4: dW4t[k][j], b4[j]
-        for (int s = s0; s < s0 + HALF; ++s) {
-            const float *r = rows + (size_t)s * ROW;
-            const float a = r[G::A3 + k4];
-            const float2 d = *reinterpret_cast<const float2 *>(r + G::D4 + j4);
-            g4[0] = fmaf(a, d.x, g4[0]); g4[1] = fmaf(a, d.y, g4[1]);
-            gb4[0] += d.x; gb4[1] += d.y;
-        }
+        wg.layer4(rows, ROW, s0, HALF);
         __syncthreads();
         dense_bwd_t<H3, OP, R>(my + G::A3, my + G::D4, RS, W4);           // a3 now holds delta3
         __syncthreads();
-        wgrad_tile<8>(g3, rows, ROW, G::A2 + k3, G::A3 + j3, s0, HALF);
+        wg.layer3(rows, ROW, s0, HALF);
         __syncthreads();
         dense_bwd_t<H2, H3, R>(my + G::A2, my + G::A3, RS, W3);           // a2 now holds delta2
         __syncthreads();
-        wgrad_tile<8>(g2, rows, ROW, G::A1 + k2, G::A2 + j2, s0, HALF);
+        wg.layer2(rows, ROW, s0, HALF);
         __syncthreads();
         dense_bwd_t<H1, H2, R>(my + G::A1, my + G::A2, RS, W2);           // a1 now holds delta1
         __syncthreads();
-        if (l1_on) wgrad_tile<TJ1>(g1, rows, ROW, G::X + k1, G::A1 + j1, s0, HALF);
-        // bias gradients b1 | b2 | b3: the deltas now sit in a1, a2, a3 of every row (128 consecutive columns)
-        for (int s = s0; s < s0 + HALF; ++s) {
-            const float2 d = *reinterpret_cast<const float2 *>(rows + (size_t)s * ROW + G::A1 + 2 * lt);
-            gbias[0] += d.x; gbias[1] += d.y;
-        }
+        wg.layer1_and_biases(rows, ROW, s0, HALF);
         __syncthreads();
     }
-    // ---- add the two halves and emit this CTA's partial gradient
-    float *scratch = rows;                              // NPAR floats, the tile rows are dead now
-    auto emit = [&](float *dst, bool add) {
-        if (l1_on)
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk)
-#pragma unroll
-                for (int j = 0; j < TJ1; ++j) { float &q = dst[(k1 + kk) * H1 + j1 + j]; q = add ? q + g1[kk][j] : g1[kk][j]; }
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk)
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                float &q2 = dst[off_w2(KP) + (k2 + kk) * H2 + j2 + j]; q2 = add ? q2 + g2[kk][j] : g2[kk][j];
-                float &q3 = dst[off_w3(KP) + (k3 + kk) * H3 + j3 + j]; q3 = add ? q3 + g3[kk][j] : g3[kk][j];
-            }
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            float &q4 = dst[off_w4(KP) + k4 * OP + j4 + j]; q4 = add ? q4 + g4[j] : g4[j];
-            if (k4 == 0) { float &qb = dst[off_b4(KP) + j4 + j]; qb = add ? qb + gb4[j] : gb4[j]; }
-            const int c = 2 * lt + j;                   // column of (b1 | b2 | b3)
-            const int o = (c < H1) ? (off_b1(KP) + c) : ((c < H1 + H2) ? (off_b2(KP) + c - H1) : (off_b3(KP) + c - H1 - H2));
-            float &qq = dst[o]; qq = add ? qq + gbias[j] : gbias[j];
-        }
-    };
-    if (half == 1) emit(scratch, false);
-    __syncthreads();
-    if (half == 0) emit(scratch, true);
-    __syncthreads();
-    float *gp = gpartial + (size_t)blockIdx.x * NPAR;
-    for (int i = tid; i < NPAR; i += kMlpBlock) gp[i] = scratch[i];
-    const double lt_sum = team_sum(loss, red, tid, kMlpBlock, 0);
-    if (tid == 0) lpartial[blockIdx.x] = lt_sum;
-    if (HEAD == 0 && la.spartial) {
-        const double t0 = team_sum(sA, red, tid, kMlpBlock, 0), t1 = team_sum(sAA, red, tid, kMlpBlock, 0), t2 = team_sum(cnt, red, tid, kMlpBlock, 0);
-        if (tid == 0) { la.spartial[blockIdx.x * 3 + 0] = t0; la.spartial[blockIdx.x * 3 + 1] = t1; la.spartial[blockIdx.x * 3 + 2] = t2; }
-    }
+    wg.template finish<HEAD>(rows, gpartial, lpartial, la, acc, red);
 }
 
 // ---- 4. deterministic reduction of the per-CTA partials ----------------------------------------------
