@@ -70,8 +70,8 @@ using namespace mhppo;
 // 13-input nets, heads 0 / 1: forward and backward-data on the tensor cores (tc_grad.cuh) unless MHPPO_MLP=ffma
 static int launch_grad_tc(int head, const SampleSet &ss, const float *net, const LossArgs &la, const Workspace &w, cudaStream_t s) {
     const size_t sm = sizeof(float) * kTcGradSmemFloats;
-    if (head == 0) { SET_SMEM((k_ppo_grad_tc<0>), sm); k_ppo_grad_tc<0><<<kGradGrid, kMlpBlock, sm, s>>>(ss, net, la, w.gpartial, w.lpartial, fail_flag()); }
-    else { SET_SMEM((k_ppo_grad_tc<1>), sm); k_ppo_grad_tc<1><<<kGradGrid, kMlpBlock, sm, s>>>(ss, net, la, w.gpartial, w.lpartial, fail_flag()); }
+    if (head == 0) { SET_SMEM((k_ppo_grad_tc<0>), sm); k_ppo_grad_tc<0><<<kGradGrid, kTcGradBlock, sm, s>>>(ss, net, la, w.gpartial, w.lpartial, fail_flag()); }
+    else { SET_SMEM((k_ppo_grad_tc<1>), sm); k_ppo_grad_tc<1><<<kGradGrid, kTcGradBlock, sm, s>>>(ss, net, la, w.gpartial, w.lpartial, fail_flag()); }
     api_count_launch();
     return ck(cudaGetLastError(), "k_ppo_grad_tc");
 }

@@ -264,10 +264,10 @@ __device__ __forceinline__ void ppo_loss(const LossArgs &la, int64_t s, float4 o
 }
 
 // ---- the weight-gradient register tiles of one thread (persist over all tiles of a CTA) ------------------
-// The CTA's 128 threads split into two halves of 64; each half sums over half of the tile's rows and every thread of a
-// half owns a 4 x TJ tile of every matrix; the halves are added once, after the last tile (finish).
+// The CTA's threads split into NG groups of 64; each group sums over 1/NG of the tile's rows and every thread of a
+// group owns a 4 x TJ tile of every matrix; the groups are added once, after the last tile (finish).  `half` = group.
 // Row layout: [x KP | a1/delta1 32 | a2/delta2 64 | a3/delta3 32 | dz 4], `row` floats apart.
-template <int KP>
+template <int KP, int NG = 2>
 struct WgradAcc {
     static constexpr int NKG1 = KP / 4;                                        // k-groups of layer 1
     static constexpr int JG1 = (NKG1 <= 4) ? 16 : ((NKG1 <= 8) ? 8 : 4);       // j-groups of layer 1 (NKG1 * JG1 <= 64 threads)
@@ -334,24 +334,24 @@ struct WgradAcc {
             float &qq = dst[o]; qq = add ? qq + gbias[j] : gbias[j];
         }
     }
-    // add the two halves through `scratch` (>= net_params floats of shared memory no longer in use) and write the CTA's
-    // partial gradient, loss and (critic) advantage statistics
+    // add the NG groups through `scratch` (>= net_params floats of shared memory no longer in use) and write the CTA's
+    // partial gradient, loss and (critic) advantage statistics; `red` holds one double per warp of the CTA
     template <int HEAD>
     __device__ __forceinline__ void finish(float *scratch, float *__restrict__ gpartial, double *__restrict__ lpartial, const LossArgs &la,
                                            const LossAcc &acc, double *red) const {
-        constexpr int NPAR = net_params(KP);
+        constexpr int NPAR = net_params(KP), NT = 64 * NG;
         const int tid = threadIdx.x;
-        if (half == 1) emit(scratch, false);
-        __syncthreads();
-        if (half == 0) emit(scratch, true);
-        __syncthreads();
+#pragma unroll 1
+        for (int g = 0; g < NG; ++g) {                  // fixed order: deterministic
+            if (half == g) emit(scratch, g > 0);
+            __syncthreads();
+        }
         float *gp = gpartial + (size_t)blockIdx.x * NPAR;
-        for (int i = tid; i < NPAR; i += kMlpBlock) gp[i] = scratch[i];
-        const double lt_sum = team_sum(acc.loss, red, tid, kMlpBlock, 0);
+        for (int i = tid; i < NPAR; i += NT) gp[i] = scratch[i];
+        const double lt_sum = team_sum(acc.loss, red, tid, NT, 0);
         if (tid == 0) lpartial[blockIdx.x] = lt_sum;
         if (HEAD == 0 && la.spartial) {
-            const double t0 = team_sum(acc.sA, red, tid, kMlpBlock, 0), t1 = team_sum(acc.sAA, red, tid, kMlpBlock, 0),
-                         t2 = team_sum(acc.cnt, red, tid, kMlpBlock, 0);
+            const double t0 = team_sum(acc.sA, red, tid, NT, 0), t1 = team_sum(acc.sAA, red, tid, NT, 0), t2 = team_sum(acc.cnt, red, tid, NT, 0);
             if (tid == 0) { la.spartial[blockIdx.x * 3 + 0] = t0; la.spartial[blockIdx.x * 3 + 1] = t1; la.spartial[blockIdx.x * 3 + 2] = t2; }
         }
     }

@@ -2,7 +2,7 @@
 // backward-data on the 5th-generation tensor cores (13-input nets: cross / wait actors and critics).
 //
 // Same contract as k_ppo_grad<16, HEAD> (ppo_update.cuh), which stays as the exact-fp32 cross-check and serves the wider
-// choice nets.  One persistent 128-thread CTA per SM walks 128-sample tiles; thread = sample = TMEM lane.
+// choice nets.  One persistent 256-thread CTA per SM walks 128-sample tiles; in warps 0-3 thread = sample = TMEM lane.
 //   forward       D[128 x J] = A[128 x K] * W[J x K]^T         (tc_mlp.cuh: 3xTF32, hi/lo operand tiles, fp32 in TMEM)
 //   backward-data dIn[128 x K] = delta[128 x J] * W[J x K]     = the same MMA shapes with B = the FLAT transposed weights
 //                 Wt[k][j] read as an [N = K rows][reduction = J] K-major tile (BwdTiles)
@@ -43,15 +43,16 @@ constexpr int kTcGradRow = 16 + H1 + H2 + H3 + OP;       // 148 floats: 16-byte 
 constexpr int kTcGradNetFloats = (tcm::NetTiles<16>::FLOATS + 255) & ~255;
 constexpr size_t kTcGradSmemFloats = (size_t)kTcGradNetFloats + BwdTiles::FLOATS + 2 * 128 * H2 + (size_t)128 * kTcGradRow;
 
+constexpr int kTcGradBlock = 256;      // warps 0-3: thread = sample (MMA issue, epilogues); all 8 warps: weight-gradient tiles
 template <int HEAD>
-__global__ void __launch_bounds__(kMlpBlock, 1) k_ppo_grad_tc(SampleSet ss, const float *__restrict__ net, LossArgs la,
+__global__ void __launch_bounds__(kTcGradBlock, 1) k_ppo_grad_tc(SampleSet ss, const float *__restrict__ net, LossArgs la,
                                                               float *__restrict__ gpartial, double *__restrict__ lpartial,
                                                               int *__restrict__ fail_flag) {
     constexpr int KP = 16, ROW = kTcGradRow;
-    typedef WgradAcc<KP> WG;
+    typedef WgradAcc<KP, kTcGradBlock / 64> WG;
     extern __shared__ __align__(1024) float smem[];
     __shared__ TcShared sh;
-    __shared__ double red[kMlpBlock / 32];
+    __shared__ double red[kTcGradBlock / 32];
     tcm::NetTiles<KP> w;
     BwdTiles bw;
     w.carve(smem);
@@ -70,16 +71,18 @@ __global__ void __launch_bounds__(kMlpBlock, 1) k_ppo_grad_tc(SampleSet ss, cons
     float *row = rows + (size_t)tid * ROW;
     WG wg;
     wg.init(tid);
-    constexpr int HALF = 64;
+    constexpr int HALF = 128 / (kTcGradBlock / 64);     // rows per weight-gradient group
     const int s0 = wg.half * HALF;
+    const bool sample_thread = tid < 128;
     LossAcc acc;
 
     for (int64_t base = (int64_t)blockIdx.x * 128; base < ss.Q; base += (int64_t)gridDim.x * 128) {
         int64_t s = 0;
-        const bool sel = map_sample(ss, base + tid, s);
+        bool sel = false;
         float v[32];
         uint32_t m1 = 0, m2a = 0, m2b = 0, m3 = 0;                    // ReLU masks of the three hidden layers
-        {
+        if (sample_thread) {
+            sel = map_sample(ss, base + tid, s);
             float x[KP];
 #pragma unroll
             for (int k = 0; k < KP; ++k) x[k] = (sel && k < ss.D) ? ss.x[(int64_t)k * ss.S + s] : 0.f;
@@ -88,19 +91,21 @@ __global__ void __launch_bounds__(kMlpBlock, 1) k_ppo_grad_tc(SampleSet ss, cons
             tcm::put_row<KP>(ah, al, tid, x);
         }
         sync_for_mma();
-        // ---- forward
+        // ---- forward (warps 4-7 only keep the barriers company here)
         if (tid == 0) tcm::issue_layer<KP, H1>(tmem, ah, al, w.w1h, w.w1l, &sh.bar);
         wait_mma();
-        tc::tmem_ld32(trow, v);
+        if (sample_thread) {
+            tc::tmem_ld32(trow, v);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) { v[j] = fmaxf(v[j] + w.b1[j], 0.f); m1 |= (v[j] > 0.f ? 1u : 0u) << j; }
+            for (int j = 0; j < 32; ++j) { v[j] = fmaxf(v[j] + w.b1[j], 0.f); m1 |= (v[j] > 0.f ? 1u : 0u) << j; }
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) st4(row + WG::A1 + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
-        tcm::put_row<H1>(ah, al, tid, v);
+            for (int j = 0; j < 32; j += 4) st4(row + WG::A1 + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+            tcm::put_row<H1>(ah, al, tid, v);
+        }
         sync_for_mma();
         if (tid == 0) tcm::issue_layer<H1, H2>(tmem, ah, al, w.w2h, w.w2l, &sh.bar);
         wait_mma();
-        {
+        if (sample_thread) {
             float u[64];
             tc::tmem_ld32(trow, v);
 #pragma unroll
@@ -115,18 +120,20 @@ __global__ void __launch_bounds__(kMlpBlock, 1) k_ppo_grad_tc(SampleSet ss, cons
         sync_for_mma();
         if (tid == 0) tcm::issue_layer<H2, H3>(tmem, ah, al, w.w3h, w.w3l, &sh.bar);
         wait_mma();
-        tc::tmem_ld32(trow, v);
+        if (sample_thread) {
+            tc::tmem_ld32(trow, v);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) { v[j] = fmaxf(v[j] + w.b3[j], 0.f); m3 |= (v[j] > 0.f ? 1u : 0u) << j; }
+            for (int j = 0; j < 32; ++j) { v[j] = fmaxf(v[j] + w.b3[j], 0.f); m3 |= (v[j] > 0.f ? 1u : 0u) << j; }
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) st4(row + WG::A3 + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
-        tcm::put_row<H3>(ah, al, tid, v);
+            for (int j = 0; j < 32; j += 4) st4(row + WG::A3 + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+            tcm::put_row<H3>(ah, al, tid, v);
+        }
         sync_for_mma();
         if (tid == 0) tcm::issue_layer<H3, tcm::OUTP>(tmem, ah, al, w.w4h, w.w4l, &sh.bar);
         wait_mma();
-        tc::tmem_ld32(trow, v);          // columns >= 16 hold stale data of layer 3 and are ignored
-        // ---- loss epilogue -> dz (an unselected row keeps dz = 0: every gradient term of it vanishes)
-        {
+        if (sample_thread) {
+            tc::tmem_ld32(trow, v);      // columns >= 16 hold stale data of layer 3 and are ignored
+            // ---- loss epilogue -> dz (an unselected row keeps dz = 0: every gradient term of it vanishes)
             float dz[tcm::OUTP];
 #pragma unroll
             for (int j = 0; j < tcm::OUTP; ++j) dz[j] = 0.f;
@@ -138,24 +145,26 @@ __global__ void __launch_bounds__(kMlpBlock, 1) k_ppo_grad_tc(SampleSet ss, cons
             tcm::put_row<tcm::OUTP>(ah, al, tid, dz);
         }
         sync_for_mma();
-        // ---- layer 4: backward-data on the tensor core while the CUDA cores take dW4
+        // ---- layer 4: backward-data on the tensor core while the CUDA cores (all 8 warps) take dW4
         if (tid == 0) tcm::issue_layer<tcm::OUTP, H3>(tmem, ah, al, bw.w4h, bw.w4l, &sh.bar);
         wg.layer4(rows, ROW, s0, HALF);
         __syncthreads();                                  // every a3 has been read before the deltas overwrite it
         wait_mma();
-        tc::tmem_ld32(trow, v);
+        if (sample_thread) {
+            tc::tmem_ld32(trow, v);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = ((m3 >> j) & 1u) ? v[j] : 0.f;                 // delta3 = relu'(a3) * (dz W4)
+            for (int j = 0; j < 32; ++j) v[j] = ((m3 >> j) & 1u) ? v[j] : 0.f;             // delta3 = relu'(a3) * (dz W4)
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) st4(row + WG::A3 + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
-        tcm::put_row<H3>(ah, al, tid, v);
+            for (int j = 0; j < 32; j += 4) st4(row + WG::A3 + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+            tcm::put_row<H3>(ah, al, tid, v);
+        }
         sync_for_mma();
         // ---- layer 3
         if (tid == 0) tcm::issue_layer<H3, H2>(tmem, ah, al, bw.w3h, bw.w3l, &sh.bar);
         wg.layer3(rows, ROW, s0, HALF);
         __syncthreads();
         wait_mma();
-        {
+        if (sample_thread) {
             float u[64];
             tc::tmem_ld32(trow, v);
 #pragma unroll
@@ -173,11 +182,13 @@ __global__ void __launch_bounds__(kMlpBlock, 1) k_ppo_grad_tc(SampleSet ss, cons
         wg.layer2(rows, ROW, s0, HALF);
         __syncthreads();
         wait_mma();
-        tc::tmem_ld32(trow, v);
+        if (sample_thread) {
+            tc::tmem_ld32(trow, v);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = ((m1 >> j) & 1u) ? v[j] : 0.f;
+            for (int j = 0; j < 32; ++j) v[j] = ((m1 >> j) & 1u) ? v[j] : 0.f;
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) st4(row + WG::A1 + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+            for (int j = 0; j < 32; j += 4) st4(row + WG::A1 + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+        }
         tc::fence_before();
         __syncthreads();                                  // deltas visible; TMEM reads done before the next tile's MMAs
         tc::fence_after();
