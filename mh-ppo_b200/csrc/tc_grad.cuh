@@ -62,13 +62,14 @@ __global__ void __launch_bounds__(kTcGradBlock, 1) k_ppo_grad_tc(SampleSet ss, c
     bw.stage<KP>(net);
     const uint32_t tmem = tc_prologue(&sh);
     const int tid = threadIdx.x;
-    const uint32_t trow = tmem + ((uint32_t)((tid >> 5) * 32) << 16);
+    const int srow = tid & 127;                           // the sample (tile row, TMEM lane) this thread works on in the epilogues
+    const uint32_t trow = tmem + ((uint32_t)(((tid >> 5) & 3) * 32) << 16);
     uint32_t phase = 0;
     bool ok = true;
     auto sync_for_mma = [&]() { tc::fence_async_smem(); tc::fence_before(); __syncthreads(); tc::fence_after(); };
     auto wait_mma = [&]() { ok &= tc::mbar_wait(&sh.bar, phase); phase ^= 1; tc::fence_after(); };
 
-    float *row = rows + (size_t)tid * ROW;
+    float *row = rows + (size_t)srow * ROW;
     WG wg;
     wg.init(tid);
     constexpr int HALF = 128 / (kTcGradBlock / 64);     // rows per weight-gradient group
@@ -76,11 +77,13 @@ __global__ void __launch_bounds__(kTcGradBlock, 1) k_ppo_grad_tc(SampleSet ss, c
     const bool sample_thread = tid < 128;
     LossAcc acc;
 
+    // Epilogues: the two threads t and t + 128 share sample t (a warp reads the TMEM lanes of quadrant warp % 4, so warps
+    // w and w + 4 see the same rows); each takes half of the layer's columns: load, bias / ReLU (or mask), fp32 row, hi/lo tile.
+    const int hs = tid >> 7;                              // which half of the columns
     for (int64_t base = (int64_t)blockIdx.x * 128; base < ss.Q; base += (int64_t)gridDim.x * 128) {
         int64_t s = 0;
         bool sel = false;
-        float v[32];
-        uint32_t m1 = 0, m2a = 0, m2b = 0, m3 = 0;                    // ReLU masks of the three hidden layers
+        uint32_t m1 = 0, m2 = 0, m3 = 0;                  // ReLU masks of this thread's columns of the three hidden layers
         if (sample_thread) {
             sel = map_sample(ss, base + tid, s);
             float x[KP];
@@ -88,61 +91,64 @@ __global__ void __launch_bounds__(kTcGradBlock, 1) k_ppo_grad_tc(SampleSet ss, c
             for (int k = 0; k < KP; ++k) x[k] = (sel && k < ss.D) ? ss.x[(int64_t)k * ss.S + s] : 0.f;
 #pragma unroll
             for (int k = 0; k < KP; k += 4) st4(row + WG::X + k, make_float4(x[k], x[k + 1], x[k + 2], x[k + 3]));
-            tcm::put_row<KP>(ah, al, tid, x);
+            tcm::put_row<KP>(ah, al, srow, x);
         }
         sync_for_mma();
-        // ---- forward (warps 4-7 only keep the barriers company here)
+        // ---- forward
         if (tid == 0) tcm::issue_layer<KP, H1>(tmem, ah, al, w.w1h, w.w1l, &sh.bar);
         wait_mma();
-        if (sample_thread) {
-            tc::tmem_ld32(trow, v);
+        {
+            float q[16];
+            const int c0 = hs * 16;
+            tc::tmem_ld16(trow + c0, q);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) { v[j] = fmaxf(v[j] + w.b1[j], 0.f); m1 |= (v[j] > 0.f ? 1u : 0u) << j; }
+            for (int j = 0; j < 16; ++j) { q[j] = fmaxf(q[j] + w.b1[c0 + j], 0.f); m1 |= (q[j] > 0.f ? 1u : 0u) << j; }
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) st4(row + WG::A1 + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
-            tcm::put_row<H1>(ah, al, tid, v);
+            for (int j = 0; j < 16; j += 4) st4(row + WG::A1 + c0 + j, make_float4(q[j], q[j + 1], q[j + 2], q[j + 3]));
+            tcm::put_cols<16>(ah, al, srow, H1, c0, q);
         }
         sync_for_mma();
         if (tid == 0) tcm::issue_layer<H1, H2>(tmem, ah, al, w.w2h, w.w2l, &sh.bar);
         wait_mma();
-        if (sample_thread) {
-            float u[64];
-            tc::tmem_ld32(trow, v);
+        {
+            float q[32];
+            const int c0 = hs * 32;
+            tc::tmem_ld32(trow + c0, q);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) { u[j] = fmaxf(v[j] + w.b2[j], 0.f); m2a |= (u[j] > 0.f ? 1u : 0u) << j; }
-            tc::tmem_ld32(trow + 32, v);
+            for (int j = 0; j < 32; ++j) { q[j] = fmaxf(q[j] + w.b2[c0 + j], 0.f); m2 |= (q[j] > 0.f ? 1u : 0u) << j; }
 #pragma unroll
-            for (int j = 0; j < 32; ++j) { u[32 + j] = fmaxf(v[j] + w.b2[32 + j], 0.f); m2b |= (u[32 + j] > 0.f ? 1u : 0u) << j; }
-#pragma unroll
-            for (int j = 0; j < 64; j += 4) st4(row + WG::A2 + j, make_float4(u[j], u[j + 1], u[j + 2], u[j + 3]));
-            tcm::put_row<H2>(ah, al, tid, u);
+            for (int j = 0; j < 32; j += 4) st4(row + WG::A2 + c0 + j, make_float4(q[j], q[j + 1], q[j + 2], q[j + 3]));
+            tcm::put_cols<32>(ah, al, srow, H2, c0, q);
         }
         sync_for_mma();
         if (tid == 0) tcm::issue_layer<H2, H3>(tmem, ah, al, w.w3h, w.w3l, &sh.bar);
         wait_mma();
-        if (sample_thread) {
-            tc::tmem_ld32(trow, v);
+        {
+            float q[16];
+            const int c0 = hs * 16;
+            tc::tmem_ld16(trow + c0, q);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) { v[j] = fmaxf(v[j] + w.b3[j], 0.f); m3 |= (v[j] > 0.f ? 1u : 0u) << j; }
+            for (int j = 0; j < 16; ++j) { q[j] = fmaxf(q[j] + w.b3[c0 + j], 0.f); m3 |= (q[j] > 0.f ? 1u : 0u) << j; }
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) st4(row + WG::A3 + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
-            tcm::put_row<H3>(ah, al, tid, v);
+            for (int j = 0; j < 16; j += 4) st4(row + WG::A3 + c0 + j, make_float4(q[j], q[j + 1], q[j + 2], q[j + 3]));
+            tcm::put_cols<16>(ah, al, srow, H3, c0, q);
         }
         sync_for_mma();
         if (tid == 0) tcm::issue_layer<H3, tcm::OUTP>(tmem, ah, al, w.w4h, w.w4l, &sh.bar);
         wait_mma();
         if (sample_thread) {
-            tc::tmem_ld32(trow, v);      // columns >= 16 hold stale data of layer 3 and are ignored
+            float q[16];
+            tc::tmem_ld16(trow, q);
             // ---- loss epilogue -> dz (an unselected row keeps dz = 0: every gradient term of it vanishes)
             float dz[tcm::OUTP];
 #pragma unroll
             for (int j = 0; j < tcm::OUTP; ++j) dz[j] = 0.f;
             float d4[OP] = {0.f, 0.f, 0.f, 0.f};
-            if (sel) ppo_loss<HEAD>(la, s, make_float4(v[0] + w.b4[0], v[1] + w.b4[1], v[2] + w.b4[2], v[3] + w.b4[3]), d4, acc);
+            if (sel) ppo_loss<HEAD>(la, s, make_float4(q[0] + w.b4[0], q[1] + w.b4[1], q[2] + w.b4[2], q[3] + w.b4[3]), d4, acc);
 #pragma unroll
             for (int j = 0; j < OP; ++j) dz[j] = d4[j];
             st4(row + WG::D4, make_float4(d4[0], d4[1], d4[2], d4[3]));
-            tcm::put_row<tcm::OUTP>(ah, al, tid, dz);
+            tcm::put_row<tcm::OUTP>(ah, al, srow, dz);
         }
         sync_for_mma();
         // ---- layer 4: backward-data on the tensor core while the CUDA cores (all 8 warps) take dW4
@@ -150,13 +156,15 @@ __global__ void __launch_bounds__(kTcGradBlock, 1) k_ppo_grad_tc(SampleSet ss, c
         wg.layer4(rows, ROW, s0, HALF);
         __syncthreads();                                  // every a3 has been read before the deltas overwrite it
         wait_mma();
-        if (sample_thread) {
-            tc::tmem_ld32(trow, v);
+        {
+            float q[16];
+            const int c0 = hs * 16;
+            tc::tmem_ld16(trow + c0, q);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = ((m3 >> j) & 1u) ? v[j] : 0.f;             // delta3 = relu'(a3) * (dz W4)
+            for (int j = 0; j < 16; ++j) q[j] = ((m3 >> j) & 1u) ? q[j] : 0.f;             // delta3 = relu'(a3) * (dz W4)
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) st4(row + WG::A3 + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
-            tcm::put_row<H3>(ah, al, tid, v);
+            for (int j = 0; j < 16; j += 4) st4(row + WG::A3 + c0 + j, make_float4(q[j], q[j + 1], q[j + 2], q[j + 3]));
+            tcm::put_cols<16>(ah, al, srow, H3, c0, q);
         }
         sync_for_mma();
         // ---- layer 3
@@ -164,17 +172,15 @@ __global__ void __launch_bounds__(kTcGradBlock, 1) k_ppo_grad_tc(SampleSet ss, c
         wg.layer3(rows, ROW, s0, HALF);
         __syncthreads();
         wait_mma();
-        if (sample_thread) {
-            float u[64];
-            tc::tmem_ld32(trow, v);
+        {
+            float q[32];
+            const int c0 = hs * 32;
+            tc::tmem_ld32(trow + c0, q);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) u[j] = ((m2a >> j) & 1u) ? v[j] : 0.f;
-            tc::tmem_ld32(trow + 32, v);
+            for (int j = 0; j < 32; ++j) q[j] = ((m2 >> j) & 1u) ? q[j] : 0.f;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) u[32 + j] = ((m2b >> j) & 1u) ? v[j] : 0.f;
-#pragma unroll
-            for (int j = 0; j < 64; j += 4) st4(row + WG::A2 + j, make_float4(u[j], u[j + 1], u[j + 2], u[j + 3]));
-            tcm::put_row<H2>(ah, al, tid, u);
+            for (int j = 0; j < 32; j += 4) st4(row + WG::A2 + c0 + j, make_float4(q[j], q[j + 1], q[j + 2], q[j + 3]));
+            tcm::put_cols<32>(ah, al, srow, H2, c0, q);
         }
         sync_for_mma();
         // ---- layer 2
@@ -182,12 +188,14 @@ __global__ void __launch_bounds__(kTcGradBlock, 1) k_ppo_grad_tc(SampleSet ss, c
         wg.layer2(rows, ROW, s0, HALF);
         __syncthreads();
         wait_mma();
-        if (sample_thread) {
-            tc::tmem_ld32(trow, v);
+        {
+            float q[16];
+            const int c0 = hs * 16;
+            tc::tmem_ld16(trow + c0, q);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = ((m1 >> j) & 1u) ? v[j] : 0.f;
+            for (int j = 0; j < 16; ++j) q[j] = ((m1 >> j) & 1u) ? q[j] : 0.f;
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) st4(row + WG::A1 + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+            for (int j = 0; j < 16; j += 4) st4(row + WG::A1 + c0 + j, make_float4(q[j], q[j + 1], q[j + 2], q[j + 3]));
         }
         tc::fence_before();
         __syncthreads();                                  // deltas visible; TMEM reads done before the next tile's MMAs

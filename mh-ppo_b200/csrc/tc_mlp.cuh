@@ -61,6 +61,20 @@ __device__ __forceinline__ void put_row(float *hi, float *lo, int row, const flo
     }
 }
 
+// NC consecutive columns [col0, col0 + NC) of this thread's row of a [128 x K] operand tile pair
+template <int NC>
+__device__ __forceinline__ void put_cols(float *hi, float *lo, int row, int K, int col0, const float *v) {
+    const int base = (row >> 3) * (K * 8) + (row & 7) * 4 + (col0 >> 2) * 32;
+#pragma unroll
+    for (int c = 0; c < NC / 4; ++c) {
+        float4 h, l;
+        h.x = hi_part(v[4 * c + 0]); h.y = hi_part(v[4 * c + 1]); h.z = hi_part(v[4 * c + 2]); h.w = hi_part(v[4 * c + 3]);
+        l.x = v[4 * c + 0] - h.x; l.y = v[4 * c + 1] - h.y; l.z = v[4 * c + 2] - h.z; l.w = v[4 * c + 3] - h.w;
+        *reinterpret_cast<float4 *>(hi + base + c * 32) = h;
+        *reinterpret_cast<float4 *>(lo + base + c * 32) = l;
+    }
+}
+
 // one thread issues the 3xTF32 chains of a layer and commits them to `bar`
 template <int K, int J>
 __device__ __forceinline__ void issue_layer(uint32_t d_tmem, const float *ah, const float *al, const float *bh, const float *bl, uint64_t *bar) {
