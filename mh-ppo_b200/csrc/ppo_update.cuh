@@ -192,6 +192,10 @@ __device__ __forceinline__ void dense_bwd_t(float *ain_din, const float *dout, i
     }
 }
 
+#ifndef MH_WGRAD_UNROLL_N
+#define MH_WGRAD_UNROLL_N 2
+#endif
+constexpr int MH_WGRAD_UNROLL = MH_WGRAD_UNROLL_N;      // rows in flight per thread in the weight-gradient loops
 // weight-gradient register tile: acc[kk][j] += in[s][k0 + kk] * delta[s][j0 + j] over the rows [s0, s0 + ns) of the tile
 template <int TJ>
 __device__ __forceinline__ void wgrad_tile(float (&acc)[4][TJ], const float *__restrict__ rows, int row, int in_off, int dl_off, int s0, int ns) {
@@ -294,6 +298,7 @@ struct WgradAcc {
     }
     // layer 4: dW4t[k][j], b4[j] from (a3, dz) of the rows [s0, s0 + ns)
     __device__ __forceinline__ void layer4(const float *__restrict__ rows, int row, int s0, int ns) {
+#pragma unroll 4
         for (int s = s0; s < s0 + ns; ++s) {
             const float *r = rows + (size_t)s * row;
             const float a = r[A3 + k4];
@@ -307,6 +312,7 @@ struct WgradAcc {
     // layer 1 and the bias gradients b1 | b2 | b3 (the deltas sit in a1, a2, a3 of every row: 128 consecutive columns)
     __device__ __forceinline__ void layer1_and_biases(const float *__restrict__ rows, int row, int s0, int ns) {
         if (l1_on) wgrad_tile<TJ1>(g1, rows, row, X + k1, A1 + j1, s0, ns);
+#pragma unroll 4
         for (int s = s0; s < s0 + ns; ++s) {
             const float2 d = *reinterpret_cast<const float2 *>(rows + (size_t)s * row + A1 + 2 * lt);
             gbias[0] += d.x; gbias[1] += d.y;

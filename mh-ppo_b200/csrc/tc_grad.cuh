@@ -2,15 +2,14 @@
 // backward-data on the 5th-generation tensor cores (13-input nets: cross / wait actors and critics).
 //
 // Same contract as k_ppo_grad<16, HEAD> (ppo_update.cuh), which stays as the exact-fp32 cross-check and serves the wider
-// choice nets.  One persistent 256-thread CTA per SM walks 128-sample tiles; in warps 0-3 thread = sample = TMEM lane.
+// choice nets.  One persistent 384-thread CTA per SM walks 128-sample tiles; in warps 0-3 thread = sample = TMEM lane.
 //   forward       D[128 x J] = A[128 x K] * W[J x K]^T         (tc_mlp.cuh: 3xTF32, hi/lo operand tiles, fp32 in TMEM)
 //   backward-data dIn[128 x K] = delta[128 x J] * W[J x K]     = the same MMA shapes with B = the FLAT transposed weights
 //                 Wt[k][j] read as an [N = K rows][reduction = J] K-major tile (BwdTiles)
 //   weight grad   dWt[k][j] += sum_s in[s][k] * delta[s][j]    FFMA register tiles (WgradAcc) on fp32 rows in shared memory:
 //                 the reduction runs over samples, which a tf32 MMA could only read from 128B-swizzled MN-major tiles
-//                 (tc.cuh); it is instead OVERLAPPED with the tensor core: the backward-data MMAs of layer l are issued,
-//                 the CUDA cores accumulate the weight gradient of layer l while they run, then the epilogue turns the
-//                 accumulator into delta_{l-1} (ReLU mask kept in registers from the forward pass).
+//                 (tc.cuh); it runs on eight dedicated warps CONCURRENTLY with the chain of backward-data MMAs and their
+//                 epilogues (ReLU masks kept in registers from the forward pass) on the other four.
 // Every epilogue writes its row twice: fp32 into the row buffer (weight gradient) and hi/lo into the next A operand tile.
 #pragma once
 #include "ppo_update.cuh"
@@ -43,13 +42,23 @@ constexpr int kTcGradRow = 16 + H1 + H2 + H3 + OP;       // 148 floats: 16-byte 
 constexpr int kTcGradNetFloats = (tcm::NetTiles<16>::FLOATS + 255) & ~255;
 constexpr size_t kTcGradSmemFloats = (size_t)kTcGradNetFloats + BwdTiles::FLOATS + 2 * 128 * H2 + (size_t)128 * kTcGradRow;
 
-constexpr int kTcGradBlock = 256;      // warps 0-3: thread = sample (MMA issue, epilogues); all 8 warps: weight-gradient tiles
+// Warp-specialised CTA: warps 0-3 ("E", thread = sample = TMEM lane) issue the MMAs and run the epilogues; warps 4-11 ("W")
+// only accumulate the weight gradient.  The two groups hand the row buffer back and forth through named barriers:
+//   R_l (E -> W): the rows now hold what the weight gradient of layer l needs;  F_l (W -> E): layer l has been read, its
+//   input-activation columns may be overwritten by the delta of the layer below.
+// E keeps a freshly computed delta in registers, feeds it to the tensor core through the A tile at once, and stores it into
+// the rows only when W releases them, so the chain of backward-data MMAs runs ahead of the (longer) weight-gradient chain.
+constexpr int kTcGradE = 128, kTcGradW = 256, kTcGradBlock = kTcGradE + kTcGradW;
+enum { BAR_E = 1, BAR_W = 10, BAR_R4 = 2, BAR_F4 = 3, BAR_R3 = 4, BAR_F3 = 5, BAR_R2 = 6, BAR_F2 = 7, BAR_R1 = 8, BAR_F1 = 9 };
+__device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int n) { __threadfence_block(); asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
 template <int HEAD>
 __global__ void __launch_bounds__(kTcGradBlock, 1) k_ppo_grad_tc(SampleSet ss, const float *__restrict__ net, LossArgs la,
                                                               float *__restrict__ gpartial, double *__restrict__ lpartial,
                                                               int *__restrict__ fail_flag) {
-    constexpr int KP = 16, ROW = kTcGradRow;
-    typedef WgradAcc<KP, kTcGradBlock / 64> WG;
+    constexpr int KP = 16, ROW = kTcGradRow, NG = kTcGradW / 64, NT = kTcGradBlock;
+    typedef WgradAcc<KP, NG> WG;
     extern __shared__ __align__(1024) float smem[];
     __shared__ TcShared sh;
     __shared__ double red[kTcGradBlock / 32];
@@ -60,153 +69,184 @@ __global__ void __launch_bounds__(kTcGradBlock, 1) k_ppo_grad_tc(SampleSet ss, c
     float *ah = smem + kTcGradNetFloats + BwdTiles::FLOATS, *al = ah + 128 * H2, *rows = al + 128 * H2;
     w.stage(net);
     bw.stage<KP>(net);
-    const uint32_t tmem = tc_prologue(&sh);
+    // TMEM: forward accumulators in columns 0-63; each backward layer has its own columns, so a delta can be read a second time
+    // (for the deferred row store) after the next MMA has been issued: layer 4 -> 64..95, layer 2 -> 96..127, layer 3 -> 128..191
+    constexpr uint32_t kCols = 256, C4 = 64, C2 = 96, C3 = 128;
+    if (threadIdx.x == 0) { tc::mbar_init(&sh.bar, 1); sh.fail = 0; }
+    if ((threadIdx.x >> 5) == 0) tc::tmem_alloc(&sh.tmem_base, kCols);
+    tc::fence_async_smem(); tc::fence_before(); __syncthreads(); tc::fence_after();
+    const uint32_t tmem = sh.tmem_base;
     const int tid = threadIdx.x;
-    const int srow = tid & 127;                           // the sample (tile row, TMEM lane) this thread works on in the epilogues
-    const uint32_t trow = tmem + ((uint32_t)(((tid >> 5) & 3) * 32) << 16);
-    uint32_t phase = 0;
-    bool ok = true;
-    auto sync_for_mma = [&]() { tc::fence_async_smem(); tc::fence_before(); __syncthreads(); tc::fence_after(); };
-    auto wait_mma = [&]() { ok &= tc::mbar_wait(&sh.bar, phase); phase ^= 1; tc::fence_after(); };
-
-    float *row = rows + (size_t)srow * ROW;
-    WG wg;
-    wg.init(tid);
-    constexpr int HALF = 128 / (kTcGradBlock / 64);     // rows per weight-gradient group
-    const int s0 = wg.half * HALF;
-    const bool sample_thread = tid < 128;
+    const bool is_e = tid < kTcGradE;
     LossAcc acc;
+    bool ok = true;
+    const int64_t tile0 = (int64_t)blockIdx.x * 128, tstep = (int64_t)gridDim.x * 128;
 
-    // Epilogues: the two threads t and t + 128 share sample t (a warp reads the TMEM lanes of quadrant warp % 4, so warps
-    // w and w + 4 see the same rows); each takes half of the layer's columns: load, bias / ReLU (or mask), fp32 row, hi/lo tile.
-    const int hs = tid >> 7;                              // which half of the columns
-    for (int64_t base = (int64_t)blockIdx.x * 128; base < ss.Q; base += (int64_t)gridDim.x * 128) {
-        int64_t s = 0;
-        bool sel = false;
-        uint32_t m1 = 0, m2 = 0, m3 = 0;                  // ReLU masks of this thread's columns of the three hidden layers
-        if (sample_thread) {
+    if (!is_e) {
+        // ================= W: weight gradient of every layer, layer 4 first =================
+        WG wg;
+        wg.init(tid - kTcGradE);
+        constexpr int PART = 128 / NG;                    // rows per group
+        const int s0 = wg.half * PART;
+        for (int64_t base = tile0; base < ss.Q; base += tstep) {
+            bar_sync(BAR_R4, NT);  wg.layer4(rows, ROW, s0, PART);             bar_arrive(BAR_F4, NT);
+            bar_sync(BAR_R3, NT);  wg.layer3(rows, ROW, s0, PART);             bar_arrive(BAR_F3, NT);
+            bar_sync(BAR_R2, NT);  wg.layer2(rows, ROW, s0, PART);             bar_arrive(BAR_F2, NT);
+            bar_sync(BAR_R1, NT);  wg.layer1_and_biases(rows, ROW, s0, PART);  bar_arrive(BAR_F1, NT);
+        }
+        // add the groups in the (now dead) row buffer, fixed order: deterministic
+        bar_sync(BAR_W, kTcGradW);
+#pragma unroll 1
+        for (int g = 0; g < NG; ++g) {
+            if (wg.half == g) wg.emit(rows, g > 0);
+            bar_sync(BAR_W, kTcGradW);
+        }
+    } else {
+        // ================= E: MMA issue + epilogues =================
+        const uint32_t trow = tmem + ((uint32_t)((tid >> 5) * 32) << 16);
+        uint32_t phase = 0;
+        float *row = rows + (size_t)tid * ROW;
+        auto sync_for_mma = [&]() { tc::fence_async_smem(); tc::fence_before(); bar_sync(BAR_E, kTcGradE); tc::fence_after(); };
+        auto wait_mma = [&]() { ok &= tc::mbar_wait(&sh.bar, phase); phase ^= 1; tc::fence_after(); };
+        auto fetch = [&](int64_t base, float (&x)[KP], bool &sel, int64_t &s) {
+            s = 0;
             sel = map_sample(ss, base + tid, s);
-            float x[KP];
 #pragma unroll
             for (int k = 0; k < KP; ++k) x[k] = (sel && k < ss.D) ? ss.x[(int64_t)k * ss.S + s] : 0.f;
+        };
+        float xn[KP];
+        bool seln = false;
+        int64_t sn = 0;
+        if (tile0 < ss.Q) fetch(tile0, xn, seln, sn);
+        bool first = true;
+        for (int64_t base = tile0; base < ss.Q; base += tstep) {
+            const bool sel = seln;
+            const int64_t s = sn;
+            float v[32];
+            uint32_t m1 = 0, m2a = 0, m2b = 0, m3 = 0;                // ReLU masks of the three hidden layers
+            // ---- forward.  The rows still belong to W (layer 1 + biases of the previous tile) until F1.
+            tcm::put_row<KP>(ah, al, tid, xn);
+            sync_for_mma();
+            if (tid == 0) tcm::issue_layer<KP, H1>(tmem, ah, al, w.w1h, w.w1l, &sh.bar);
+            if (!first) bar_sync(BAR_F1, NT);
+            first = false;
 #pragma unroll
-            for (int k = 0; k < KP; k += 4) st4(row + WG::X + k, make_float4(x[k], x[k + 1], x[k + 2], x[k + 3]));
-            tcm::put_row<KP>(ah, al, srow, x);
+            for (int k = 0; k < KP; k += 4) st4(row + WG::X + k, make_float4(xn[k], xn[k + 1], xn[k + 2], xn[k + 3]));
+            wait_mma();
+            tc::tmem_ld32(trow, v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { v[j] = fmaxf(v[j] + w.b1[j], 0.f); m1 |= (v[j] > 0.f ? 1u : 0u) << j; }
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) st4(row + WG::A1 + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+            tcm::put_row<H1>(ah, al, tid, v);
+            sync_for_mma();
+            if (tid == 0) tcm::issue_layer<H1, H2>(tmem, ah, al, w.w2h, w.w2l, &sh.bar);
+            wait_mma();
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                tc::tmem_ld32(trow + 32 * h, v);
+                uint32_t m = 0;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) { v[j] = fmaxf(v[j] + w.b2[32 * h + j], 0.f); m |= (v[j] > 0.f ? 1u : 0u) << j; }
+                if (h) m2b = m; else m2a = m;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) st4(row + WG::A2 + 32 * h + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+                tcm::put_cols<32>(ah, al, tid, H2, 32 * h, v);
+            }
+            sync_for_mma();
+            if (tid == 0) tcm::issue_layer<H2, H3>(tmem, ah, al, w.w3h, w.w3l, &sh.bar);
+            wait_mma();
+            tc::tmem_ld32(trow, v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { v[j] = fmaxf(v[j] + w.b3[j], 0.f); m3 |= (v[j] > 0.f ? 1u : 0u) << j; }
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) st4(row + WG::A3 + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+            tcm::put_row<H3>(ah, al, tid, v);
+            sync_for_mma();
+            if (tid == 0) tcm::issue_layer<H3, tcm::OUTP>(tmem, ah, al, w.w4h, w.w4l, &sh.bar);
+            wait_mma();
+            {
+                float q[16];
+                tc::tmem_ld16(trow, q);
+                // ---- loss epilogue -> dz (an unselected row keeps dz = 0: every gradient term of it vanishes)
+                float dz[tcm::OUTP];
+#pragma unroll
+                for (int j = 0; j < tcm::OUTP; ++j) dz[j] = 0.f;
+                float d4[OP] = {0.f, 0.f, 0.f, 0.f};
+                if (sel) ppo_loss<HEAD>(la, s, make_float4(q[0] + w.b4[0], q[1] + w.b4[1], q[2] + w.b4[2], q[3] + w.b4[3]), d4, acc);
+#pragma unroll
+                for (int j = 0; j < OP; ++j) dz[j] = d4[j];
+                st4(row + WG::D4, make_float4(d4[0], d4[1], d4[2], d4[3]));
+                tcm::put_row<tcm::OUTP>(ah, al, tid, dz);
+            }
+            sync_for_mma();
+            // ---- layer 4: backward-data on the tensor core, dW4 on W
+            if (tid == 0) tcm::issue_layer<tcm::OUTP, H3>(tmem + C4, ah, al, bw.w4h, bw.w4l, &sh.bar);
+            bar_arrive(BAR_R4, NT);                           // a3 and dz are in the rows
+            // the next tile's features travel from HBM while the backward chain runs
+            if (base + tstep < ss.Q) fetch(base + tstep, xn, seln, sn);
+            wait_mma();
+            tc::tmem_ld32(trow + C4, v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = ((m3 >> j) & 1u) ? v[j] : 0.f;                 // delta3 = relu'(a3) * (dz W4)
+            tcm::put_row<H3>(ah, al, tid, v);
+            sync_for_mma();
+            if (tid == 0) tcm::issue_layer<H3, H2>(tmem + C3, ah, al, bw.w3h, bw.w3l, &sh.bar);
+            bar_sync(BAR_F4, NT);                             // a3 has been read
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) st4(row + WG::A3 + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+            bar_arrive(BAR_R3, NT);                           // delta3 is in the rows
+            // ---- layer 3: the 64 deltas go to the A tile now and are read from TMEM once more for the rows
+            wait_mma();
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                tc::tmem_ld32(trow + C3 + 32 * h, v);
+                const uint32_t m = h ? m2b : m2a;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = ((m >> j) & 1u) ? v[j] : 0.f;
+                tcm::put_cols<32>(ah, al, tid, H2, 32 * h, v);
+            }
+            sync_for_mma();
+            if (tid == 0) tcm::issue_layer<H2, H1>(tmem + C2, ah, al, bw.w2h, bw.w2l, &sh.bar);
+            bar_sync(BAR_F3, NT);                             // a2 has been read
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                tc::tmem_ld32(trow + C3 + 32 * h, v);
+                const uint32_t m = h ? m2b : m2a;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    st4(row + WG::A2 + 32 * h + j, make_float4(((m >> j) & 1u) ? v[j] : 0.f, ((m >> (j + 1)) & 1u) ? v[j + 1] : 0.f,
+                                                               ((m >> (j + 2)) & 1u) ? v[j + 2] : 0.f, ((m >> (j + 3)) & 1u) ? v[j + 3] : 0.f));
+            }
+            bar_arrive(BAR_R2, NT);                           // delta2 is in the rows
+            // ---- layer 2
+            wait_mma();
+            tc::tmem_ld32(trow + C2, v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = ((m1 >> j) & 1u) ? v[j] : 0.f;
+            tc::fence_before();                               // TMEM reads are done before the next tile's MMAs (sync_for_mma follows)
+            bar_sync(BAR_F2, NT);                             // a1 has been read
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) st4(row + WG::A1 + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+            bar_arrive(BAR_R1, NT);                           // delta1 is in the rows: layer 1 and the biases
         }
-        sync_for_mma();
-        // ---- forward
-        if (tid == 0) tcm::issue_layer<KP, H1>(tmem, ah, al, w.w1h, w.w1l, &sh.bar);
-        wait_mma();
-        {
-            float q[16];
-            const int c0 = hs * 16;
-            tc::tmem_ld16(trow + c0, q);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) { q[j] = fmaxf(q[j] + w.b1[c0 + j], 0.f); m1 |= (q[j] > 0.f ? 1u : 0u) << j; }
-#pragma unroll
-            for (int j = 0; j < 16; j += 4) st4(row + WG::A1 + c0 + j, make_float4(q[j], q[j + 1], q[j + 2], q[j + 3]));
-            tcm::put_cols<16>(ah, al, srow, H1, c0, q);
-        }
-        sync_for_mma();
-        if (tid == 0) tcm::issue_layer<H1, H2>(tmem, ah, al, w.w2h, w.w2l, &sh.bar);
-        wait_mma();
-        {
-            float q[32];
-            const int c0 = hs * 32;
-            tc::tmem_ld32(trow + c0, q);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) { q[j] = fmaxf(q[j] + w.b2[c0 + j], 0.f); m2 |= (q[j] > 0.f ? 1u : 0u) << j; }
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) st4(row + WG::A2 + c0 + j, make_float4(q[j], q[j + 1], q[j + 2], q[j + 3]));
-            tcm::put_cols<32>(ah, al, srow, H2, c0, q);
-        }
-        sync_for_mma();
-        if (tid == 0) tcm::issue_layer<H2, H3>(tmem, ah, al, w.w3h, w.w3l, &sh.bar);
-        wait_mma();
-        {
-            float q[16];
-            const int c0 = hs * 16;
-            tc::tmem_ld16(trow + c0, q);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) { q[j] = fmaxf(q[j] + w.b3[c0 + j], 0.f); m3 |= (q[j] > 0.f ? 1u : 0u) << j; }
-#pragma unroll
-            for (int j = 0; j < 16; j += 4) st4(row + WG::A3 + c0 + j, make_float4(q[j], q[j + 1], q[j + 2], q[j + 3]));
-            tcm::put_cols<16>(ah, al, srow, H3, c0, q);
-        }
-        sync_for_mma();
-        if (tid == 0) tcm::issue_layer<H3, tcm::OUTP>(tmem, ah, al, w.w4h, w.w4l, &sh.bar);
-        wait_mma();
-        if (sample_thread) {
-            float q[16];
-            tc::tmem_ld16(trow, q);
-            // ---- loss epilogue -> dz (an unselected row keeps dz = 0: every gradient term of it vanishes)
-            float dz[tcm::OUTP];
-#pragma unroll
-            for (int j = 0; j < tcm::OUTP; ++j) dz[j] = 0.f;
-            float d4[OP] = {0.f, 0.f, 0.f, 0.f};
-            if (sel) ppo_loss<HEAD>(la, s, make_float4(q[0] + w.b4[0], q[1] + w.b4[1], q[2] + w.b4[2], q[3] + w.b4[3]), d4, acc);
-#pragma unroll
-            for (int j = 0; j < OP; ++j) dz[j] = d4[j];
-            st4(row + WG::D4, make_float4(d4[0], d4[1], d4[2], d4[3]));
-            tcm::put_row<tcm::OUTP>(ah, al, srow, dz);
-        }
-        sync_for_mma();
-        // ---- layer 4: backward-data on the tensor core while the CUDA cores (all 8 warps) take dW4
-        if (tid == 0) tcm::issue_layer<tcm::OUTP, H3>(tmem, ah, al, bw.w4h, bw.w4l, &sh.bar);
-        wg.layer4(rows, ROW, s0, HALF);
-        __syncthreads();                                  // every a3 has been read before the deltas overwrite it
-        wait_mma();
-        {
-            float q[16];
-            const int c0 = hs * 16;
-            tc::tmem_ld16(trow + c0, q);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) q[j] = ((m3 >> j) & 1u) ? q[j] : 0.f;             // delta3 = relu'(a3) * (dz W4)
-#pragma unroll
-            for (int j = 0; j < 16; j += 4) st4(row + WG::A3 + c0 + j, make_float4(q[j], q[j + 1], q[j + 2], q[j + 3]));
-            tcm::put_cols<16>(ah, al, srow, H3, c0, q);
-        }
-        sync_for_mma();
-        // ---- layer 3
-        if (tid == 0) tcm::issue_layer<H3, H2>(tmem, ah, al, bw.w3h, bw.w3l, &sh.bar);
-        wg.layer3(rows, ROW, s0, HALF);
-        __syncthreads();
-        wait_mma();
-        {
-            float q[32];
-            const int c0 = hs * 32;
-            tc::tmem_ld32(trow + c0, q);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) q[j] = ((m2 >> j) & 1u) ? q[j] : 0.f;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) st4(row + WG::A2 + c0 + j, make_float4(q[j], q[j + 1], q[j + 2], q[j + 3]));
-            tcm::put_cols<32>(ah, al, srow, H2, c0, q);
-        }
-        sync_for_mma();
-        // ---- layer 2
-        if (tid == 0) tcm::issue_layer<H2, H1>(tmem, ah, al, bw.w2h, bw.w2l, &sh.bar);
-        wg.layer2(rows, ROW, s0, HALF);
-        __syncthreads();
-        wait_mma();
-        {
-            float q[16];
-            const int c0 = hs * 16;
-            tc::tmem_ld16(trow + c0, q);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) q[j] = ((m1 >> j) & 1u) ? q[j] : 0.f;
-#pragma unroll
-            for (int j = 0; j < 16; j += 4) st4(row + WG::A1 + c0 + j, make_float4(q[j], q[j + 1], q[j + 2], q[j + 3]));
-        }
-        tc::fence_before();
-        __syncthreads();                                  // deltas visible; TMEM reads done before the next tile's MMAs
-        tc::fence_after();
-        // ---- layer 1 and the biases
-        wg.layer1_and_biases(rows, ROW, s0, HALF);
-        __syncthreads();
+        if (!first) bar_sync(BAR_F1, NT);                     // the last tile's rows have been read
     }
+    // ================= emit the CTA's partials =================
     if (!ok) atomicExch(fail_flag, 1);
-    wg.template finish<HEAD>(rows, gpartial, lpartial, la, acc, red);
-    tc_epilogue(tmem);
+    __syncthreads();
+    constexpr int NPAR = net_params(KP);
+    float *gp = gpartial + (size_t)blockIdx.x * NPAR;
+    for (int i = tid; i < NPAR; i += NT) gp[i] = rows[i];
+    const double lsum = team_sum(acc.loss, red, tid, NT, 0);
+    if (tid == 0) lpartial[blockIdx.x] = lsum;
+    if (HEAD == 0 && la.spartial) {
+        const double t0 = team_sum(acc.sA, red, tid, NT, 0), t1 = team_sum(acc.sAA, red, tid, NT, 0), t2 = team_sum(acc.cnt, red, tid, NT, 0);
+        if (tid == 0) { la.spartial[blockIdx.x * 3 + 0] = t0; la.spartial[blockIdx.x * 3 + 1] = t1; la.spartial[blockIdx.x * 3 + 2] = t2; }
+    }
+    tc::fence_before();
+    __syncthreads();
+    if ((threadIdx.x >> 5) == 0) tc::tmem_dealloc(tmem, 256);
 }
 
 }  // namespace mhppo
