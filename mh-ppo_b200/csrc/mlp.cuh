@@ -10,12 +10,12 @@
 // input index and reads 4 output weights per 128-bit shared-memory broadcast; the input width is
 // zero-padded to KP (13 -> 16, 18/30 -> 32, 54 -> 56) and the output width to 4.
 //
-// Execution model of all MLP kernels here: one thread owns one sample; activations live in shared
+// Execution model of the FFMA kernels here: one thread owns one sample; activations live in shared
 // memory as [sample][feature] rows with an odd stride (conflict-free for lane = sample), weights
-// are staged once per CTA.  The 13..64-wide layers are far too small for a 128xN tcgen05 tile to pay
-// off without batching samples across the CTA -- that tensor-core formulation is the planned next
-// step (DESIGN.md "Next"); this version is exact fp32 FFMA, which is what the 1e-5 loss parity
-// bar (north_star) is checked with.
+// are staged once per CTA.  These are the exact-fp32 kernels (the 1e-5 loss-parity bar is checked
+// with them, MHPPO_MLP=ffma) and they serve the wider choice nets and the rollout inference; the
+// 13-input nets of the update run on the tensor cores by default (tc_mlp.cuh, tc_grad.cuh), batching
+// 128 samples per CTA tile.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
