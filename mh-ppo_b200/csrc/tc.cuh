@@ -55,10 +55,15 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
                  : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     return ok != 0;
 }
-// bounded spin: a wrong descriptor must not hang the GPU; returns false on timeout
+// bounded wait: a wrong descriptor must not hang the GPU; returns false on timeout.  The poll backs off with nanosleep:
+// in the warp-specialised update kernel the waiting warps share their schedulers with the weight-gradient warps, and a
+// hot try_wait loop took more than half of their issue slots (weight-gradient chain 2.4x slower, measured).
 __device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity) {
-    for (uint32_t spin = 0; spin < (1u << 24); ++spin)
+    if (mbar_try_wait(bar, parity)) return true;
+    for (uint32_t spin = 0; spin < (1u << 22); ++spin) {
+        __nanosleep(40);
         if (mbar_try_wait(bar, parity)) return true;
+    }
     return false;
 }
 // D[tmem] (+)= A[smem] * B[smem]^T, issued by ONE thread
