@@ -116,7 +116,8 @@ int mhppo_policy_act(const mhppo_rollout_cfg *cfg, const float *obs, const float
     ActIO io; io.obs = obs; io.action_d = action_d; io.light = light; io.actions = actions; io.obs_c = obs_c; io.act = act;
     io.logp = logp; io.t = t; io.T = cfg->T; io.iteration = iteration;
     if (use_tc(true)) {
-        const dim3 g2((unsigned)((d.N + 127) / 128), (unsigned)d.C);
+        const int64_t items = ((d.N + 127) / 128) * d.C;
+        const unsigned g2 = (unsigned)(items < 148 ? items : 148);       // persistent: one CTA per SM walks the (env block, car) items
         SET_SMEM(k_policy_act_tc, smem_tc(2));
         k_policy_act_tc<<<g2, 128, smem_tc(2), (cudaStream_t)stream>>>(d, net_cross, net_wait, io, fail_flag());
         api_count_launch();

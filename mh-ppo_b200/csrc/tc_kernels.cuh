@@ -85,10 +85,13 @@ __global__ void __launch_bounds__(128) k_policy_act_tc(RolloutDims d, const floa
     const uint32_t tmem = tc_prologue(&sh);
     uint32_t phase = 0;
     bool ok = true;
-    const int64_t n = (int64_t)blockIdx.x * 128 + threadIdx.x;
+    // persistent CTA: the two nets are staged once and the CTA walks (env block, car) work items
+    const int64_t nblk = (d.N + 127) / 128;
+    for (int64_t item = blockIdx.x; item < nblk * d.C; item += gridDim.x) {
+    const int64_t n = (item % nblk) * 128 + threadIdx.x;
     const bool live = n < d.N;
     const int64_t nn = live ? n : d.N - 1;
-    const int i = blockIdx.y;
+    const int i = (int)(item / nblk);
     const ObsView v{io.obs, d.N, nn, 7 * d.C + 4, 7 * d.C};
     float mean = 2.0f;                                   // car_b[1,0], PY:436
     float st[13], x[KP];
@@ -120,7 +123,6 @@ __global__ void __launch_bounds__(128) k_policy_act_tc(RolloutDims d, const floa
             }
         }
     }
-    if (!ok) atomicExch(fail_flag, 1);
     if (live) {
         const PhiloxBlock b = policy_block(d, n, (uint32_t)(io.t * d.C + i), 1u | (io.iteration << 8));
         const double z = sqrt(-2.0 * log(1.0 - u53(b.w0, b.w1))) * cos(2.0 * 3.141592653589793 * u53(b.w2, b.w3));
@@ -133,6 +135,8 @@ __global__ void __launch_bounds__(128) k_policy_act_tc(RolloutDims d, const floa
         for (int k = 0; k < 13; ++k) io.obs_c[(int64_t)k * S + s] = st[k];
         io.act[s] = a; io.logp[s] = lp;
     }
+    }
+    if (!ok) atomicExch(fail_flag, 1);
     tc_epilogue(tmem);
 }
 
