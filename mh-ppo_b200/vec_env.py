@@ -178,6 +178,25 @@ class VecCrosswalkEnv:
                                              self._stream()))
         torch.cuda.current_stream(dev).synchronize()   # `t` must outlive the kernel
 
+    # -- scenario snapshots (the reference pickles copy.deepcopy(env) per scenario, PY:255-277, 1873-1883) ----------
+    def save_state(self, path):
+        """Write the canonical state dump of every env (include/mhppo.h "state dump") plus the constructor arguments to
+        one .npz file: the flat struct-of-arrays counterpart of the reference's pickled env lists."""
+        s = {k: v.cpu().numpy() for k, v in self.get_state().items()}
+        np.savez_compressed(path, variant=self.variant, nb_car=self.nb_car, nb_ped=self.nb_ped, nb_lines=self.nb_lines,
+                            n_envs=self.n_envs, dt=self.dt, max_episode=self.max_episode, seed=self._seed, env_id0=self._env_id0,
+                            car_b=self.car_b, ped_b=self.ped_b, cross_b=self.cross_b, **s)
+
+    def load_state(self, path):
+        """Restore a snapshot written by save_state into this (same-shaped) env set; returns the current observation."""
+        z = np.load(path)
+        for k in ("nb_car", "nb_ped", "nb_lines", "n_envs"):
+            if int(z[k]) != getattr(self, k):
+                raise ValueError("snapshot %s=%d does not match this env (%d)" % (k, int(z[k]), getattr(self, k)))
+        if str(z["variant"]) != self.variant:
+            raise ValueError("snapshot is of env class %s, this is %s" % (z["variant"], self.variant))
+        self.set_state({k: z[k] for k in ("car_f", "car_i", "ped_f", "ped_i", "env_f", "env_i")})
+
     @property
     def car_exist(self):
         return self.get_state()["car_i"][:, :, 1].bool()

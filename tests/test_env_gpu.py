@@ -198,3 +198,28 @@ def test_full_size_properties(oracle_mod, cuda_env_cls, cfg, N):
     for a, b in zip(*runs):
         for x, y in zip(a, b):
             assert_equal("determinism", x, y)
+
+
+def test_snapshot_file_roundtrip(tmp_path):
+    """save_state / load_state: an env set restored from a snapshot file continues bit-identically (scenario datasets)."""
+    import mhppo_b200
+    N = 257
+    a = mhppo_b200.VecCrosswalkEnv("coop_scalable", N, nb_car=4, nb_ped=3, nb_lines=2, seed=11, env_id0=40)
+    a.reset()
+    rng = np.random.default_rng(1)
+    for t in range(23):
+        a.step(torch.as_tensor(random_actions(rng, N, a.n_action)).cuda())
+    a.save_state(str(tmp_path / "snap.npz"))
+    b = mhppo_b200.VecCrosswalkEnv("coop_scalable", N, nb_car=4, nb_ped=3, nb_lines=2, seed=11, env_id0=40)
+    b.reset()
+    b.load_state(str(tmp_path / "snap.npz"))
+    for t in range(70):
+        act = torch.as_tensor(random_actions(rng, N, a.n_action)).cuda()
+        oa, ra, da, _, _ = a.step(act)
+        ob, rb, db, _, _ = b.step(act)
+        for k in oa:
+            assert torch.equal(oa[k], ob[k]), (t, k)
+        assert torch.equal(ra, rb) and torch.equal(da, db)
+    c = mhppo_b200.VecCrosswalkEnv("coop", N, nb_car=2, nb_ped=1, nb_lines=2, seed=11)
+    with pytest.raises(ValueError):
+        c.load_state(str(tmp_path / "snap.npz"))
