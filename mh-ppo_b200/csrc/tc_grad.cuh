@@ -4,6 +4,7 @@
 // Same contract as k_ppo_grad<16, HEAD> (ppo_update.cuh), which stays as the exact-fp32 cross-check and serves the wider
 // choice nets.  One persistent 384-thread CTA per SM walks 128-sample tiles; in warps 0-3 thread = sample = TMEM lane.
 //   forward       D[128 x J] = A[128 x K] * W[J x K]^T         (tc_mlp.cuh: 3xTF32, hi/lo operand tiles, fp32 in TMEM)
+//   (layers 1-3; the 32 -> 4 output layer and its backward-data are 2 x 128 FFMAs per sample on the CUDA cores)
 //   backward-data dIn[128 x K] = delta[128 x J] * W[J x K]     = the same MMA shapes with B = the FLAT transposed weights
 //                 Wt[k][j] read as an [N = K rows][reduction = J] K-major tile (BwdTiles)
 //   weight grad   dWt[k][j] += sum_s in[s][k] * delta[s][j]    FFMA register tiles (WgradAcc) on fp32 rows in shared memory:
@@ -62,6 +63,7 @@ __global__ void __launch_bounds__(kTcGradBlock, 1) k_ppo_grad_tc(SampleSet ss, c
     extern __shared__ __align__(1024) float smem[];
     __shared__ TcShared sh;
     __shared__ double red[kTcGradBlock / 32];
+    __shared__ __align__(16) float w4f[H3 * OP + OP];             // Wt4[k][j] and b4, fp32 (layer 4 runs on the CUDA cores)
     tcm::NetTiles<KP> w;
     BwdTiles bw;
     w.carve(smem);
@@ -69,6 +71,7 @@ __global__ void __launch_bounds__(kTcGradBlock, 1) k_ppo_grad_tc(SampleSet ss, c
     float *ah = smem + kTcGradNetFloats + BwdTiles::FLOATS, *al = ah + 128 * H2, *rows = al + 128 * H2;
     w.stage(net);
     bw.stage<KP>(net);
+    for (int i = threadIdx.x; i < H3 * OP + OP; i += blockDim.x) w4f[i] = net[off_w4(KP) + i];      // W4t then b4 are contiguous in the flat layout
     // TMEM: forward accumulators in columns 0-63; each backward layer has its own columns, so a delta can be read a second time
     // (for the deferred row store) after the next MMA has been issued: layer 4 -> 64..95, layer 2 -> 96..127, layer 3 -> 128..191
     constexpr uint32_t kCols = 256, C4 = 64, C2 = 96, C3 = 128;
@@ -161,34 +164,29 @@ __global__ void __launch_bounds__(kTcGradBlock, 1) k_ppo_grad_tc(SampleSet ss, c
             for (int j = 0; j < 32; ++j) { v[j] = fmaxf(v[j] + w.b3[j], 0.f); m3 |= (v[j] > 0.f ? 1u : 0u) << j; }
 #pragma unroll
             for (int j = 0; j < 32; j += 4) st4(row + WG::A3 + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
-            tcm::put_row<H3>(ah, al, tid, v);
-            sync_for_mma();
-            if (tid == 0) tcm::issue_layer<H3, tcm::OUTP>(tmem, ah, al, w.w4h, w.w4l, &sh.bar);
-            wait_mma();
+            // ---- layer 4 (32 -> 4 outputs) and its backward-data stay on the CUDA cores: 2 x 128 FFMAs per sample from the
+            // registers that already hold a3, exact fp32, instead of two more dependent MMA round trips per tile
             {
-                float q[16];
-                tc::tmem_ld16(trow, q);
+                float o[OP] = {w4f[4 * H3 + 0], w4f[4 * H3 + 1], w4f[4 * H3 + 2], w4f[4 * H3 + 3]};       // b4
+#pragma unroll
+                for (int k = 0; k < H3; ++k) {
+                    const float4 wk = ld4(w4f + 4 * k);                                               // Wt4[k][0..3]
+                    o[0] = fmaf(v[k], wk.x, o[0]); o[1] = fmaf(v[k], wk.y, o[1]); o[2] = fmaf(v[k], wk.z, o[2]); o[3] = fmaf(v[k], wk.w, o[3]);
+                }
                 // ---- loss epilogue -> dz (an unselected row keeps dz = 0: every gradient term of it vanishes)
-                float dz[tcm::OUTP];
-#pragma unroll
-                for (int j = 0; j < tcm::OUTP; ++j) dz[j] = 0.f;
                 float d4[OP] = {0.f, 0.f, 0.f, 0.f};
-                if (sel) ppo_loss<HEAD>(la, s, make_float4(q[0] + w.b4[0], q[1] + w.b4[1], q[2] + w.b4[2], q[3] + w.b4[3]), d4, acc);
-#pragma unroll
-                for (int j = 0; j < OP; ++j) dz[j] = d4[j];
+                if (sel) ppo_loss<HEAD>(la, s, make_float4(o[0], o[1], o[2], o[3]), d4, acc);
                 st4(row + WG::D4, make_float4(d4[0], d4[1], d4[2], d4[3]));
-                tcm::put_row<tcm::OUTP>(ah, al, tid, dz);
-            }
-            sync_for_mma();
-            // ---- layer 4: backward-data on the tensor core, dW4 on W
-            if (tid == 0) tcm::issue_layer<tcm::OUTP, H3>(tmem + C4, ah, al, bw.w4h, bw.w4l, &sh.bar);
-            bar_arrive(BAR_R4, NT);                           // a3 and dz are in the rows
-            // the next tile's features travel from HBM while the backward chain runs
-            if (base + tstep < ss.Q) fetch(base + tstep, xn, seln, sn);
-            wait_mma();
-            tc::tmem_ld32(trow + C4, v);
+                bar_arrive(BAR_R4, NT);                       // a3 and dz are in the rows: dW4 on W
+                // the next tile's features travel from HBM while the backward chain runs
+                if (base + tstep < ss.Q) fetch(base + tstep, xn, seln, sn);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = ((m3 >> j) & 1u) ? v[j] : 0.f;                 // delta3 = relu'(a3) * (dz W4)
+                for (int k = 0; k < H3; ++k) {                                                        // delta3 = relu'(a3) * (dz W4)
+                    const float4 wk = ld4(w4f + 4 * k);
+                    const float g = fmaf(d4[3], wk.w, fmaf(d4[2], wk.z, fmaf(d4[1], wk.y, d4[0] * wk.x)));
+                    v[k] = ((m3 >> k) & 1u) ? g : 0.f;
+                }
+            }
             tcm::put_row<H3>(ah, al, tid, v);
             sync_for_mma();
             if (tid == 0) tcm::issue_layer<H3, H2>(tmem + C3, ah, al, bw.w3h, bw.w3l, &sh.bar);
