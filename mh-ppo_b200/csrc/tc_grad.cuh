@@ -39,9 +39,38 @@ struct BwdTiles {
     }
 };
 
+// NC columns [col0, col0 + NC) of this thread's row of the A operand, split hi / lo, into tensor memory
+template <int NC>
+__device__ __forceinline__ void put_tmem(uint32_t a_hi, uint32_t a_lo, const float *v) {
+    float t[NC];
+#pragma unroll
+    for (int j = 0; j < NC; ++j) t[j] = tcm::hi_part(v[j]);
+    if (NC == 32) tc::tmem_st32(a_hi, reinterpret_cast<const float (&)[32]>(t)); else tc::tmem_st16(a_hi, reinterpret_cast<const float (&)[16]>(t));
+#pragma unroll
+    for (int j = 0; j < NC; ++j) t[j] = v[j] - tcm::hi_part(v[j]);
+    if (NC == 32) tc::tmem_st32(a_lo, reinterpret_cast<const float (&)[32]>(t)); else tc::tmem_st16(a_lo, reinterpret_cast<const float (&)[16]>(t));
+}
+// one thread issues the 3xTF32 chains of a layer with the A operand in tensor memory (hi at a_hi, lo at a_lo: K columns each)
+template <int K, int J>
+__device__ __forceinline__ void issue_layer_ts(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, const float *bh, const float *bl, uint64_t *bar) {
+    constexpr uint32_t idesc = tc::make_idesc_tf32(128, J);
+    const uint32_t b0 = tc::smem_u32(bh), b1 = tc::smem_u32(bl);
+    bool acc = false;
+#pragma unroll
+    for (int pass = 0; pass < 3; ++pass) {
+        const uint32_t pa = (pass == 1) ? a_lo : a_hi, pb = (pass == 2) ? b1 : b0;
+#pragma unroll
+        for (int k0 = 0; k0 < K; k0 += 8) {
+            tc::mma_tf32_ts(d_tmem, pa + k0, tc::make_desc(pb + (k0 / 4) * 128, K), idesc, acc);
+            acc = true;
+        }
+    }
+    tc::mma_commit(bar);
+}
+
 constexpr int kTcGradRow = 16 + H1 + H2 + H3 + OP;       // 148 floats: 16-byte aligned rows, stride = 20 (mod 32) words -> conflict-free 128-bit accesses
 constexpr int kTcGradNetFloats = (tcm::NetTiles<16>::FLOATS + 255) & ~255;
-constexpr size_t kTcGradSmemFloats = (size_t)kTcGradNetFloats + BwdTiles::FLOATS + 2 * 128 * H2 + (size_t)128 * kTcGradRow;
+constexpr size_t kTcGradSmemFloats = (size_t)kTcGradNetFloats + BwdTiles::FLOATS + (size_t)128 * kTcGradRow;
 
 // Warp-specialised CTA: warps 0-3 ("E", thread = sample = TMEM lane) issue the MMAs and run the epilogues; warps 4-11 ("W")
 // only accumulate the weight gradient.  The two groups hand the row buffer back and forth through named barriers:
@@ -68,13 +97,14 @@ __global__ void __launch_bounds__(kTcGradBlock, 1) k_ppo_grad_tc(SampleSet ss, c
     BwdTiles bw;
     w.carve(smem);
     bw.carve(smem + kTcGradNetFloats);
-    float *ah = smem + kTcGradNetFloats + BwdTiles::FLOATS, *al = ah + 128 * H2, *rows = al + 128 * H2;
+    float *rows = smem + kTcGradNetFloats + BwdTiles::FLOATS;
     w.stage(net);
     bw.stage<KP>(net);
     for (int i = threadIdx.x; i < H3 * OP + OP; i += blockDim.x) w4f[i] = net[off_w4(KP) + i];      // W4t then b4 are contiguous in the flat layout
     // TMEM: forward accumulators in columns 0-63; each backward layer has its own columns, so a delta can be read a second time
     // (for the deferred row store) after the next MMA has been issued: layer 4 -> 64..95, layer 2 -> 96..127, layer 3 -> 128..191
-    constexpr uint32_t kCols = 256, C4 = 64, C2 = 96, C3 = 128;
+    // A operands (activations / deltas, hi and lo halves) live in tensor memory too: columns 256..319 and 320..383
+    constexpr uint32_t kCols = 512, C2 = 96, C3 = 128, AH = 256, AL = 320;
     if (threadIdx.x == 0) { tc::mbar_init(&sh.bar, 1); sh.fail = 0; }
     if ((threadIdx.x >> 5) == 0) tc::tmem_alloc(&sh.tmem_base, kCols);
     tc::fence_async_smem(); tc::fence_before(); __syncthreads(); tc::fence_after();
@@ -109,7 +139,9 @@ __global__ void __launch_bounds__(kTcGradBlock, 1) k_ppo_grad_tc(SampleSet ss, c
         const uint32_t trow = tmem + ((uint32_t)((tid >> 5) * 32) << 16);
         uint32_t phase = 0;
         float *row = rows + (size_t)tid * ROW;
-        auto sync_for_mma = [&]() { tc::fence_async_smem(); tc::fence_before(); bar_sync(BAR_E, kTcGradE); tc::fence_after(); };
+        auto sync_for_mma = [&]() { tc::tmem_wait_st(); tc::fence_before(); bar_sync(BAR_E, kTcGradE); tc::fence_after(); };
+        const uint32_t ahi = trow + AH, alo = trow + AL;        // this warp's lanes of the A operand
+        const uint32_t Ahi = tmem + AH, Alo = tmem + AL;        // operand addresses for the MMA (lane 0)
         auto wait_mma = [&]() { ok &= tc::mbar_wait(&sh.bar, phase); phase ^= 1; tc::fence_after(); };
         auto fetch = [&](int64_t base, float (&x)[KP], bool &sel, int64_t &s) {
             s = 0;
@@ -128,9 +160,9 @@ __global__ void __launch_bounds__(kTcGradBlock, 1) k_ppo_grad_tc(SampleSet ss, c
             float v[32];
             uint32_t m1 = 0, m2a = 0, m2b = 0, m3 = 0;                // ReLU masks of the three hidden layers
             // ---- forward.  The rows still belong to W (layer 1 + biases of the previous tile) until F1.
-            tcm::put_row<KP>(ah, al, tid, xn);
+            put_tmem<KP>(ahi, alo, xn);
             sync_for_mma();
-            if (tid == 0) tcm::issue_layer<KP, H1>(tmem, ah, al, w.w1h, w.w1l, &sh.bar);
+            if (tid == 0) issue_layer_ts<KP, H1>(tmem, Ahi, Alo, w.w1h, w.w1l, &sh.bar);
             if (!first) bar_sync(BAR_F1, NT);
             first = false;
 #pragma unroll
@@ -141,9 +173,9 @@ __global__ void __launch_bounds__(kTcGradBlock, 1) k_ppo_grad_tc(SampleSet ss, c
             for (int j = 0; j < 32; ++j) { v[j] = fmaxf(v[j] + w.b1[j], 0.f); m1 |= (v[j] > 0.f ? 1u : 0u) << j; }
 #pragma unroll
             for (int j = 0; j < 32; j += 4) st4(row + WG::A1 + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
-            tcm::put_row<H1>(ah, al, tid, v);
+            put_tmem<32>(ahi, alo, v);
             sync_for_mma();
-            if (tid == 0) tcm::issue_layer<H1, H2>(tmem, ah, al, w.w2h, w.w2l, &sh.bar);
+            if (tid == 0) issue_layer_ts<H1, H2>(tmem, Ahi, Alo, w.w2h, w.w2l, &sh.bar);
             wait_mma();
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
@@ -154,10 +186,10 @@ __global__ void __launch_bounds__(kTcGradBlock, 1) k_ppo_grad_tc(SampleSet ss, c
                 if (h) m2b = m; else m2a = m;
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) st4(row + WG::A2 + 32 * h + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
-                tcm::put_cols<32>(ah, al, tid, H2, 32 * h, v);
+                put_tmem<32>(ahi + 32 * h, alo + 32 * h, v);
             }
             sync_for_mma();
-            if (tid == 0) tcm::issue_layer<H2, H3>(tmem, ah, al, w.w3h, w.w3l, &sh.bar);
+            if (tid == 0) issue_layer_ts<H2, H3>(tmem, Ahi, Alo, w.w3h, w.w3l, &sh.bar);
             wait_mma();
             tc::tmem_ld32(trow, v);
 #pragma unroll
@@ -187,9 +219,9 @@ __global__ void __launch_bounds__(kTcGradBlock, 1) k_ppo_grad_tc(SampleSet ss, c
                     v[k] = ((m3 >> k) & 1u) ? g : 0.f;
                 }
             }
-            tcm::put_row<H3>(ah, al, tid, v);
+            put_tmem<32>(ahi, alo, v);
             sync_for_mma();
-            if (tid == 0) tcm::issue_layer<H3, H2>(tmem + C3, ah, al, bw.w3h, bw.w3l, &sh.bar);
+            if (tid == 0) issue_layer_ts<H3, H2>(tmem + C3, Ahi, Alo, bw.w3h, bw.w3l, &sh.bar);
             bar_sync(BAR_F4, NT);                             // a3 has been read
 #pragma unroll
             for (int j = 0; j < 32; j += 4) st4(row + WG::A3 + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
@@ -202,10 +234,10 @@ __global__ void __launch_bounds__(kTcGradBlock, 1) k_ppo_grad_tc(SampleSet ss, c
                 const uint32_t m = h ? m2b : m2a;
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = ((m >> j) & 1u) ? v[j] : 0.f;
-                tcm::put_cols<32>(ah, al, tid, H2, 32 * h, v);
+                put_tmem<32>(ahi + 32 * h, alo + 32 * h, v);
             }
             sync_for_mma();
-            if (tid == 0) tcm::issue_layer<H2, H1>(tmem + C2, ah, al, bw.w2h, bw.w2l, &sh.bar);
+            if (tid == 0) issue_layer_ts<H2, H1>(tmem + C2, Ahi, Alo, bw.w2h, bw.w2l, &sh.bar);
             bar_sync(BAR_F3, NT);                             // a2 has been read
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
@@ -244,7 +276,7 @@ __global__ void __launch_bounds__(kTcGradBlock, 1) k_ppo_grad_tc(SampleSet ss, c
     }
     tc::fence_before();
     __syncthreads();
-    if ((threadIdx.x >> 5) == 0) tc::tmem_dealloc(tmem, 256);
+    if ((threadIdx.x >> 5) == 0) tc::tmem_dealloc(tmem, 512);
 }
 
 }  // namespace mhppo
