@@ -70,7 +70,7 @@ __device__ __forceinline__ void issue_layer_ts(uint32_t d_tmem, uint32_t a_hi, u
 
 constexpr int kTcGradRow = 16 + H1 + H2 + H3 + OP;       // 148 floats: 16-byte aligned rows, stride = 20 (mod 32) words -> conflict-free 128-bit accesses
 constexpr int kTcGradNetFloats = (tcm::NetTiles<16>::FLOATS + 255) & ~255;
-constexpr size_t kTcGradSmemFloats = (size_t)kTcGradNetFloats + BwdTiles::FLOATS + (size_t)128 * kTcGradRow;
+constexpr size_t kTcGradSmemFloats = (size_t)kTcGradNetFloats + BwdTiles::FLOATS + (size_t)2 * 128 * kTcGradRow;      // two row buffers
 
 // Warp-specialised CTA: warps 0-3 ("E", thread = sample = TMEM lane) issue the MMAs and run the epilogues; warps 4-11 ("W")
 // only accumulate the weight gradient.  The two groups hand the row buffer back and forth through named barriers:
@@ -79,7 +79,7 @@ constexpr size_t kTcGradSmemFloats = (size_t)kTcGradNetFloats + BwdTiles::FLOATS
 // E keeps a freshly computed delta in registers, feeds it to the tensor core through the A tile at once, and stores it into
 // the rows only when W releases them, so the chain of backward-data MMAs runs ahead of the (longer) weight-gradient chain.
 constexpr int kTcGradE = 128, kTcGradW = 256, kTcGradBlock = kTcGradE + kTcGradW;
-enum { BAR_E = 1, BAR_W = 10, BAR_R4 = 2, BAR_F4 = 3, BAR_R3 = 4, BAR_F3 = 5, BAR_R2 = 6, BAR_F2 = 7, BAR_R1 = 8, BAR_F1 = 9 };
+enum { BAR_E = 1, BAR_W = 10, BAR_R4 = 2, BAR_F4 = 3, BAR_R3 = 4, BAR_F3 = 5, BAR_R2 = 6, BAR_F2 = 7, BAR_R1 = 8, BAR_F1 = 9, BAR_F1B = 11 };   // F1 of odd tiles: BAR_F1B
 __device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id, int n) { __threadfence_block(); asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
@@ -97,7 +97,8 @@ __global__ void __launch_bounds__(kTcGradBlock, 1) k_ppo_grad_tc(SampleSet ss, c
     BwdTiles bw;
     w.carve(smem);
     bw.carve(smem + kTcGradNetFloats);
-    float *rows = smem + kTcGradNetFloats + BwdTiles::FLOATS;
+    float *rows0 = smem + kTcGradNetFloats + BwdTiles::FLOATS;     // tile t lives in row buffer t & 1
+    constexpr int RBUF = 128 * kTcGradRow;
     w.stage(net);
     bw.stage<KP>(net);
     for (int i = threadIdx.x; i < H3 * OP + OP; i += blockDim.x) w4f[i] = net[off_w4(KP) + i];      // W4t then b4 are contiguous in the flat layout
@@ -121,12 +122,15 @@ __global__ void __launch_bounds__(kTcGradBlock, 1) k_ppo_grad_tc(SampleSet ss, c
         wg.init(tid - kTcGradE);
         constexpr int PART = 128 / NG;                    // rows per group
         const int s0 = wg.half * PART;
-        for (int64_t base = tile0; base < ss.Q; base += tstep) {
+        int t = 0;
+        for (int64_t base = tile0; base < ss.Q; base += tstep, ++t) {
+            const float *rows = rows0 + (t & 1) * RBUF;
             bar_sync(BAR_R4, NT);  wg.layer4(rows, ROW, s0, PART);             bar_arrive(BAR_F4, NT);
             bar_sync(BAR_R3, NT);  wg.layer3(rows, ROW, s0, PART);             bar_arrive(BAR_F3, NT);
             bar_sync(BAR_R2, NT);  wg.layer2(rows, ROW, s0, PART);             bar_arrive(BAR_F2, NT);
-            bar_sync(BAR_R1, NT);  wg.layer1_and_biases(rows, ROW, s0, PART);  bar_arrive(BAR_F1, NT);
+            bar_sync(BAR_R1, NT);  wg.layer1_and_biases(rows, ROW, s0, PART);  bar_arrive((t & 1) ? BAR_F1B : BAR_F1, NT);
         }
+        float *rows = rows0;
         // add the groups in the (now dead) row buffer, fixed order: deterministic
         bar_sync(BAR_W, kTcGradW);
 #pragma unroll 1
@@ -138,7 +142,6 @@ __global__ void __launch_bounds__(kTcGradBlock, 1) k_ppo_grad_tc(SampleSet ss, c
         // ================= E: MMA issue + epilogues =================
         const uint32_t trow = tmem + ((uint32_t)((tid >> 5) * 32) << 16);
         uint32_t phase = 0;
-        float *row = rows + (size_t)tid * ROW;
         auto sync_for_mma = [&]() { tc::tmem_wait_st(); tc::fence_before(); bar_sync(BAR_E, kTcGradE); tc::fence_after(); };
         const uint32_t ahi = trow + AH, alo = trow + AL;        // this warp's lanes of the A operand
         const uint32_t Ahi = tmem + AH, Alo = tmem + AL;        // operand addresses for the MMA (lane 0)
@@ -153,18 +156,19 @@ __global__ void __launch_bounds__(kTcGradBlock, 1) k_ppo_grad_tc(SampleSet ss, c
         bool seln = false;
         int64_t sn = 0;
         if (tile0 < ss.Q) fetch(tile0, xn, seln, sn);
-        bool first = true;
-        for (int64_t base = tile0; base < ss.Q; base += tstep) {
+        int t = 0;
+        for (int64_t base = tile0; base < ss.Q; base += tstep, ++t) {
+            float *row = rows0 + (t & 1) * RBUF + (size_t)tid * ROW;
             const bool sel = seln;
             const int64_t s = sn;
             float v[32];
             uint32_t m1 = 0, m2a = 0, m2b = 0, m3 = 0;                // ReLU masks of the three hidden layers
-            // ---- forward.  The rows still belong to W (layer 1 + biases of the previous tile) until F1.
+            // ---- forward.  This tile's row buffer still belongs to W (layer 1 + biases of the tile before the previous one) until its F1;
+            // the previous tile's weight gradient runs on the other buffer meanwhile.
             put_tmem<KP>(ahi, alo, xn);
             sync_for_mma();
             if (tid == 0) issue_layer_ts<KP, H1>(tmem, Ahi, Alo, w.w1h, w.w1l, &sh.bar);
-            if (!first) bar_sync(BAR_F1, NT);
-            first = false;
+            if (t >= 2) bar_sync((t & 1) ? BAR_F1B : BAR_F1, NT);
 #pragma unroll
             for (int k = 0; k < KP; k += 4) st4(row + WG::X + k, make_float4(xn[k], xn[k + 1], xn[k + 2], xn[k + 3]));
             wait_mma();
@@ -260,14 +264,16 @@ __global__ void __launch_bounds__(kTcGradBlock, 1) k_ppo_grad_tc(SampleSet ss, c
             for (int j = 0; j < 32; j += 4) st4(row + WG::A1 + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
             bar_arrive(BAR_R1, NT);                           // delta1 is in the rows: layer 1 and the biases
         }
-        if (!first) bar_sync(BAR_F1, NT);                     // the last tile's rows have been read
+        // the last two tiles' rows have been read (one F1 arrival of W is still unmatched per buffer in use)
+        if (t >= 2) bar_sync((t & 1) ? BAR_F1B : BAR_F1, NT);
+        if (t >= 1) bar_sync(((t - 1) & 1) ? BAR_F1B : BAR_F1, NT);
     }
     // ================= emit the CTA's partials =================
     if (!ok) atomicExch(fail_flag, 1);
     __syncthreads();
     constexpr int NPAR = net_params(KP);
     float *gp = gpartial + (size_t)blockIdx.x * NPAR;
-    for (int i = tid; i < NPAR; i += NT) gp[i] = rows[i];
+    for (int i = tid; i < NPAR; i += NT) gp[i] = rows0[i];
     const double lsum = team_sum(acc.loss, red, tid, NT, 0);
     if (tid == 0) lpartial[blockIdx.x] = lsum;
     if (HEAD == 0 && la.spartial) {
