@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(kTcGradBlock, 1) k_ppo_grad_tc(SampleSet ss, c
     extern __shared__ __align__(1024) float smem[];
     __shared__ TcShared sh;
     __shared__ double red[kTcGradBlock / 32];
-    __shared__ __align__(16) float w4f[H3 * OP + OP];             // Wt4[k][j] and b4, fp32 (layer 4 runs on the CUDA cores)
+    __shared__ __align__(16) float w4c[H3 + 4];                   // column 0 of Wt4 and b4[0], fp32 (the output layer runs on the CUDA cores)
     tcm::NetTiles<KP> w;
     BwdTiles bw;
     w.carve(smem);
@@ -101,7 +101,8 @@ __global__ void __launch_bounds__(kTcGradBlock, 1) k_ppo_grad_tc(SampleSet ss, c
     constexpr int RBUF = 128 * kTcGradRow;
     w.stage(net);
     bw.stage<KP>(net);
-    for (int i = threadIdx.x; i < H3 * OP + OP; i += blockDim.x) w4f[i] = net[off_w4(KP) + i];      // W4t then b4 are contiguous in the flat layout
+    static_assert(HEAD == 0 || HEAD == 1, "single-output heads only: the categorical choice nets use k_ppo_grad");
+    for (int i = threadIdx.x; i <= H3; i += blockDim.x) w4c[i] = (i < H3) ? net[off_w4(KP) + i * OP] : net[off_b4(KP)];
     // TMEM: forward accumulators in columns 0-63; each backward layer has its own columns, so a delta can be read a second time
     // (for the deferred row store) after the next MMA has been issued: layer 4 -> 64..95, layer 2 -> 96..127, layer 3 -> 128..191
     // A operands (activations / deltas, hi and lo halves) live in tensor memory too: columns 256..319 and 320..383
@@ -200,27 +201,29 @@ __global__ void __launch_bounds__(kTcGradBlock, 1) k_ppo_grad_tc(SampleSet ss, c
             for (int j = 0; j < 32; ++j) { v[j] = fmaxf(v[j] + w.b3[j], 0.f); m3 |= (v[j] > 0.f ? 1u : 0u) << j; }
 #pragma unroll
             for (int j = 0; j < 32; j += 4) st4(row + WG::A3 + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
-            // ---- layer 4 (32 -> 4 outputs) and its backward-data stay on the CUDA cores: 2 x 128 FFMAs per sample from the
-            // registers that already hold a3, exact fp32, instead of two more dependent MMA round trips per tile
+            // ---- output layer and its backward-data stay on the CUDA cores, exact fp32, from the registers that already hold a3,
+            // instead of two more dependent MMA round trips per tile.  The 13-input nets (heads 0 and 1) have ONE output: only column
+            // 0 of the padded 32 x 4 weight block is live, so this is 32 FFMAs forward and 32 FMULs backward per sample.
             {
-                float o[OP] = {w4f[4 * H3 + 0], w4f[4 * H3 + 1], w4f[4 * H3 + 2], w4f[4 * H3 + 3]};       // b4
+                float o0 = w4c[H3];                                                                   // b4[0]
 #pragma unroll
-                for (int k = 0; k < H3; ++k) {
-                    const float4 wk = ld4(w4f + 4 * k);                                               // Wt4[k][0..3]
-                    o[0] = fmaf(v[k], wk.x, o[0]); o[1] = fmaf(v[k], wk.y, o[1]); o[2] = fmaf(v[k], wk.z, o[2]); o[3] = fmaf(v[k], wk.w, o[3]);
+                for (int k4 = 0; k4 < H3 / 4; ++k4) {
+                    const float4 wk = ld4(w4c + 4 * k4);                                              // Wt4[4 k4 .. 4 k4 + 3][0]
+                    o0 = fmaf(v[4 * k4 + 0], wk.x, o0); o0 = fmaf(v[4 * k4 + 1], wk.y, o0);
+                    o0 = fmaf(v[4 * k4 + 2], wk.z, o0); o0 = fmaf(v[4 * k4 + 3], wk.w, o0);
                 }
                 // ---- loss epilogue -> dz (an unselected row keeps dz = 0: every gradient term of it vanishes)
                 float d4[OP] = {0.f, 0.f, 0.f, 0.f};
-                if (sel) ppo_loss<HEAD>(la, s, make_float4(o[0], o[1], o[2], o[3]), d4, acc);
-                st4(row + WG::D4, make_float4(d4[0], d4[1], d4[2], d4[3]));
+                if (sel) ppo_loss<HEAD>(la, s, make_float4(o0, 0.f, 0.f, 0.f), d4, acc);
+                st4(row + WG::D4, make_float4(d4[0], 0.f, 0.f, 0.f));
                 bar_arrive(BAR_R4, NT);                       // a3 and dz are in the rows: dW4 on W
                 // the next tile's features travel from HBM while the backward chain runs
                 if (base + tstep < ss.Q) fetch(base + tstep, xn, seln, sn);
 #pragma unroll
-                for (int k = 0; k < H3; ++k) {                                                        // delta3 = relu'(a3) * (dz W4)
-                    const float4 wk = ld4(w4f + 4 * k);
-                    const float g = fmaf(d4[3], wk.w, fmaf(d4[2], wk.z, fmaf(d4[1], wk.y, d4[0] * wk.x)));
-                    v[k] = ((m3 >> k) & 1u) ? g : 0.f;
+                for (int k4 = 0; k4 < H3 / 4; ++k4) {                                                 // delta3 = relu'(a3) * dz0 * W4[:, 0]
+                    const float4 wk = ld4(w4c + 4 * k4);
+                    v[4 * k4 + 0] = ((m3 >> (4 * k4 + 0)) & 1u) ? d4[0] * wk.x : 0.f; v[4 * k4 + 1] = ((m3 >> (4 * k4 + 1)) & 1u) ? d4[0] * wk.y : 0.f;
+                    v[4 * k4 + 2] = ((m3 >> (4 * k4 + 2)) & 1u) ? d4[0] * wk.z : 0.f; v[4 * k4 + 3] = ((m3 >> (4 * k4 + 3)) & 1u) ? d4[0] * wk.w : 0.f;
                 }
             }
             put_tmem<32>(ahi, alo, v);
