@@ -175,7 +175,12 @@ __global__ void __launch_bounds__(kTcGradBlock, 1) k_ppo_grad_tc(SampleSet ss, c
             wait_mma();
             tc::tmem_ld32(trow, v);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) { v[j] = fmaxf(v[j] + w.b1[j], 0.f); m1 |= (v[j] > 0.f ? 1u : 0u) << j; }
+            for (int j = 0; j < 32; j += 4) {
+                const float4 b = ld4(w.b1 + j);               // (the bias arrays are 16-byte aligned in the weight image)
+                v[j] = fmaxf(v[j] + b.x, 0.f); v[j + 1] = fmaxf(v[j + 1] + b.y, 0.f); v[j + 2] = fmaxf(v[j + 2] + b.z, 0.f); v[j + 3] = fmaxf(v[j + 3] + b.w, 0.f);
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) m1 |= (v[j] > 0.f ? 1u : 0u) << j;
 #pragma unroll
             for (int j = 0; j < 32; j += 4) st4(row + WG::A1 + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
             put_tmem<32>(ahi, alo, v);
@@ -187,7 +192,12 @@ __global__ void __launch_bounds__(kTcGradBlock, 1) k_ppo_grad_tc(SampleSet ss, c
                 tc::tmem_ld32(trow + 32 * h, v);
                 uint32_t m = 0;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) { v[j] = fmaxf(v[j] + w.b2[32 * h + j], 0.f); m |= (v[j] > 0.f ? 1u : 0u) << j; }
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 b = ld4(w.b2 + 32 * h + j);
+                    v[j] = fmaxf(v[j] + b.x, 0.f); v[j + 1] = fmaxf(v[j + 1] + b.y, 0.f); v[j + 2] = fmaxf(v[j + 2] + b.z, 0.f); v[j + 3] = fmaxf(v[j + 3] + b.w, 0.f);
+                }
+#pragma unroll
+                for (int j = 0; j < 32; ++j) m |= (v[j] > 0.f ? 1u : 0u) << j;
                 if (h) m2b = m; else m2a = m;
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) st4(row + WG::A2 + 32 * h + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
@@ -198,7 +208,12 @@ __global__ void __launch_bounds__(kTcGradBlock, 1) k_ppo_grad_tc(SampleSet ss, c
             wait_mma();
             tc::tmem_ld32(trow, v);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) { v[j] = fmaxf(v[j] + w.b3[j], 0.f); m3 |= (v[j] > 0.f ? 1u : 0u) << j; }
+            for (int j = 0; j < 32; j += 4) {
+                const float4 b = ld4(w.b3 + j);
+                v[j] = fmaxf(v[j] + b.x, 0.f); v[j + 1] = fmaxf(v[j + 1] + b.y, 0.f); v[j + 2] = fmaxf(v[j + 2] + b.z, 0.f); v[j + 3] = fmaxf(v[j + 3] + b.w, 0.f);
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) m3 |= (v[j] > 0.f ? 1u : 0u) << j;
 #pragma unroll
             for (int j = 0; j < 32; j += 4) st4(row + WG::A3 + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
             // ---- output layer and its backward-data stay on the CUDA cores, exact fp32, from the registers that already hold a3,
