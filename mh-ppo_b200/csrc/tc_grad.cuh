@@ -81,7 +81,9 @@ constexpr size_t kTcGradSmemFloats = (size_t)kTcGradNetFloats + BwdTiles::FLOATS
 constexpr int kTcGradE = 128, kTcGradW = 256, kTcGradBlock = kTcGradE + kTcGradW;
 enum { BAR_E = 1, BAR_W = 10, BAR_R4 = 2, BAR_F4 = 3, BAR_R3 = 4, BAR_F3 = 5, BAR_R2 = 6, BAR_F2 = 7, BAR_R1 = 8, BAR_F1 = 9, BAR_F1B = 11 };   // F1 of odd tiles: BAR_F1B
 __device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
-__device__ __forceinline__ void bar_arrive(int id, int n) { __threadfence_block(); asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+// (producer side of the PTX producer / consumer barrier pattern: shared-memory stores before bar.arrive are visible to the
+// threads that leave the matching bar.sync, no extra fence needed)
+__device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
 template <int HEAD>
 __global__ void __launch_bounds__(kTcGradBlock, 1) k_ppo_grad_tc(SampleSet ss, const float *__restrict__ net, LossArgs la,
