@@ -78,7 +78,7 @@ constexpr size_t kTcGradSmemFloats = (size_t)kTcGradNetFloats + BwdTiles::FLOATS
 //   input-activation columns may be overwritten by the delta of the layer below.
 // E keeps a freshly computed delta in registers, feeds it to the tensor core through the A tile at once, and stores it into
 // the rows only when W releases them, so the chain of backward-data MMAs runs ahead of the (longer) weight-gradient chain.
-constexpr int kTcGradE = 128, kTcGradW = 256, kTcGradBlock = kTcGradE + kTcGradW;
+constexpr int kTcGradE = 128, kTcGradW = 128, kTcGradBlock = kTcGradE + kTcGradW;
 enum { BAR_E = 1, BAR_W = 10, BAR_R4 = 2, BAR_F4 = 3, BAR_R3 = 4, BAR_F3 = 5, BAR_R2 = 6, BAR_F2 = 7, BAR_R1 = 8, BAR_F1 = 9, BAR_F1B = 11 };   // F1 of odd tiles: BAR_F1B
 __device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 // (producer side of the PTX producer / consumer barrier pattern: shared-memory stores before bar.arrive are visible to the
