@@ -222,25 +222,34 @@ __device__ __forceinline__ void wgrad_tile(float (&acc)[4][TJ], const float *__r
 // o: raw outputs of the net; returns dLoss/dz (4 padded outputs) and accumulates the loss and, for the critic,
 // the advantage statistics.
 struct LossAcc { double loss = 0.0, sA = 0.0, sAA = 0.0, cnt = 0.0; };
+// the per-sample inputs of the loss (rtg for every head; V, action, old log-prob for the actors): can be loaded ahead of use
+struct LossIn { float rtg, V, act, logp; };
 template <int HEAD>
-__device__ __forceinline__ void ppo_loss(const LossArgs &la, int64_t s, float4 o, float (&dz)[OP], LossAcc &acc) {
+__device__ __forceinline__ LossIn load_loss_in(const LossArgs &la, int64_t s) {
+    LossIn in; in.rtg = la.rtg[s]; in.V = 0.f; in.act = 0.f; in.logp = 0.f;
+    if (HEAD != 0) { in.V = la.V[s]; in.logp = la.logp_old[s]; }
+    if (HEAD == 1) in.act = la.act[s];
+    return in;
+}
+template <int HEAD>
+__device__ __forceinline__ void ppo_loss(const LossArgs &la, int64_t s, const LossIn &in, float4 o, float (&dz)[OP], LossAcc &acc) {
     if (HEAD == 0) {                                           // critic_loss = MSE(V, rtg), PY:808-809
-        const float e = o.x - la.rtg[s];
+        const float e = o.x - in.rtg;
         acc.loss += (double)e * (double)e * (double)la.inv_n;
         dz[0] = 2.0f * e * la.inv_n;
         if (la.V_out) {                                        // V = critic(s), A = rtgs - V (PY:785-786)
             la.V_out[s] = o.x;
-            const double A = (double)(la.rtg[s] - o.x);
+            const double A = (double)(in.rtg - o.x);
             acc.sA += A; acc.sAA += A * A; acc.cnt += 1.0;
         }
         return;
     }
-    const float An = ((la.rtg[s] - la.V[s]) - la.adv_mean) * la.adv_inv_std;     // PY:786-787
+    const float An = ((in.rtg - in.V) - la.adv_mean) * la.adv_inv_std;     // PY:786-787
     if (HEAD == 1) {
         const float th = tanhf(o.x), mu = th * 3.0f + (-1.0f);
-        const float a = la.act[s];
+        const float a = in.act;
         const float lp = -((a - mu) * (a - mu)) - 0.57236494292470008f;          // MVN(mu, .5 I).log_prob, PY:795-800
-        const float ratio = expf(lp - la.logp_old[s]);                           // PY:803
+        const float ratio = expf(lp - in.logp);                           // PY:803
         const float s1 = ratio * An, s2 = fminf(fmaxf(ratio, 0.8f), 1.2f) * An;   // PY:804-805
         acc.loss += (double)(-fminf(s1, s2)) * (double)la.inv_n;                 // PY:806
         if (s1 <= s2) dz[0] = -la.inv_n * An * ratio * (2.0f * (a - mu)) * (3.0f * (1.0f - th * th));
@@ -249,7 +258,7 @@ __device__ __forceinline__ void ppo_loss(const LossArgs &la, int64_t s, float4 o
         // (PY:834-842).  With two actions the mean over i collapses to the action frequencies f0, f1.
         const float m = fmaxf(o.x, o.y), e0 = expf(o.x - m), e1 = expf(o.y - m);
         const float p0 = e0 / (e0 + e1), p1 = e1 / (e0 + e1);
-        const float inv_old = expf(-la.logp_old[s]);
+        const float inv_old = expf(-in.logp);
         float dp0 = 0.f, dp1 = 0.f;
         {
             const float rr = p0 * inv_old, s1 = rr * An, s2 = fminf(fmaxf(rr, 0.8f), 1.2f) * An;
@@ -421,7 +430,7 @@ __global__ void __launch_bounds__(kMlpBlock, 1) k_ppo_grad(SampleSet ss, const f
         for (int r = 0; r < R; ++r) {
             float *row = my + r * RS;
             float dz[OP] = {0.f, 0.f, 0.f, 0.f};
-            if (sel[r]) ppo_loss<HEAD>(la, sidx[r], ld4(row + G::D4), dz, acc);
+            if (sel[r]) ppo_loss<HEAD>(la, sidx[r], load_loss_in<HEAD>(la, sidx[r]), ld4(row + G::D4), dz, acc);
             // an unselected row has x = 0 but its activations are relu(bias) != 0: its dz = 0 keeps every gradient term zero
             st4(row + G::D4, make_float4(dz[0], dz[1], dz[2], dz[3]));
         }

@@ -149,11 +149,14 @@ __global__ void __launch_bounds__(kTcGradBlock, 1) k_ppo_grad_tc(SampleSet ss, c
         const uint32_t ahi = trow + AH, alo = trow + AL;        // this warp's lanes of the A operand
         const uint32_t Ahi = tmem + AH, Alo = tmem + AL;        // operand addresses for the MMA (lane 0)
         auto wait_mma = [&]() { ok &= tc::mbar_wait(&sh.bar, phase); phase ^= 1; tc::fence_after(); };
-        auto fetch = [&](int64_t base, float (&x)[KP], bool &sel, int64_t &s) {
+        LossIn lin;
+        lin.rtg = lin.V = lin.act = lin.logp = 0.f;
+        auto fetch = [&](int64_t base, float (&x)[KP], bool &sel, int64_t &s) {      // features and loss inputs of a tile, ahead of use
             s = 0;
             sel = map_sample(ss, base + tid, s);
 #pragma unroll
             for (int k = 0; k < KP; ++k) x[k] = (sel && k < ss.D) ? ss.x[(int64_t)k * ss.S + s] : 0.f;
+            if (sel) lin = load_loss_in<HEAD>(la, s);
         };
         float xn[KP];
         bool seln = false;
@@ -164,6 +167,7 @@ __global__ void __launch_bounds__(kTcGradBlock, 1) k_ppo_grad_tc(SampleSet ss, c
             float *row = rows0 + (t & 1) * RBUF + (size_t)tid * ROW;
             const bool sel = seln;
             const int64_t s = sn;
+            const LossIn lcur = lin;
             float v[32];
             uint32_t m1 = 0, m2a = 0, m2b = 0, m3 = 0;                // ReLU masks of the three hidden layers
             // ---- forward.  This tile's row buffer still belongs to W (layer 1 + biases of the tile before the previous one) until its F1;
@@ -231,7 +235,7 @@ __global__ void __launch_bounds__(kTcGradBlock, 1) k_ppo_grad_tc(SampleSet ss, c
                 }
                 // ---- loss epilogue -> dz (an unselected row keeps dz = 0: every gradient term of it vanishes)
                 float d4[OP] = {0.f, 0.f, 0.f, 0.f};
-                if (sel) ppo_loss<HEAD>(la, s, make_float4(o0, 0.f, 0.f, 0.f), d4, acc);
+                if (sel) ppo_loss<HEAD>(la, s, lcur, make_float4(o0, 0.f, 0.f, 0.f), d4, acc);
                 st4(row + WG::D4, make_float4(d4[0], 0.f, 0.f, 0.f));
                 bar_arrive(BAR_R4, NT);                       // a3 and dz are in the rows: dW4 on W
                 // the next tile's features travel from HBM while the backward chain runs
