@@ -84,10 +84,6 @@ MH_HD bool gap_eval(double dx, double vden, double light, double size, double v0
 // The cars of NT envs (one CTA; NT = 1 in the host build), [field][slot][thread].  Positions and
 // speeds are the fp64 values after this step's move (they are rounded to fp32 only when stored);
 // brake = Vc^2/(2b) and rVc = 1/Vc are the two per-car quotients every (pedestrian, car) pair reuses.
-#ifndef MH_PAIR_UNROLL
-#define MH_PAIR_UNROLL 1
-#endif
-constexpr int kPairUnroll = MH_PAIR_UNROLL;
 template <int MC, int NT>
 struct CarSlots {
     double Sc[MC][NT], Vc[MC][NT], brake[MC][NT], rVc[MC][NT];
@@ -346,19 +342,6 @@ MH_HD void env_step_thread(const EnvArena &a, const EnvConst &c, const RngKey &k
         rng.ctr = f2u(ee.w); rng.env_lo = (uint32_t)gid; rng.env_hi = (uint32_t)(gid >> 32); rng.k0 = key.k0; rng.k1 = key.k1;
     }
     const Geo g = make_geo(cross, c.L);
-#if defined(__CUDA_ARCH__) && defined(MH_PREFETCH)
-    // every later load of this thread's state is a dependent DRAM round trip in a rolled loop: start them all now
-    // (L2 prefetch holds no registers; the loops below then hit L2)
-    for (int i = 0; i < c.nC; ++i) {
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.car_a + (int64_t)i * a.N + n));
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.car_b + (int64_t)i * a.N + n));
-    }
-    for (int j = 0; j < c.nP; ++j) {
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.ped_a + (int64_t)j * a.N + n));
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.ped_b + (int64_t)j * a.N + n));
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.ped_c + (int64_t)j * a.N + n));
-    }
-#endif
     const bool done = (step >= c.done_idx) || (ped_traffic <= 0);                    // SC:874
     const bool will_reset = done && io.autoreset;
     const mhppo_view ov = will_reset ? io.term_obs : io.obs;
@@ -484,7 +467,7 @@ MH_HD void env_step_thread(const EnvArena &a, const EnvConst &c, const RngKey &k
         // min(fp32 old, fp32(candidate)) == fp32(min(old, candidate)) bit for bit.
         uint32_t fl = p.fl;
         const bool counts = (p.fl & PF_CROSSING) && (!T::scal || pex);               // SC:844-845
-#pragma unroll kPairUnroll
+#pragma unroll 1
         for (int i = 0; i < c.nlead; ++i) {
             const double Sc = S.Sc[i][t], Vc = S.Vc[i][t];
             const float light = S.light[i][t];
@@ -543,7 +526,7 @@ MH_HD void env_step_thread(const EnvArena &a, const EnvConst &c, const RngKey &k
             const bool guard_p = pex && !left && (p.fl & PF_CROSSING);
             const float acc_pen = (p.fl & PF_ACCIDENT) ? 20.0f : 0.0f;
             float pwdl = (float)p.wdl;
-#pragma unroll kPairUnroll
+#pragma unroll 1
             for (int i = 0; i < c.nlead; ++i) {
                 const double Vc = S.Vc[i][t];
                 const bool grn = pex && (S.light[i][t] > 0.f);
