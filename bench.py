@@ -341,7 +341,7 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "Env_hybrid_multi_%s nb_car=%d nb_ped=%d nb_lines=%d, %d envs/GPU, env.step with in-kernel auto-reset" % (
                 variant, nb_car, nb_ped, nb_lines, n_envs),
-                "l2": "inputs+state+outputs per step exceed no cache assumption: L2 flushed by an untimed 256 MiB memset between timed steps"
+                "l2": "flushed: an untimed 256 MiB memset (2x the 126 MB L2) runs between timed steps; the per-step working set is ~150 MB"
                 if flushed else "not flushed", "state_bytes_per_env": state_bytes,
                 "parallelism": "env shards per rank, no data-path collective"},
             "env_steps_per_s": env_steps, "slot_agent_steps_per_s": env_steps * (C + nb_ped),
