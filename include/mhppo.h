@@ -198,8 +198,9 @@ int mhppo_adam(float *param_dev, const float *grad_dev, float *m_dev, float *v_d
 
 /* Self-test of the tcgen05 / TMEM building blocks behind the policy GEMMs: D[128,N] = A[128,K] * B[N,K]^T on one CTA,
  * mode 0 = one tf32 pass, mode 1 = 3xTF32 split accumulation.  (N,K) in {(64,32),(32,64),(64,16),(16,32)}. */
-/* implementation of the 13-input nets' forward-only kernels: 0 auto (tcgen05 critic forward in the update, FFMA rollout
- * inference), 1 FFMA everywhere (exact fp32 cross-check), 2 tcgen05 wherever a tensor-core kernel exists */
+/* implementation of the 13-input nets' kernels: 0 auto (tcgen05 for the update: forward + backward-data of ppo_grad /
+ * critic_grad_stats and the critic forward of value_stats; exact-fp32 FFMA for the rollout inference), 1 FFMA everywhere
+ * (exact fp32 cross-check), 2 tcgen05 wherever a tensor-core kernel exists (also the rollout inference) */
 int mhppo_set_mlp_mode(int32_t mode);
 /* 1 if a tensor-core kernel ever timed out waiting for its MMAs (diagnostic; synchronises the device) */
 int mhppo_tc_failures(void);
