@@ -117,9 +117,17 @@ MH_HD double dmin(double a, double b) { return b < a ? b : a; }   // Python min(
 // x / den for den > 0, bit-identical to the plain quotient.  A zero numerator (a stopped car: Vc = 0, a = 0) sends
 // the device's fp64 division into its out-of-line slow path; a third of the cars stand still at any time, so the
 // quotient is formed from a stand-in numerator and the (signed) zero is passed through instead.
+// keeps the compiler from folding a select of the operand back through the division (it turned
+// `(z ? 1 : x) / den` into `z ? 1 / den : x / den`, and the zero was back in the divider)
+MH_HD double opaque(double x) {
+#if defined(__CUDA_ARCH__) && !defined(MH_NO_DIVFIX)
+    asm volatile("" : "+d"(x));
+#endif
+    return x;
+}
 MH_HD double div_pos(double x, double den) {
     const bool z = (x == 0.0);
-    const double q = (z ? 1.0 : x) / den;
+    const double q = opaque(z ? 1.0 : x) / den;
     return z ? x : q;
 }
 MH_HD double dmax(double a, double b) { return b > a ? b : a; }   // Python max(a, b)
