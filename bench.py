@@ -104,29 +104,126 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.rows)}
 
 
-def cpu_port_rate(variant, nb_car, nb_ped, nb_lines, n_envs, n_steps, threads=0):
-    """env-steps/s of the C oracle port on the host cores (actions pre-generated, untimed)."""
+EPISODE = 80   # every episode of every env class lasts exactly 80 steps
+
+
+def synthetic_actions_np(n_envs, A, seed=0):
+    """acc ~ U(-4, 2) fresh every step (a pool of 4 draws, cycled), light in {-1, +1} drawn once per
+    episode and held for its 80 steps (two light draws, alternating from one episode to the next)."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    lights = [rng.choice([-1.0, 1.0], (n_envs, A // 2)) for _ in range(2)]
+    acts = []
+    for e in range(2):
+        row = []
+        for _ in range(4):
+            a = np.empty((n_envs, A))
+            a[:, :A // 2] = rng.uniform(-4, 2, (n_envs, A // 2))
+            a[:, A // 2:] = lights[e]
+            row.append(a)
+        acts.append(row)
+    return acts
+
+
+def cpu_port_run(variant, nb_car, nb_ped, nb_lines, n_envs, warmup, steps, threads=0, min_seconds=5.0, max_rounds=64):
+    """The CPU leg of both arms: the C oracle port on the host cores over the WHOLE n_envs batch.  One round = reset,
+    `warmup` untimed steps, `steps` timed steps (the same window of the episode the GPU arm times); rounds are repeated
+    until `min_seconds` of timed work.  Returns (env-steps/s, timed seconds, active agents per env, rounds)."""
     import numpy as np
     from oracle import oracle as O
     env = O.OracleVecEnv(variant, n_envs, nb_car, nb_ped, nb_lines, seed=1234, n_threads=threads, store_f32=False)
-    env.reset()
-    rng = np.random.default_rng(0)
     A = env.n_action
-    pool = []
-    for _ in range(4):
-        a = np.empty((n_envs, A))
-        a[:, :A // 2] = rng.uniform(-4, 2, (n_envs, A // 2))
-        a[:, A // 2:] = rng.choice([-1.0, 1.0], (n_envs, A // 2))
-        pool.append(a)
-    for t in range(3):
-        env.step(pool[t % 4], autoreset=True)
+    acts = synthetic_actions_np(n_envs, A)
+    obs = np.empty((n_envs, env.n_obs), np.float32)
+    rew = np.empty((n_envs, env.n_lead)); rl = np.empty((n_envs, env.n_lead)); done = np.empty(n_envs, np.uint8)
+    timed, rounds, active = 0.0, 0, []
+    while rounds < max_rounds and (rounds == 0 or timed < min_seconds):
+        env.reset()
+        for t in range(warmup):
+            env.step_into(acts[(t // EPISODE) % 2][t % 4], obs, rew, rl, done)
+        t0 = time.perf_counter()
+        for t in range(warmup, warmup + steps):
+            env.step_into(acts[(t // EPISODE) % 2][t % 4], obs, rew, rl, done)
+        timed += time.perf_counter() - t0
+        rounds += 1
+        s = env.get_state()
+        active.append(float((s["env_i"][:, 1] + s["env_i"][:, 2]).mean()))
+    return n_envs * steps * rounds / timed, timed, sum(active) / len(active), rounds
+
+
+def cpu_ppo_rate(n_envs=256):
+    """PPO samples/s of the CPU restatement of the PPO pipeline (oracle/ppo_oracle.py: vectorised numpy feature builders,
+    torch CPU networks / autograd / Adam on all host threads, C env port): one iteration = one 80-step episode per env,
+    reward-to-go, 10 x (cross, wait) + 10 x choice epochs (Algo_PPO.train, PY:854-917)."""
+    import numpy as np
+    import torch
+    from oracle import oracle as O, ppo_oracle as PO
+    torch.manual_seed(0)
+    P, L, seed = 3, 2, 1234
+    D = 2 + 6 * (2 * L - 1) + 8 + 2
+    actors = [PO.Net(13, 1, 1), PO.Net(13, 1, 1), PO.Net(D, 2, 2)]
+    critics = [PO.Net(13, 1, 0), PO.Net(13, 1, 0), PO.Net(D, 1, 0)]
+    opt_a = [torch.optim.Adam(n.parameters(), lr=3e-4) for n in actors]
+    opt_c = [torch.optim.Adam(n.parameters(), lr=1e-3) for n in critics]
+    env = O.OracleVecEnv("coop_scalable", n_envs, 4, 3, L, seed=seed, store_f32=False)
     t0 = time.perf_counter()
-    for t in range(n_steps):
-        env.step(pool[t % 4], autoreset=True)
+    sds = [{k: v.detach().clone() for k, v in n.state_dict().items()} for n in actors]
+    b = PO.rollout_episode(env, *sds, seed, np.arange(n_envs), P, L)
+    rtg = PO.reward_to_go(b["rew"])
+    t_roll = time.perf_counter() - t0
+    n_samples = 0
+    for k in (0, 1):                                                        # cross, wait (PY:868-877)
+        m = b["route"] == k                                                 # [C, N]
+        if not m.any():
+            continue
+        st, ac, lp, rt = b["obs_c"][:, m], b["act"][:, m], b["logp"][:, m], rtg[:, m]
+        st, ac, lp, rt = st.reshape(-1, 13), ac.reshape(-1), lp.reshape(-1), rt.reshape(-1)
+        n_samples += st.shape[0]
+        for _ in range(10):
+            PO.train_step_c(actors[k], critics[k], opt_a[k], opt_c[k], st, ac, lp, rt)
+    m = b["exist"]                                                          # one choice sample per existing car (PY:504-507)
+    n_samples += int(m.sum())
+    for _ in range(10):
+        PO.train_step_d(actors[2], critics[2], opt_a[2], opt_c[2], b["obs_d"][m], b["act_d"][m], b["logp_d"][m], b["rew_d"][m])
     dt = time.perf_counter() - t0
-    s = env.get_state()
-    active = float((s["env_i"][:, 1] + s["env_i"][:, 2]).mean())
-    return n_envs * n_steps / dt, dt, active
+    return n_samples / dt, dt, t_roll, n_samples
+
+
+def ppo_roofline(flops, tot_ms, world):
+    """Useful flops of the policy MLPs (last iteration's sample counts, all ranks) over the whole iteration time,
+    against the measured dense bf16 tensor throughput (the roofline the brief names for the policy GEMMs; the
+    kernels compute in fp32 / 3xTF32, so three tensor-core products per useful one)."""
+    peak = None
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops_sustained"])
+        src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
+    except Exception:
+        peak, src = 1359.2, "fallback (B200_PROFILING.md)"
+    ach = flops / (tot_ms * 1e-3) / 1e12 / world
+    return {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+            "peak_source": src, "kernel": "k_ppo_grad_tc (78 % of an iteration) + k_policy_act",
+            "note": "useful fp32 flops per GPU of update (54.5 kflop/sample/epoch) and rollout inference / iteration time"}
+
+
+def bind_to_gpu_numa_node(torch, local):
+    """Pin this rank to the CPUs of the NUMA node its GPU hangs off (sysfs), before any pinned buffer is allocated, so
+    the host side of the end-to-end copies is node-local (at 8 ranks the host memory system is the e2e ceiling)."""
+    try:
+        p = torch.cuda.get_device_properties(local)
+        bdf = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read())
+        if node < 0:
+            return {"numa_node": None}
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return {"numa_node": node, "cpus_bound": len(cpus)}
+    except Exception as e:   # no sysfs / no permission: run unbound
+        return {"numa_node": None, "note": type(e).__name__}
 
 
 def run_ppo(mh, torch, dist, world, rank, dev, n_envs, iters, warm=1):
@@ -157,39 +254,60 @@ def run_ppo(mh, torch, dist, world, rank, dev, n_envs, iters, warm=1):
         t_roll += e0.elapsed_time(e1); t_upd += e1.elapsed_time(e2)
         samples += sum(r.counts())
     launches = mh.launch_count() - n0
-    t = torch.tensor([t_roll + t_upd, t_roll, t_upd, float(samples)], dtype=torch.float64, device=dev)
+    # useful flops of the policy networks: forward 2*(D*32 + 32*64 + 64*32 + 32*out), backward = 2 x forward
+    fwd = lambda D, out: 2.0 * (D * 32 + 32 * 64 + 64 * 32 + 32 * out)
+    n_c, n_w, n_d = [float(x) for x in r.counts()]
+    ped_mean = float(env.get_state()["env_i"][:, 1].float().mean().item())       # existing pedestrians per env (current episode)
+    fl_update = 10.0 * ((n_c + n_w) * 3.0 * 2.0 * fwd(13, 1) + n_d * 3.0 * (fwd(30, 2) + fwd(30, 1)))
+    fl_roll = n_envs * (80.0 * 4 * ped_mean * fwd(13, 1) + 4 * 3 * fwd(30, 2))
+    t = torch.tensor([t_roll + t_upd, t_roll, t_upd, float(samples), fl_update + fl_roll], dtype=torch.float64, device=dev)
     if world > 1:
         mx = t.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX); dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        tot_ms, roll_ms, upd_ms, samples = mx[0].item(), mx[1].item(), mx[2].item(), t[3].item()
+        tot_ms, roll_ms, upd_ms, samples, flops = mx[0].item(), mx[1].item(), mx[2].item(), t[3].item(), t[4].item() * iters
     else:
-        tot_ms, roll_ms, upd_ms, samples = [x.item() for x in t]
+        tot_ms, roll_ms, upd_ms, samples, flops = [x.item() for x in t]
+        flops *= iters
     del algo, env
     torch.cuda.empty_cache()
     return {"samples_per_s": samples / (tot_ms * 1e-3), "unit": "PPO samples/s (cross + wait + choice samples consumed by the update)",
             "iteration_ms": tot_ms / iters, "rollout_ms": roll_ms / iters, "update_ms": upd_ms / iters, "iterations": iters,
             "samples_per_iteration": samples / iters, "n_envs_per_gpu": n_envs, "update_epochs": "10 x (cross, wait) + 10 x choice",
             "gpu_launches": int(launches),
+            "roofline": ppo_roofline(flops, tot_ms, world),
             "config": "Coop-MH-PPO-scalable on Env_hybrid_multi_coop_scalable nb_car=4 nb_ped=3 nb_lines=2, %d envs/GPU x 80 steps" % n_envs}
 
 
+def workload_config(variant, nb_car, nb_ped, nb_lines, n_envs, state_bytes=None, flushed=True):
+    """`config` of the JSON line -- the same dict for both arms (the driver compares them)."""
+    if state_bytes is None:
+        C = 2 * nb_lines if variant == "coop_scalable" else (2 * nb_car if "4cars" in variant else nb_car)
+        state_bytes = 32 * C + 48 * nb_ped + 16
+    return {"workload": "Env_hybrid_multi_%s nb_car=%d nb_ped=%d nb_lines=%d, %d envs/GPU, env.step with auto-reset, "
+                        "acc ~ U(-4,2) per step, lights held per episode" % (variant, nb_car, nb_ped, nb_lines, n_envs),
+            "l2": "GPU arm: flushed, an untimed 256 MiB memset (2x the 126 MB L2) runs between timed steps; the per-step working set "
+                  "is ~150 MB" if flushed else "GPU arm: not flushed",
+            "state_bytes_per_env": state_bytes, "parallelism": "env shards per rank, no data-path collective"}
+
+
 def run_reference(args, wl):
+    """--impl reference: the reference's own CPU implementation of the path.  The reference is single-process Python and
+    cannot travel to the GPU box; this arm times its pinned C restatement (oracle/mhppo_oracle.c) on all host threads,
+    on the SAME workload, warm-up and step count as the GPU arm (whole batch per step, same window of the episode)."""
     variant, nb_car, nb_ped, nb_lines, n_envs = wl
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    n_sample = 16384                      # bounded sample of the n_envs-per-GPU batch, per step
-    rate, dt, active = cpu_port_rate(variant, nb_car, nb_ped, nb_lines, n_sample, max(args.steps, 1), threads=cores)
-    B, C, nobs = algorithmic_bytes(variant, nb_car, nb_ped, nb_lines)
-    sample = "%d envs x %d steps of the %d-env batch, C oracle port (oracle/mhppo_oracle.c), %d threads" % (
-        n_sample, args.steps, n_envs, cores)
+    W, K = max(args.warmup, 3), args.steps
+    rate, timed, active, rounds = cpu_port_run(variant, nb_car, nb_ped, nb_lines, n_envs, W, K, threads=cores, min_seconds=5.0)
+    sample = "%d envs x %d steps after %d warm-up steps, %d round(s) from a fresh reset (%.1f s timed), C oracle port " \
+             "(oracle/mhppo_oracle.c), %d threads" % (n_envs, K, W, rounds, timed, cores)
     val = rate * active
     line = {"metric": "agent-steps/sec (env.step)", "value": val, "unit": "agent-steps/s", "impl": "reference",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": 3, "ms_per_step": 1e3 * dt / args.steps,
+            "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": 1e3 * timed / (K * rounds),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "Env_hybrid_multi_%s nb_car=%d nb_ped=%d nb_lines=%d, %d envs/GPU, env.step" % (
-                variant, nb_car, nb_ped, nb_lines, n_envs)},
-            "env_steps_per_s": rate, "active_agents_per_env": active,
+            "config": workload_config(variant, nb_car, nb_ped, nb_lines, n_envs, flushed=not args.no_flush),
+            "env_steps_per_s": rate, "active_agents_per_env": active, "rounds": rounds,
             "cpu_baseline": {"value": val, "unit": "agent-steps/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "the reference is single-process Python (one env, global RNG, GIL) and is not shippable to the GPU box; "
@@ -251,6 +369,7 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    host_binding = bind_to_gpu_numa_node(torch, local) if world > 1 else {"numa_node": None, "note": "single rank: unbound"}
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     W = max(args.warmup, 3)
@@ -261,17 +380,24 @@ def main():
     A = env.n_action
     state_bytes, n_obs_env, n_lead_env = env.state_bytes_per_env, env.n_obs, env.n_lead
     g = torch.Generator(device=dev).manual_seed(1000 + rank)
-    pool = []
-    for _ in range(4):   # synthetic actions resident in HBM: acc ~ U(-4,2), light in {-1,+1}
-        # [N, A] view of a component-major buffer: the layout the rollout kernels hand to env.step (coalesced reads)
-        a = torch.empty(n_envs, A, device=dev) if args.row_major_actions else torch.empty(A, n_envs, device=dev).t()
-        a[:, :A // 2] = torch.rand(n_envs, A // 2, device=dev, generator=g) * 6 - 4
-        a[:, A // 2:] = (torch.rand(n_envs, A // 2, device=dev, generator=g) < 0.5).float() * 2 - 1
-        pool.append(a)
+    # synthetic actions resident in HBM: acc ~ U(-4,2) fresh every step (4 draws, cycled), light in {-1,+1}
+    # drawn once per episode and held (2 light draws, alternating from one 80-step episode to the next)
+    lights = [(torch.rand(n_envs, A // 2, device=dev, generator=g) < 0.5).float() * 2 - 1 for _ in range(2)]
+    acts = []
+    for e in range(2):
+        row = []
+        for _ in range(4):
+            # [N, A] view of a component-major buffer: the layout the rollout kernels hand to env.step (coalesced reads)
+            a = torch.empty(n_envs, A, device=dev) if args.row_major_actions else torch.empty(A, n_envs, device=dev).t()
+            a[:, :A // 2] = torch.rand(n_envs, A // 2, device=dev, generator=g) * 6 - 4
+            a[:, A // 2:] = lights[e]
+            row.append(a)
+        acts.append(row)
+    pick = lambda lst, t: lst[(t // EPISODE) % 2][t % 4]      # t = steps since the reset
     flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     env.reset()
     for t in range(W):
-        env.step(pool[t % 4])
+        env.step(pick(acts, t))
     torch.cuda.synchronize()
 
     def barrier():
@@ -290,7 +416,7 @@ def main():
         if flush is not None:
             flush.zero_()
         ev[t][0].record()
-        env.step(pool[t % 4])
+        env.step(pick(acts, W + t))
         ev[t][1].record()
     barrier()
     wall = time.perf_counter() - wall0
@@ -299,17 +425,17 @@ def main():
 
     # ---- end-to-end region: host buffers through the reference-facing call -------------------------
     Ke = max(8, min(K, 40))
-    act_h = [p.cpu().pin_memory() for p in pool]
+    act_h = [[p.cpu().pin_memory() for p in row] for row in acts]
     obs_h = torch.empty(n_envs, env.n_obs).pin_memory()
     rew_h = torch.empty(n_envs, env.n_lead).pin_memory()
     rl_h = torch.empty(n_envs, env.n_lead).pin_memory()
     done_h = torch.empty(n_envs, dtype=torch.uint8).pin_memory()
     for t in range(3):
-        env.step_host(act_h[t % 4], obs_h, rew_h, rl_h, done_h)
+        env.step_host(pick(act_h, W + K + t), obs_h, rew_h, rl_h, done_h)
     barrier()
     e0 = time.perf_counter()
     for t in range(Ke):
-        env.step_host(act_h[t % 4], obs_h, rew_h, rl_h, done_h)
+        env.step_host(pick(act_h, W + K + 3 + t), obs_h, rew_h, rl_h, done_h)
     barrier()
     e2e_s = time.perf_counter() - e0
     h2d = n_envs * A * 4
@@ -318,7 +444,7 @@ def main():
     st = env.get_state()
     active = float((st["env_i"][:, 1] + st["env_i"][:, 2]).float().mean().item())
     flushed = flush is not None
-    del st, env, flush, pool, act_h, obs_h
+    del st, env, flush, acts, act_h, obs_h
     torch.cuda.empty_cache()
     ppo = run_ppo(mhppo_b200, torch, dist, world, rank, dev, args.ppo_envs, args.ppo_iters) if args.ppo_envs > 0 and args.ppo_iters > 0 else None
     clocks = sampler.stop()        # sampled every 200 ms from the start of the device-timed region to the end of the PPO section
@@ -339,11 +465,7 @@ def main():
             "metric": "agent-steps/sec (env.step)", "value": env_steps * active, "unit": "agent-steps/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": kern_ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "Env_hybrid_multi_%s nb_car=%d nb_ped=%d nb_lines=%d, %d envs/GPU, env.step with in-kernel auto-reset" % (
-                variant, nb_car, nb_ped, nb_lines, n_envs),
-                "l2": "flushed: an untimed 256 MiB memset (2x the 126 MB L2) runs between timed steps; the per-step working set is ~150 MB"
-                if flushed else "not flushed", "state_bytes_per_env": state_bytes,
-                "parallelism": "env shards per rank, no data-path collective"},
+            "config": workload_config(variant, nb_car, nb_ped, nb_lines, n_envs, state_bytes, flushed),
             "env_steps_per_s": env_steps, "slot_agent_steps_per_s": env_steps * (C + nb_ped),
             "active_agents_per_env": active, "wall_s_timed_region": wall, "gpu_launches": int(launches),
             "clocks": clocks,
@@ -352,19 +474,27 @@ def main():
                          "traffic_source": "profiles/round1_env_step_ncu_metrics.json (ncu --set full, bytes per launch)", "algorithmic_bytes_per_env_step": B, "peak_source": peak_src,
                          "kernel": "k_env_step<%s>" % variant},
             "e2e": {"value": world * n_envs * Ke / e2e_s * active, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "steps": Ke, "call": "mhppo_env_step_host (pinned host buffers, H2D+kernel+D2H+sync)"},
+                    "d2h_bytes_per_step": d2h, "steps": Ke, "pcie_gbs_per_gpu": (h2d + d2h) * Ke / e2e_s / 1e9, "host_binding": host_binding,
+                    "call": "mhppo_env_step_host (pinned host buffers; env range in slices over 3 streams: H2D, kernel and D2H overlap)"},
         }
         if ppo is not None:
             line["ppo"] = ppo
         if not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            ns = 16384
-            r0, dt0, _ = cpu_port_rate(variant, nb_car, nb_ped, nb_lines, ns, 20, threads=cores)      # calibration
-            ks = int(max(40, min(20000, 12.0 * r0 / ns)))                                            # ~12 s of CPU work
-            rate, dt, act_cpu = cpu_port_rate(variant, nb_car, nb_ped, nb_lines, ns, ks, threads=cores)
+            # the same procedure as `--impl reference`: whole batch, same warm-up and window, >= 10 s of timed CPU work
+            rate, dt, act_cpu, rounds = cpu_port_run(variant, nb_car, nb_ped, nb_lines, n_envs, W, K, threads=cores, min_seconds=10.0)
             line["cpu_baseline"] = {"value": rate * act_cpu, "unit": "agent-steps/s", "cores": cores, "kind": "port",
-                                    "sample": "%d envs x %d steps of the same workload, C oracle port on all host threads (%.1f s)" % (ns, ks, dt),
+                                    "sample": "%d envs x %d steps after %d warm-up steps, %d round(s) from a fresh reset (%.1f s timed), "
+                                              "C oracle port on all host threads" % (n_envs, K, W, rounds, dt),
                                     "env_steps_per_s": rate}
+            if ppo is not None:
+                n_cpu = 256
+                r_ppo, dt_ppo, dt_roll, n_s = cpu_ppo_rate(n_cpu)
+                ppo["cpu_baseline"] = {"value": r_ppo, "unit": "PPO samples/s", "cores": cores, "kind": "port",
+                                       "sample": "one iteration at %d envs (%d samples, %.1f s of which rollout %.1f s): vectorised numpy/torch "
+                                                 "restatement of Env_rollout + Algo_PPO (oracle/ppo_oracle.py) over the C env port; the "
+                                                 "unmodified per-sample Python reference does 544 samples/s (BASELINE.md section 2)" % (
+                                                     n_cpu, n_s, dt_ppo, dt_roll)}
         emit(line)
     if world > 1:
         dist.destroy_process_group()

@@ -96,7 +96,9 @@ int mhppo_env_step(void *handle, mhppo_view actions_dev, mhppo_view obs_dev, mhp
 
 /* Same call for HOST buffers in the reference's own layout (row-major [n_envs, width], what
  * env.step(np.ndarray) takes and returns): copies actions host->device, steps, copies the results
- * back and synchronises `stream`.  Pinned staging lives in the handle. */
+ * back and synchronises `stream`.  The env range is processed in slices on streams owned by the handle so that the
+ * device->host copy of one slice overlaps the host->device copy and the kernel of the next; the device staging
+ * buffers live in the handle, the host buffers are the caller's (pin them for full PCIe rate). */
 int mhppo_env_step_host(void *handle, const float *actions_host, float *obs_host, float *rewards_host,
                         float *reward_light_host, uint8_t *done_host, int autoreset, void *stream);
 int mhppo_env_reset_host(void *handle, float *obs_host, void *stream);

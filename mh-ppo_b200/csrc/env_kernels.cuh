@@ -33,8 +33,8 @@ __global__ void __launch_bounds__(kEnvBlock, kEnvMinBlocks) k_env_step(const __g
                                                                            const __grid_constant__ RngKey key, const __grid_constant__ StepIO io) {
     extern __shared__ __align__(16) unsigned char step_smem[];
     StepShared<MC> &sh = *reinterpret_cast<StepShared<MC> *>(step_smem);
-    const int64_t n = (int64_t)blockIdx.x * kEnvBlock + threadIdx.x;
-    if (n >= a.N) return;
+    const int64_t n = io.n_begin + (int64_t)blockIdx.x * kEnvBlock + threadIdx.x;
+    if (n >= io.n_end) return;
     env_step_thread<V, MC, MP, kEnvBlock>(a, c, key, io, n, sh.cars, (int)threadIdx.x);
 }
 

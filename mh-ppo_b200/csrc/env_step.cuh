@@ -55,6 +55,7 @@ struct StepIO {
     mhppo_view actions, obs, rewards, reward_light, term_obs;
     uint8_t *done;
     int autoreset;
+    int64_t n_begin, n_end;        // env range of this launch ([0, N) except for the sliced host-buffer path)
 };
 
 // ---------------------------------------------------------------------------------------------

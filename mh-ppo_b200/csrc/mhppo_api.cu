@@ -29,6 +29,10 @@ static int cuda_fail(cudaError_t e, const char *what) {
         if (e_ != cudaSuccess) return cuda_fail(e_, #call);        \
     } while (0)
 
+constexpr int kHostStreams = 3;          // slices of the host-buffer step rotate over these streams
+constexpr int64_t kHostSliceMin = 16384;  // envs per slice at least (a slice must still fill the GPU)
+constexpr int kHostSlicesMax = 8;
+
 struct EnvHandle {
     mhppo_env_cfg cfg;
     EnvConst c;
@@ -37,8 +41,11 @@ struct EnvHandle {
     const EnvKernelEntry *k;
     void *arena_base;
     size_t arena_bytes;
-    // staging for the *_host entry points (row-major, reference layout)
+    // device staging for the *_host entry points (row-major, reference layout) and the streams / events that
+    // pipeline slices of the env range through H2D -> kernel -> D2H
     float *d_act, *d_obs, *d_rew, *d_rl; uint8_t *d_done;
+    cudaStream_t hs[kHostStreams];
+    cudaEvent_t ev_in, ev_out[kHostStreams];
 };
 
 __global__ void __launch_bounds__(kEnvBlock) k_env_export(EnvArena a, EnvConst c, DumpPtrs d) {
@@ -165,6 +172,12 @@ int mhppo_env_create(const mhppo_env_cfg *cfg, void **handle) {
     if (e == cudaSuccess) e = cudaMalloc(&h->d_rl, nb * c.nlead);
     if (e == cudaSuccess) e = cudaMalloc(&h->d_done, (size_t)N);
     if (e != cudaSuccess) { mhppo_env_destroy(h); return cuda_fail(e, "cudaMalloc(host-API staging)"); }
+    for (int i = 0; i < kHostStreams && e == cudaSuccess; ++i) {
+        e = cudaStreamCreateWithFlags(&h->hs[i], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_out[i], cudaEventDisableTiming);
+    }
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming);
+    if (e != cudaSuccess) { mhppo_env_destroy(h); return cuda_fail(e, "cudaStreamCreate(host-API pipeline)"); }
     *handle = h;
     return MHPPO_OK;
 }
@@ -174,6 +187,11 @@ int mhppo_env_destroy(void *handle) {
     if (!h) return MHPPO_OK;
     cudaFree(h->arena_base); cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_rew); cudaFree(h->d_rl);
     cudaFree(h->d_done);
+    for (int i = 0; i < kHostStreams; ++i) {
+        if (h->hs[i]) cudaStreamDestroy(h->hs[i]);
+        if (h->ev_out[i]) cudaEventDestroy(h->ev_out[i]);
+    }
+    if (h->ev_in) cudaEventDestroy(h->ev_in);
     delete h;
     return MHPPO_OK;
 }
@@ -210,7 +228,7 @@ int mhppo_env_step(void *handle, mhppo_view actions_dev, mhppo_view obs_dev, mhp
     if (!actions_dev.ptr) return fail(MHPPO_EINVAL, "actions are required");
     StepIO io;
     io.actions = actions_dev; io.obs = obs_dev; io.rewards = rewards_dev; io.reward_light = reward_light_dev;
-    io.term_obs = term_obs_dev; io.done = done_dev; io.autoreset = autoreset;
+    io.term_obs = term_obs_dev; io.done = done_dev; io.autoreset = autoreset; io.n_begin = 0; io.n_end = h->a.N;
     auto fn = h->k->step;
     fn<<<grid_for(h->a.N), kEnvBlock, h->k->step_smem, (cudaStream_t)stream>>>(h->a, h->c, h->key, io);
     g_launches.fetch_add(1);
@@ -236,17 +254,43 @@ int mhppo_env_step_host(void *handle, const float *actions_host, float *obs_host
     if (!h || !actions_host) return fail(MHPPO_EINVAL, "null argument");
     cudaStream_t s = (cudaStream_t)stream;
     const int64_t N = h->a.N; const EnvConst &c = h->c;
-    CK(cudaMemcpyAsync(h->d_act, actions_host, sizeof(float) * c.nA * N, cudaMemcpyHostToDevice, s));
-    mhppo_view act = { h->d_act, c.nA, 1 }, none = { nullptr, 0, 0 };
-    mhppo_view obs = obs_host ? mhppo_view{ h->d_obs, c.nobs, 1 } : none;
-    mhppo_view rew = rewards_host ? mhppo_view{ h->d_rew, c.nlead, 1 } : none;
-    mhppo_view rl = reward_light_host ? mhppo_view{ h->d_rl, c.nlead, 1 } : none;
-    int rc = mhppo_env_step(handle, act, obs, rew, rl, done_host ? h->d_done : nullptr, autoreset, none, stream);
-    if (rc) return rc;
-    if (obs_host) CK(cudaMemcpyAsync(obs_host, h->d_obs, sizeof(float) * c.nobs * N, cudaMemcpyDeviceToHost, s));
-    if (rewards_host) CK(cudaMemcpyAsync(rewards_host, h->d_rew, sizeof(float) * c.nlead * N, cudaMemcpyDeviceToHost, s));
-    if (reward_light_host) CK(cudaMemcpyAsync(reward_light_host, h->d_rl, sizeof(float) * c.nlead * N, cudaMemcpyDeviceToHost, s));
-    if (done_host) CK(cudaMemcpyAsync(done_host, h->d_done, (size_t)N, cudaMemcpyDeviceToHost, s));
+    // The env range is cut into slices; slice k runs H2D(actions) -> kernel -> D2H(results) on stream k % 3, so the
+    // D2H of one slice (the long pole: n_obs + 2 n_lead floats per env over PCIe) overlaps the H2D and the kernel of the
+    // next ones (the two copy engines and the SMs work at the same time).  Rows of a slice are contiguous in every
+    // host buffer: one cudaMemcpyAsync per buffer and slice.
+    int ns = (int)(N / kHostSliceMin);
+    ns = ns < 1 ? 1 : (ns > kHostSlicesMax ? kHostSlicesMax : ns);
+    const int64_t per = ((N + ns - 1) / ns + kEnvBlock - 1) / kEnvBlock * kEnvBlock;
+    CK(cudaEventRecord(h->ev_in, s));                                // work already queued on the caller's stream comes first
+    const int used = ns < kHostStreams ? ns : kHostStreams;
+    for (int i = 0; i < used; ++i) CK(cudaStreamWaitEvent(h->hs[i], h->ev_in, 0));
+    StepIO io;
+    const mhppo_view none = { nullptr, 0, 0 };
+    io.actions = mhppo_view{ h->d_act, c.nA, 1 };
+    io.obs = obs_host ? mhppo_view{ h->d_obs, c.nobs, 1 } : none;
+    io.rewards = rewards_host ? mhppo_view{ h->d_rew, c.nlead, 1 } : none;
+    io.reward_light = reward_light_host ? mhppo_view{ h->d_rl, c.nlead, 1 } : none;
+    io.term_obs = none; io.done = done_host ? h->d_done : nullptr; io.autoreset = autoreset;
+    auto fn = h->k->step;
+    for (int k = 0; k < ns; ++k) {
+        const int64_t n0 = (int64_t)k * per, n1 = (n0 + per < N) ? n0 + per : N;
+        if (n0 >= n1) break;
+        cudaStream_t q = h->hs[k % kHostStreams];
+        const size_t cnt = (size_t)(n1 - n0);
+        CK(cudaMemcpyAsync(h->d_act + n0 * c.nA, actions_host + n0 * c.nA, sizeof(float) * c.nA * cnt, cudaMemcpyHostToDevice, q));
+        io.n_begin = n0; io.n_end = n1;
+        fn<<<grid_for(n1 - n0), kEnvBlock, h->k->step_smem, q>>>(h->a, h->c, h->key, io);
+        g_launches.fetch_add(1);
+        CK(cudaGetLastError());
+        if (obs_host) CK(cudaMemcpyAsync(obs_host + n0 * c.nobs, h->d_obs + n0 * c.nobs, sizeof(float) * c.nobs * cnt, cudaMemcpyDeviceToHost, q));
+        if (rewards_host) CK(cudaMemcpyAsync(rewards_host + n0 * c.nlead, h->d_rew + n0 * c.nlead, sizeof(float) * c.nlead * cnt, cudaMemcpyDeviceToHost, q));
+        if (reward_light_host) CK(cudaMemcpyAsync(reward_light_host + n0 * c.nlead, h->d_rl + n0 * c.nlead, sizeof(float) * c.nlead * cnt, cudaMemcpyDeviceToHost, q));
+        if (done_host) CK(cudaMemcpyAsync(done_host + n0, h->d_done + n0, cnt, cudaMemcpyDeviceToHost, q));
+    }
+    for (int i = 0; i < used; ++i) {                                  // the caller's stream continues after every slice
+        CK(cudaEventRecord(h->ev_out[i], h->hs[i]));
+        CK(cudaStreamWaitEvent(s, h->ev_out[i], 0));
+    }
     CK(cudaStreamSynchronize(s));
     return MHPPO_OK;
 }

@@ -759,23 +759,64 @@ static void job_run(Job *j) {
         }
     }
 }
-static void *job_thread(void *p) { job_run((Job *)p); return NULL; }
+/* Persistent worker pool (one per process, grown on demand): the workers sleep on a condition variable between
+ * batched calls, so a step does not pay thread creation; envs are handed out in chunks from a shared cursor. */
+#define POOL_MAX 256
+#define POOL_CHUNK 256
+typedef struct {
+    pthread_mutex_t mu; pthread_cond_t go, fin;
+    pthread_t th[POOL_MAX];
+    int n_threads, active, pending; unsigned long gen;
+    Job job; int64_t N; volatile int64_t cursor;
+} Pool;
+static Pool g_pool = { PTHREAD_MUTEX_INITIALIZER, PTHREAD_COND_INITIALIZER, PTHREAD_COND_INITIALIZER };
+
+static void pool_work(Pool *p) {
+    for (;;) {
+        const int64_t lo = __atomic_fetch_add(&p->cursor, POOL_CHUNK, __ATOMIC_RELAXED);
+        if (lo >= p->N) break;
+        Job j = p->job;
+        j.lo = lo; j.hi = lo + POOL_CHUNK < p->N ? lo + POOL_CHUNK : p->N;
+        job_run(&j);
+    }
+}
+static void *pool_thread(void *arg) {
+    Pool *p = &g_pool; const int id = (int)(intptr_t)arg;
+    unsigned long seen = 0;
+    pthread_mutex_lock(&p->mu);
+    for (;;) {
+        while (p->gen == seen) pthread_cond_wait(&p->go, &p->mu);
+        seen = p->gen;
+        if (id >= p->active) continue;
+        pthread_mutex_unlock(&p->mu);
+        pool_work(p);
+        pthread_mutex_lock(&p->mu);
+        if (--p->pending == 0) pthread_cond_signal(&p->fin);
+    }
+    return NULL;
+}
 
 static void run_parallel(Job *proto) {
     OHandle *h = proto->h;
     int nt = h->c.n_threads > 0 ? h->c.n_threads : (int)sysconf(_SC_NPROCESSORS_ONLN);
     if (nt < 1) nt = 1;
-    if (nt > 256) nt = 256;
-    if ((int64_t)nt > h->N) nt = (int)h->N;
+    if (nt > POOL_MAX) nt = POOL_MAX;
+    if ((int64_t)nt * POOL_CHUNK > h->N) nt = (int)((h->N + POOL_CHUNK - 1) / POOL_CHUNK);
     if (nt <= 1) { proto->lo = 0; proto->hi = h->N; job_run(proto); return; }
-    Job jobs[256]; pthread_t th[256];
-    int64_t chunk = (h->N + nt - 1) / nt;
-    for (int t = 0; t < nt; ++t) {
-        jobs[t] = *proto;
-        jobs[t].lo = t * chunk; jobs[t].hi = (t + 1) * chunk < h->N ? (t + 1) * chunk : h->N;
-        pthread_create(&th[t], NULL, job_thread, &jobs[t]);
+    Pool *p = &g_pool;
+    pthread_mutex_lock(&p->mu);
+    while (p->n_threads < nt - 1) {              /* the caller is worker 0 */
+        pthread_create(&p->th[p->n_threads], NULL, pool_thread, (void *)(intptr_t)p->n_threads);
+        pthread_detach(p->th[p->n_threads]);
+        p->n_threads++;
     }
-    for (int t = 0; t < nt; ++t) pthread_join(th[t], NULL);
+    p->job = *proto; p->N = h->N; p->cursor = 0; p->active = nt - 1; p->pending = nt - 1; p->gen++;
+    pthread_cond_broadcast(&p->go);
+    pthread_mutex_unlock(&p->mu);
+    pool_work(p);
+    pthread_mutex_lock(&p->mu);
+    while (p->pending != 0) pthread_cond_wait(&p->fin, &p->mu);
+    pthread_mutex_unlock(&p->mu);
 }
 
 void mho_reset(void *hh, const uint8_t *mask, float *obs) {

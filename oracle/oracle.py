@@ -105,6 +105,11 @@ class OracleVecEnv:
         lib().mho_reset(self._h, _ptr(m), _ptr(obs))
         return obs
 
+    def step_into(self, actions, obs, rew, rl, done, autoreset=True):
+        """env.step into caller-owned buffers (float64 [N, A] actions, float32 obs, float64 rewards / reward_light,
+        uint8 done): the timed loop of bench.py's CPU legs, no allocation per step."""
+        lib().mho_step(self._h, _ptr(actions), _ptr(obs), _ptr(rew), _ptr(rl), _ptr(done), int(autoreset), None)
+
     def step(self, actions, autoreset=False, want_term_obs=False):
         a = np.ascontiguousarray(actions, np.float64).reshape(self.N, self.n_action)
         obs = np.empty((self.N, self.n_obs), np.float32)

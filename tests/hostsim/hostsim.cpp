@@ -35,7 +35,7 @@ static void sim_step(Sim *s, mhppo_view actions, mhppo_view obs, mhppo_view rewa
                      int autoreset, mhppo_view term_obs) {
     StepIO io;
     io.actions = actions; io.obs = obs; io.rewards = rewards; io.reward_light = reward_light; io.term_obs = term_obs;
-    io.done = done; io.autoreset = autoreset;
+    io.done = done; io.autoreset = autoreset; io.n_begin = 0; io.n_end = s->a.N;
     RngKey key; key.k0 = s->k0; key.k1 = s->k1; key.env_id0 = s->env_id0;
     CarSlots<MC, 1> cars;
     for (int64_t n = 0; n < s->a.N; ++n) env_step_thread<V, MC, MP, 1>(s->a, s->c, key, io, n, cars, 0);   // the kernel's thread body

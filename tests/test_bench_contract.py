@@ -9,7 +9,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_reference_arm_prints_one_json_line():
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "4", "--envs", "8192"],
                        capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.splitlines() if l.strip()]
@@ -20,7 +20,8 @@ def test_reference_arm_prints_one_json_line():
               "cpu_baseline", "e2e"):
         assert k in d, k
     assert d["higher_is_better"] is True and d["scaling"] == "weak" and d["vs_baseline"] is None
-    assert d["value"] > 0 and d["warmup"] >= 3
+    assert d["value"] > 0 and d["warmup"] == 4 and d["steps"] == 2      # the arm honours --warmup / --steps
+    assert "8192 envs/GPU" in d["config"]["workload"] and "8192 envs x 2 steps" in d["cpu_baseline"]["sample"]
     assert "workload" in d["config"] and "model" not in d["config"]
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0

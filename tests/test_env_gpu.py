@@ -86,11 +86,13 @@ def test_gym_layout_and_device_layout_agree(cuda_env_cls):
         assert_equal("rl", al, rl.cpu().numpy()); assert_equal("done", ad, done.cpu().numpy().astype(bool))
 
 
-def test_host_buffer_entry_point(cuda_env_cls):
-    """mhppo_env_step_host (numpy-in / numpy-out convention of env.step) == device entry point."""
-    N = 777
-    a_env = cuda_env_cls("coop", N, 2, 1, 2, seed=11)
-    b_env = cuda_env_cls("coop", N, 2, 1, 2, seed=11)
+@pytest.mark.parametrize("cfg", [("coop", 777, 2, 1, 2), ("coop_scalable", 50001, 4, 3, 2)], ids=["one_slice", "three_slices"])
+def test_host_buffer_entry_point(cuda_env_cls, cfg):
+    """mhppo_env_step_host (numpy-in / numpy-out convention of env.step) == device entry point; the larger case runs
+    through the sliced, three-stream H2D -> kernel -> D2H pipeline (ragged last slice)."""
+    v, N, c, p, l = cfg
+    a_env = cuda_env_cls(v, N, c, p, l, seed=11)
+    b_env = cuda_env_cls(v, N, c, p, l, seed=11)
     o0 = a_env.reset()
     e = b_env.env
     obs_h = torch.zeros(N, e.n_obs).pin_memory(); rew_h = torch.zeros(N, e.n_lead).pin_memory()
