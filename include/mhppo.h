@@ -85,6 +85,11 @@ int mhppo_env_get_dims(void *handle, mhppo_env_dims *dims);
  * mask_dev: uint8[n_envs] or NULL (= all). obs receives the first observation of reset envs only. */
 int mhppo_env_reset(void *handle, const uint8_t *mask_dev, mhppo_view obs_dev, void *stream);
 
+/* Crosswalk_hybrid_multi_*.get_state (SC:960-969): observation of the current state without stepping (after an
+ * import_state / state injection).  As in the reference, get_data folds the current gap into every pedestrian's
+ * running-min `delta` (SC:457), i.e. the call is not idempotent on that one field. */
+int mhppo_env_observe(void *handle, mhppo_view obs_dev, void *stream);
+
 /* Crosswalk_hybrid_multi_*.step  (SC:789-878, CO:745-832, ST:754, NA:736, C4:783-844, C42:799-860).
  * actions [n_envs,n_action]; obs [n_envs,n_obs]; rewards, reward_light (= env.reward_light, SC:846)
  * [n_envs,n_lead]; done uint8[n_envs].  autoreset != 0: a done env is re-initialised inside the same
@@ -145,6 +150,11 @@ typedef struct mhppo_rollout_cfg {
     int64_t env_id0;
 } mhppo_rollout_cfg;
 
+/* Gaussian head of the cross / wait actors and its exploration noise, for the calling thread's later rollout / update calls:
+ * mu = tanh(z) * std + mean (Model_PPO head type 1, PY:88-90; the driver derives mean = (car_b[1,0] + car_b[0,0]) / 2 and
+ * std = (car_b[1,0] - car_b[0,0]) / 2, PY:1044-1045), a ~ N(mu, variance) (Algo_PPO.value_std, PY:726-729), acc_hi = car_b[1,0]
+ * is the start value of the min over pedestrians (PY:436).  Defaults: -1, 3, 0.5, 2. */
+int mhppo_set_gaussian_head(float mean, float std, float variance, float acc_hi);
 int mhppo_net_padded_in(int32_t n_in);
 int mhppo_net_param_count(int32_t n_in);
 

@@ -46,6 +46,7 @@ SYMBOLS = {
     "mhppo_env_get_dims": (C.c_int, [C.c_void_p, C.POINTER(EnvDims)]),
     "mhppo_env_reset": (C.c_int, [C.c_void_p, C.c_void_p, View, C.c_void_p]),
     "mhppo_env_step": (C.c_int, [C.c_void_p, View, View, View, View, C.c_void_p, C.c_int, View, C.c_void_p]),
+    "mhppo_env_observe": (C.c_int, [C.c_void_p, View, C.c_void_p]),
     "mhppo_env_step_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_int, C.c_void_p]),
     "mhppo_env_reset_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -68,6 +69,7 @@ SYMBOLS = {
                        + [C.c_void_p] * 5 + [C.c_float] * 5 + [C.c_void_p] * 4),
     "mhppo_tc_failures": (C.c_int, []),
     "mhppo_set_mlp_mode": (C.c_int, [C.c_int32]),
+    "mhppo_set_gaussian_head": (C.c_int, [C.c_float, C.c_float, C.c_float, C.c_float]),
     "mhppo_tc_selftest": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "mhppo_adam": (C.c_int, [C.c_void_p] * 4 + [C.c_int32] + [C.c_float] * 4 + [C.c_int32, C.c_float, C.c_void_p]),
 }

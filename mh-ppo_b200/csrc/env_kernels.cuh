@@ -51,14 +51,29 @@ __global__ void __launch_bounds__(kEnvBlock) k_env_reset(const __grid_constant__
     reset_and_store<V, MC, MP>(a, c, n, rng, obs);
 }
 
+// Crosswalk_hybrid_multi_*.get_state (SC:960-969): the observation of the CURRENT state, no step.  Like the reference it
+// runs get_data of every car and pedestrian (all car slots are handed to pedestrian.get_data, as in reset), which also
+// folds the current gap into each pedestrian's running-min `delta` (SC:457), so the state is written back.
+template <int V, int MC, int MP>
+__global__ void __launch_bounds__(kEnvBlock) k_env_observe(const __grid_constant__ EnvArena a, const __grid_constant__ EnvConst c, mhppo_view obs) {
+    const int64_t n = (int64_t)blockIdx.x * kEnvBlock + threadIdx.x;
+    if (n >= a.N) return;
+    EnvR<MC, MP> e;
+    load_env<MC, MP>(a, c, n, e);
+    if (obs.ptr) { ViewOut out{obs.ptr + n * obs.env_stride, obs.comp_stride}; write_obs<V, MC, MP>(c, e, true, out); }
+    else { NullOut nul; write_obs<V, MC, MP>(c, e, true, nul); }
+    store_env<MC, MP>(a, c, n, e);
+}
+
 // ---- instantiation table -----------------------------------------------------------------------
 struct EnvKernelEntry {
     int variant, mc, mp, step_smem;
     void (*step)(EnvArena, EnvConst, RngKey, StepIO);
     void (*reset)(EnvArena, EnvConst, RngKey, const uint8_t *, mhppo_view);
+    void (*observe)(EnvArena, EnvConst, mhppo_view);
 };
 
-#define MHPPO_ENV_ENTRY(V, MC, MP) { V, MC, MP, (int)sizeof(StepShared<MC>), k_env_step<V, MC, MP>, k_env_reset<V, MC, MP> }
+#define MHPPO_ENV_ENTRY(V, MC, MP) { V, MC, MP, (int)sizeof(StepShared<MC>), k_env_step<V, MC, MP>, k_env_reset<V, MC, MP>, k_env_observe<V, MC, MP> }
 
 // each env_inst_*.cu defines one of these
 const EnvKernelEntry *env_table_stop(int *n);

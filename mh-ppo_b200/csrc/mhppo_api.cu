@@ -220,6 +220,16 @@ int mhppo_env_reset(void *handle, const uint8_t *mask_dev, mhppo_view obs_dev, v
     return MHPPO_OK;
 }
 
+int mhppo_env_observe(void *handle, mhppo_view obs_dev, void *stream) {
+    EnvHandle *h = (EnvHandle *)handle;
+    if (!h) return fail(MHPPO_EINVAL, "null handle");
+    auto fn = h->k->observe;
+    fn<<<grid_for(h->a.N), kEnvBlock, 0, (cudaStream_t)stream>>>(h->a, h->c, obs_dev);
+    g_launches.fetch_add(1);
+    CK(cudaGetLastError());
+    return MHPPO_OK;
+}
+
 int mhppo_env_step(void *handle, mhppo_view actions_dev, mhppo_view obs_dev, mhppo_view rewards_dev,
                    mhppo_view reward_light_dev, uint8_t *done_dev, int autoreset, mhppo_view term_obs_dev,
                    void *stream) {

@@ -22,6 +22,13 @@
 
 namespace mhppo {
 
+// Gaussian head of the cross / wait actors (Model_PPO head type 1, PY:88-90: tanh(z) * std + mean with mean / std derived
+// from car_b, PY:1044-1045) and the exploration noise N(mu, variance) of PY:726-729 / 451-453 / 795-800:
+// log_prob = -(a - mu)^2 * inv_2var - logp_c, inv_2var = 1 / (2 variance), logp_c = ln(2 pi variance) / 2.
+// Filled on the host by mhppo_set_gaussian_head (defaults: mean -1, std 3, variance 0.5, acc_hi 2).
+struct HeadCfg { float mean, std, sigma, inv_2var, logp_c, acc_hi; };
+
+
 constexpr int H1 = 32, H2 = 64, H3 = 32, OP = 4;
 constexpr int kMlpBlock = 128;
 

@@ -24,10 +24,22 @@ static int padded_in(int n_in) { return n_in <= 16 ? 16 : (n_in <= 32 ? 32 : (n_
 //   1 ffma : exact-fp32 CUDA-core kernels everywhere (cross-check)      2 tc : tcgen05 wherever a kernel exists
 static int g_mlp_mode = []() { const char *e = std::getenv("MHPPO_MLP"); return (e && std::string(e) == "ffma") ? 1 : ((e && std::string(e) == "tc") ? 2 : 0); }();
 static bool use_tc(bool rollout) { return g_mlp_mode == 2 || (g_mlp_mode == 0 && !rollout); }
+static HeadCfg make_head(double mean, double std, double variance, double acc_hi) {
+    HeadCfg h;
+    h.mean = (float)mean; h.std = (float)std; h.sigma = (float)std::sqrt(variance); h.inv_2var = (float)(1.0 / (2.0 * variance));
+    h.logp_c = (float)(0.5 * std::log(2.0 * 3.141592653589793 * variance)); h.acc_hi = (float)acc_hi;
+    return h;
+}
+static thread_local HeadCfg g_head = make_head(-1.0, 3.0, 0.5, 2.0);      // PY:1044-1045, 726
+// sticky per-device flag the tensor-core kernels raise when an mbarrier wait times out (their results are then
+// unusable); Algo_PPO.update reads it through mhppo_tc_failures after every update and raises.  The PPO entry
+// points have no handle, so the 4 bytes are allocated on the first tensor-core launch on each device.
 static int *fail_flag() {
-    static int *p = nullptr;
-    if (!p) { cudaMalloc(&p, sizeof(int)); cudaMemset(p, 0, sizeof(int)); }
-    return p;
+    static int *p[64] = {nullptr};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+    if (!p[dev]) { cudaMalloc(&p[dev], sizeof(int)); cudaMemset(p[dev], 0, sizeof(int)); }
+    return p[dev];
 }
 static size_t smem_tc(int nets) {
     return sizeof(float) * ((size_t)nets * ((tcm::NetTiles<16>::FLOATS + 255) & ~255) + 2 * 128 * H2) + 1024;
@@ -45,6 +57,7 @@ static RolloutDims dims_of(const mhppo_rollout_cfg *c) {
     RolloutDims d;
     d.P = c->nb_ped; d.L = c->nb_lines; d.C = 2 * c->nb_lines; d.n_obs = 7 * d.C + 4 + 9 * d.P; d.D = 2 + 6 * (d.C - 1) + 10;
     d.N = c->n_envs; d.k0 = (uint32_t)c->seed; d.k1 = (uint32_t)(c->seed >> 32); d.env_id0 = c->env_id0;
+    d.head = g_head;
     return d;
 }
 struct Workspace { float *gpartial; double *lpartial; double *spartial; };
@@ -167,6 +180,12 @@ int mhppo_returns(const float *rew, const float *rl, int32_t T, int64_t CN, doub
     return ck(cudaGetLastError(), "k_returns");
 }
 
+int mhppo_set_gaussian_head(float mean, float std, float variance, float acc_hi) {
+    if (!(std > 0.f) || !(variance > 0.f)) return api_fail(MHPPO_EINVAL, "std and variance must be > 0");
+    g_head = make_head(mean, std, variance, acc_hi);
+    return 0;
+}
+
 int mhppo_set_mlp_mode(int32_t mode) {
     if (mode < 0 || mode > 2) return api_fail(MHPPO_EINVAL, "mode must be 0 (auto), 1 (ffma) or 2 (tc)");
     g_mlp_mode = mode;
@@ -227,6 +246,7 @@ static int ppo_grad_impl(int32_t n_in, int32_t head, const float *x, int32_t D, 
     const Workspace w = carve(workspace, kp);
     LossArgs la; la.act = act; la.logp_old = logp_old; la.rtg = rtg; la.V = V; la.adv_mean = adv_mean; la.adv_inv_std = adv_inv_std;
     la.inv_n = inv_n; la.f0 = f0; la.f1 = f1; la.V_out = V_out; la.spartial = stats3 ? w.spartial : nullptr;
+    la.head = g_head;
     cudaStream_t s = (cudaStream_t)stream;
     int rc = (kp == 16) ? launch_grad<16>(head, ss, net, la, w, s) : ((kp == 32) ? launch_grad<32>(head, ss, net, la, w, s) : launch_grad<56>(head, ss, net, la, w, s));
     if (rc) return rc;

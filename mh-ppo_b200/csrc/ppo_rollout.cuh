@@ -21,6 +21,7 @@ struct RolloutDims {
     int64_t N;
     uint32_t k0, k1;
     int64_t env_id0;
+    HeadCfg head;
 };
 
 // flat scalable observation (gym Dict key order car, env, ped; PY:543-554), component-major
@@ -153,7 +154,7 @@ __global__ void __launch_bounds__(kFwdBlock, 2) k_policy_act(RolloutDims d, cons
     if (n >= d.N) return;
     float *row = rows + (size_t)threadIdx.x * kRowFwd;   // one in-place row per sample (odd stride: conflict-free)
     const ObsView v{io.obs, d.N, n, 7 * d.C + 4, 7 * d.C};
-    float mean = 2.0f;                                   // car_b[1,0], PY:436
+    float mean = d.head.acc_hi;                           // car_b[1,0], PY:436
     float st[13], x[13];
     feat_c(v, i, 0, st);                                 // state_c_tensor starts as ped 0's features, PY:437
     for (int p = 0; p < d.P; ++p) {
@@ -164,7 +165,7 @@ __global__ void __launch_bounds__(kFwdBlock, 2) k_policy_act(RolloutDims d, cons
         for (int k = 0; k < 13; ++k) row[k] = x[k];
         row[13] = row[14] = row[15] = 0.f;
         const float4 o = mlp_fwd_inplace<KP>(sw + sel * NP, row);
-        const float m = tanhf(o.x) * 3.0f + (-1.0f);     // head type 1, PY:88-90 (std 3, mean -1)
+        const float m = tanhf(o.x) * d.head.std + d.head.mean;   // head type 1, PY:88-90
         mean = fminf(mean, m);
         if (m == mean) {                                 // PY:449-450 (ties: the later pedestrian)
 #pragma unroll
@@ -173,8 +174,8 @@ __global__ void __launch_bounds__(kFwdBlock, 2) k_policy_act(RolloutDims d, cons
     }
     const PhiloxBlock b = policy_block(d, n, (uint32_t)(io.t * d.C + i), 1u | (io.iteration << 8));
     const double z = sqrt(-2.0 * log(1.0 - u53(b.w0, b.w1))) * cos(2.0 * 3.141592653589793 * u53(b.w2, b.w3));
-    const float a = mean + 0.70710678118654757f * (float)z;      // MultivariateNormal(mean, 0.5 I).sample()
-    const float lp = -((a - mean) * (a - mean)) - 0.57236494292470008f;   // log_prob = -(a-mu)^2 - ln(pi)/2
+    const float a = mean + d.head.sigma * (float)z;               // MultivariateNormal(mean, variance I).sample()
+    const float lp = -((a - mean) * (a - mean)) * d.head.inv_2var - d.head.logp_c;   // -(a-mu)^2 / (2 var) - ln(2 pi var)/2
     io.actions[(int64_t)i * d.N + n] = a;
     io.actions[(int64_t)(d.C + i) * d.N + n] = io.light[(int64_t)i * d.N + n];
     const int64_t S = (int64_t)io.T * d.C * d.N, s = ((int64_t)io.t * d.C + i) * d.N + n;
@@ -249,7 +250,7 @@ __global__ void __launch_bounds__(kFwdBlock, 2) k_policy_eval(RolloutDims d, con
             for (int k = 0; k < 13; ++k) row[k] = x[k];
             row[13] = row[14] = row[15] = 0.f;
             const float4 o = mlp_fwd_inplace<KP>(sw + sel * NP, row);
-            na = tanhf(o.x) * 3.0f + (-1.0f);
+            na = tanhf(o.x) * d.head.std + d.head.mean;
         }
         a = (na < a) ? na : a;                           // PY:209
         const float cap = (10.0f - x[0]) / io.dt;        // PY:210

@@ -91,6 +91,7 @@ struct LossArgs {
     float f0, f1;                              // choice only: fraction of samples whose action is 0 / 1 (PY:834-842 broadcast)
     float *V_out;                              // critic only, optional: V[s] of this forward pass and the advantage statistics
     double *spartial;                          //   [grid][3] partial (sum A, sum A^2, n) with A = rtg - V (replaces k_value_stats)
+    HeadCfg head;                              // Gaussian head (HEAD == 1)
 };
 
 // ---- register-tiled dense layers for the fused kernel -------------------------------------------------
@@ -246,13 +247,13 @@ __device__ __forceinline__ void ppo_loss(const LossArgs &la, int64_t s, const Lo
     }
     const float An = ((in.rtg - in.V) - la.adv_mean) * la.adv_inv_std;     // PY:786-787
     if (HEAD == 1) {
-        const float th = tanhf(o.x), mu = th * 3.0f + (-1.0f);
+        const float th = tanhf(o.x), mu = th * la.head.std + la.head.mean;
         const float a = in.act;
-        const float lp = -((a - mu) * (a - mu)) - 0.57236494292470008f;          // MVN(mu, .5 I).log_prob, PY:795-800
+        const float lp = -((a - mu) * (a - mu)) * la.head.inv_2var - la.head.logp_c;   // MVN(mu, var I).log_prob, PY:795-800
         const float ratio = expf(lp - in.logp);                           // PY:803
         const float s1 = ratio * An, s2 = fminf(fmaxf(ratio, 0.8f), 1.2f) * An;   // PY:804-805
         acc.loss += (double)(-fminf(s1, s2)) * (double)la.inv_n;                 // PY:806
-        if (s1 <= s2) dz[0] = -la.inv_n * An * ratio * (2.0f * (a - mu)) * (3.0f * (1.0f - th * th));
+        if (s1 <= s2) dz[0] = -la.inv_n * An * ratio * (2.0f * la.head.inv_2var * (a - mu)) * (la.head.std * (1.0f - th * th));
     } else {
         // Categorical(probs [M,2]).log_prob(actions [M,1]) broadcasts to (M,M): lp[i,j] = log p_j(a_i)
         // (PY:834-842).  With two actions the mean over i collapses to the action frequencies f0, f1.

@@ -60,7 +60,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
 // hot try_wait loop took more than half of their issue slots (weight-gradient chain 2.4x slower, measured).
 __device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return true;
-    for (uint32_t spin = 0; spin < (1u << 22); ++spin) {
+    for (uint32_t spin = 0; spin < (1u << 25); ++spin) {      // > 1.3 s: only a wrong descriptor / lost commit ends here
         __nanosleep(40);
         if (mbar_try_wait(bar, parity)) return true;
     }

@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(128) k_policy_act_tc(RolloutDims d, const floa
     const int64_t nn = live ? n : d.N - 1;
     const int i = (int)(item / nblk);
     const ObsView v{io.obs, d.N, nn, 7 * d.C + 4, 7 * d.C};
-    float mean = 2.0f;                                   // car_b[1,0], PY:436
+    float mean = d.head.acc_hi;                           // car_b[1,0], PY:436
     float st[13], x[KP];
     feat_c(v, i, 0, st);                                 // state_c_tensor starts as ped 0's features, PY:437
     x[13] = x[14] = x[15] = 0.f;
@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(128) k_policy_act_tc(RolloutDims d, const floa
             if (sel == 1) out = o;
         }
         if (ex) {
-            const float m = tanhf(out) * 3.0f + (-1.0f);  // head type 1, PY:88-90
+            const float m = tanhf(out) * d.head.std + d.head.mean;  // head type 1, PY:88-90
             mean = fminf(mean, m);
             if (m == mean) {                              // PY:449-450
 #pragma unroll
@@ -126,8 +126,8 @@ __global__ void __launch_bounds__(128) k_policy_act_tc(RolloutDims d, const floa
     if (live) {
         const PhiloxBlock b = policy_block(d, n, (uint32_t)(io.t * d.C + i), 1u | (io.iteration << 8));
         const double z = sqrt(-2.0 * log(1.0 - u53(b.w0, b.w1))) * cos(2.0 * 3.141592653589793 * u53(b.w2, b.w3));
-        const float a = mean + 0.70710678118654757f * (float)z;
-        const float lp = -((a - mean) * (a - mean)) - 0.57236494292470008f;
+        const float a = mean + d.head.sigma * (float)z;
+        const float lp = -((a - mean) * (a - mean)) * d.head.inv_2var - d.head.logp_c;
         io.actions[(int64_t)i * d.N + n] = a;
         io.actions[(int64_t)(d.C + i) * d.N + n] = io.light[(int64_t)i * d.N + n];
         const int64_t S = (int64_t)io.T * d.C * d.N, s = ((int64_t)io.t * d.C + i) * d.N + n;

@@ -73,8 +73,11 @@ class Algo_PPO:
         self.optimizer_actor_cross = Adam(self.actor_net_cross, self.actor_lr)
         self.optimizer_actor_wait = Adam(self.actor_net_wait, self.actor_lr)
         self.optimizer_actor_choice = Adam(self.actor_net_choice, self.actor_d_lr)
-        self.value_std, self.value_std_d = 0.5, 0.1                                                                      # PY:726-727
+        if not hasattr(self, "value_std"):
+            self.value_std = 0.5                                                                                         # PY:726
+        self.value_std_d = 0.1                                                                                           # PY:727 (unused by the reference's Categorical)
         self.rollout = Env_rollout(env, nc, self.max_steps, self.dt)
+        self.rollout.value_std = self.value_std
         self.ep_reward_cross, self.ep_reward_wait, self.ep_reward_choice, self.ep_scenario_balance = [], [], [], []
         L = _lib.lib()
         nbytes = max(L.mhppo_update_workspace_bytes(self.num_states_c), L.mhppo_update_workspace_bytes(self.num_states_d))
@@ -83,6 +86,20 @@ class Algo_PPO:
         self._loss = torch.zeros(2, dtype=torch.float64, device=dev)
         self.last_losses = {}
         self._sel_cache = {}
+        self.sync_parameters()
+
+    def sync_parameters(self):
+        """Multi-GPU: every rank must hold rank 0's parameters and optimiser state (only gradients and advantage statistics
+        are all-reduced afterwards, so the replicas then stay identical).  Called after construction and loading()."""
+        d = _dist()
+        if d is None:
+            return
+        for _, _, net in self._nets():
+            for t in (net.flat, net.m, net.v):
+                d.broadcast(t, src=0)
+            step = torch.tensor([net.step], dtype=torch.int64, device=net.flat.device)
+            d.broadcast(step, src=0)
+            net.step = int(step.item())
 
     def _init_hyperparameters(self, hyperparameters):
         """PY:919-933."""
@@ -99,7 +116,7 @@ class Algo_PPO:
     def _selection(self, want):
         """Compacted (car, env) columns routed to the cross (0) / wait (1) buffer, or the existing cars (want=None)."""
         r = self.rollout
-        key = (r.iteration, want, r.route.data_ptr(), int(r.route._version), int(r.exist._version))
+        key = (r.iteration, r.route.data_ptr(), int(r.route._version), int(r.exist._version))
         if self._sel_cache.get("key") != key:
             self._sel_cache = {"key": key}
         if want not in self._sel_cache:
@@ -163,12 +180,17 @@ class Algo_PPO:
 
     def update(self, epochs=10):
         """The update half of train() (PY:866-882): 10 x (cross, wait) then 10 x choice."""
+        self.rollout.value_std = self.value_std
+        self.rollout._set_head(self.actor_net_cross)
         self.rollout.futur_rewards()
         for _ in range(epochs):
             self.train_model_c(self.actor_net_cross, self.critic_net_cross, self.optimizer_actor_cross, self.optimizer_critic_cross, 0)
             self.train_model_c(self.actor_net_wait, self.critic_net_wait, self.optimizer_actor_wait, self.optimizer_critic_wait, 1)
         for _ in range(epochs):
             self.train_model_d(self.actor_net_choice, self.critic_net_choice, self.optimizer_actor_choice, self.optimizer_critic_choice)
+        if _lib.lib().mhppo_tc_failures():              # a tensor-core kernel gave up waiting for its MMAs: its gradients are garbage
+            raise RuntimeError("a tcgen05 kernel of the update timed out on its mbarrier; the parameters of this update are not "
+                               "trustworthy (reload a checkpoint; MHPPO_MLP=ffma selects the CUDA-core kernels)")
 
     _TRACE = "load_model/parameters/pappo-scalable-coop-{num_algo:02d}-{name}-step-{epoch:03d}000.npy"
 
@@ -178,8 +200,7 @@ class Algo_PPO:
         for ep in range(nb_loop):
             self.rollout.iterations_rand(self.actor_net_cross, self.actor_net_wait, self.actor_net_choice)
             self.update()
-            cross, wait, choice = self.rollout.immediate_rewards()
-            nc, nw, nd = self.rollout.counts()
+            cross, wait, choice, (nc, nw, nd) = self._global_rewards()
             if cross is not None:
                 self.ep_reward_cross.append(float(cross))
             if wait is not None:
@@ -199,6 +220,19 @@ class Algo_PPO:
                 path = os.path.join(root, self._TRACE.format(num_algo=self.num_algo, epoch=int(self.total_loop / 1000), name=name))
                 os.makedirs(os.path.dirname(path), exist_ok=True)
                 np.save(path, arr)
+
+    def _global_rewards(self):
+        """Mean immediate rewards per buffer and the sample counts (PY:885-906), over the envs of ALL ranks."""
+        r = self.rollout
+        rew = r.rew.view(r.T, r.C, r.N)
+        mc, mw, ex = (r.route == 0), (r.route == 1), (r.exist != 0)
+        t = torch.stack([rew[:, mc].sum().double(), mc.sum().double() * r.T, rew[:, mw].sum().double(), mw.sum().double() * r.T,
+                         r.rew_d.view(r.C, r.N)[ex].sum().double(), ex.sum().double()])
+        t = allreduce_sum_(t).cpu()
+        cross = float(t[0] / t[1]) if t[1] > 0 else None
+        wait = float(t[2] / t[3]) if t[3] > 0 else None
+        choice = float(t[4] / t[5]) if t[5] > 0 else float("nan")
+        return cross, wait, choice, (int(t[1]), int(t[3]), int(t[5]))
 
     # -- checkpoints: same file names and state_dict layout as the reference (PY:935-1001) ------------------------
     _PATH = "load_model/weights/pappo-scalable-coop-{name}-{num_algo:02d}-{kind}-step-{epoch:03d}0.pth"
@@ -225,3 +259,4 @@ class Algo_PPO:
         for name, kind, net in self._nets():
             path = os.path.join(root, self._PATH.format(name=name, kind=kind, num_algo=num_algo, epoch=int(total_loop / 10)))
             net.load_state_dict(torch.load(path, map_location="cpu"))
+        self.sync_parameters()

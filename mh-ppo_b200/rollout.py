@@ -39,6 +39,12 @@ class Env_rollout:
         self.exist = torch.zeros(Cn, N, dtype=torch.int8, device=dev)
         self._cfg = RolloutCfg(nb_ped=P, nb_lines=env.nb_lines, T=T, n_envs=N, seed=env._seed, env_id0=env._env_id0)
         self.iteration = 0
+        self.value_std = 0.5                             # exploration variance of the Gaussian head (Algo_PPO.value_std, PY:726)
+
+    def _set_head(self, actor):
+        """The kernels' Gaussian head = the actor's own (tanh * std + mean, PY:88-90), the noise variance of PY:726-729 and
+        car_b[1,0] as the start of the min over pedestrians (PY:436) -- so Model_PPO.forward, rollout and update agree."""
+        check(self._L.mhppo_set_gaussian_head(float(actor.mean), float(actor.std), float(self.value_std), float(self.env.car_b[1, 0])))
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.env.device).cuda_stream)
@@ -52,6 +58,9 @@ class Env_rollout:
         """One episode per env of the reference's rollout (PY:357-516).  Resets the envs first (PY:377)."""
         env, L, cfg, st = self.env, self._L, self._cfg, self._stream()
         N, Cn, T = self.N, self.C, self.T
+        if (actor_net_cross.mean, actor_net_cross.std) != (actor_net_wait.mean, actor_net_wait.std):
+            raise ValueError("the cross and wait actors must share mean / std (PY:711-714)")
+        self._set_head(actor_net_cross)
         env.reset()
         self.exist.copy_(env.get_state()["car_i"][:, :, 1].t().to(torch.int8))               # cars_exist, PY:380
         check(L.mhppo_choice_act(C.byref(cfg), env._obs.data_ptr(), actor_net_choice.flat.data_ptr(), self.iteration,
@@ -88,6 +97,7 @@ class Env_rollout:
             raise NotImplementedError("choix_test (PY:128-150) is an analysis helper outside the hot path")
         env, L, cfg, st = self.env, self._L, self._cfg, self._stream()
         N, Cn, P, T, dev = self.N, self.C, self.P, self.T, env.device
+        self._set_head(actor_net_cross)
         E = int(nbr_episodes)
         f = lambda *s: torch.zeros(*s, device=dev)
         out = dict(acts=f(E, T, Cn, N), rews=f(E, T, Cn, N), reward_light=f(E, T, Cn, N),

@@ -144,6 +144,12 @@ class VecCrosswalkEnv:
                                      _view(self._term, True) if self.autoreset else View(None, 0, 0), self._stream()))
         return self._obs_dict(self._obs), self._rew.t(), self._done.bool(), self._trunc, {}
 
+    def observe(self):
+        """env.get_state() of the reference (SC:960-969): the observation of the current state, e.g. after set_state /
+        load_state / a state injection; refreshes the buffer the rollout kernels read."""
+        check(self._L.mhppo_env_observe(self._h, _view(self._obs, True), self._stream()))
+        return self._obs_dict(self._obs)
+
     @property
     def terminal_obs(self):
         return self._term.t()
@@ -196,6 +202,7 @@ class VecCrosswalkEnv:
         if str(z["variant"]) != self.variant:
             raise ValueError("snapshot is of env class %s, this is %s" % (z["variant"], self.variant))
         self.set_state({k: z[k] for k in ("car_f", "car_i", "ped_f", "ped_i", "env_f", "env_i")})
+        return self.observe()
 
     @property
     def car_exist(self):

@@ -18,7 +18,8 @@ from mhppo_b200 import ppo  # noqa: E402
 def run(N, env_id0, dev, use_dist, epochs=3):
     ppo.set_distributed(use_dist)
     env = mhppo_b200.VecCrosswalkEnv("coop_scalable", N, nb_car=4, nb_ped=3, nb_lines=2, seed=77, env_id0=env_id0, device=dev)
-    torch.manual_seed(0)
+    # the sharded run seeds every rank differently: Algo_PPO must broadcast rank 0's initial parameters (sync_parameters)
+    torch.manual_seed(0 if not use_dist else 1000 * int(os.environ.get("RANK", "0")))
     algo = mhppo_b200.Algo_PPO(mhppo_b200.Model_PPO, env, num_states_c=13, num_states_d=30, num_actions=1, mean=-1.0, std=3.0, nb_cars=4, dt=0.3)
     algo.rollout.iterations_rand(algo.actor_net_cross, algo.actor_net_wait, algo.actor_net_choice)
     algo.update(epochs=epochs)
@@ -50,6 +51,8 @@ def main():
     if rank == 0:
         print("dist_ppo_check world=%d: rollout shards bit-identical, max relative weight difference %.3e" % (world, t.item()))
     assert t.item() < 1e-4, t.item()
+    if rank == 0:
+        print("OK")
     dist.destroy_process_group()
 
 

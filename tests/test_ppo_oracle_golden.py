@@ -97,3 +97,21 @@ def test_state_dict_pack_roundtrip():
         from oracle import ppo_oracle as PO
         want = PO.mlp_forward(sd, x, mt)
         torch.testing.assert_close(net(x).reshape(want.shape), want, rtol=1e-6, atol=1e-6)
+
+
+def test_eval_oracle_reproduces_shipped_checkpoint_111_episodes(oracle_mod):
+    from oracle import ppo_oracle as PO
+    """The oracle's deterministic evaluation rollout with the SHIPPED trained nets (1/1/1 scalable env, 18-input choice
+    net) against episodes recorded from the unmodified reference (tools/gen_golden_ckpt111.py)."""
+    z = np.load(os.path.join(GOLDEN_DIR, "ppo_eval_ckpt111.npz"))
+    sd = lambda p: {k[len(p) + 1:]: torch.as_tensor(z[k]) for k in z.files if k.startswith(p + ".")}
+    sds = [sd("cross"), sd("wait"), sd("choice")]
+    assert sds[2]["layer1.weight"].shape == (32, 18)
+    for e, (seed, env_id) in enumerate(z["streams"]):
+        venv = oracle_mod.OracleVecEnv("coop_scalable", 1, 1, 1, 1, seed=int(seed), env_id0=int(env_id), store_f32=False)
+        b = PO.eval_episode(venv, *sds, 1, 1)
+        want = {k.split(".", 1)[1]: z[k] for k in z.files if k.startswith("ep%d." % e)}
+        np.testing.assert_array_equal(b["action_d"][:, 0], want["actions"][:, 2:])
+        np.testing.assert_allclose(b["acts"][:, 0], want["acts"], rtol=1e-5, atol=1e-5)
+        np.testing.assert_allclose(b["rew"][:, 0], want["rew"], rtol=1e-5, atol=1e-5)
+        np.testing.assert_allclose(b["rl"][:, 0], want["rl"], rtol=1e-5, atol=1e-5)
