@@ -151,7 +151,7 @@ def cpu_port_run(variant, nb_car, nb_ped, nb_lines, n_envs, warmup, steps, threa
     return n_envs * steps * rounds / timed, timed, sum(active) / len(active), rounds
 
 
-def cpu_ppo_rate(n_envs=256):
+def cpu_ppo_rate(n_envs=256, wl=("coop_scalable", 4, 3, 2)):
     """PPO samples/s of the CPU restatement of the PPO pipeline (oracle/ppo_oracle.py: vectorised numpy feature builders,
     torch CPU networks / autograd / Adam on all host threads, C env port): one iteration = one 80-step episode per env,
     reward-to-go, 10 x (cross, wait) + 10 x choice epochs (Algo_PPO.train, PY:854-917)."""
@@ -159,16 +159,18 @@ def cpu_ppo_rate(n_envs=256):
     import torch
     from oracle import oracle as O, ppo_oracle as PO
     torch.manual_seed(0)
-    P, L, seed = 3, 2, 1234
-    D = 2 + 6 * (2 * L - 1) + 8 + 2
+    variant, nb_car, P, L = wl
+    seed = 1234
+    legacy = 0 if variant == "coop_scalable" else nb_car
+    D = 2 + (5 * (nb_car - 1) if legacy else 6 * (2 * L - 1)) + 8 + 2
     actors = [PO.Net(13, 1, 1), PO.Net(13, 1, 1), PO.Net(D, 2, 2)]
     critics = [PO.Net(13, 1, 0), PO.Net(13, 1, 0), PO.Net(D, 1, 0)]
     opt_a = [torch.optim.Adam(n.parameters(), lr=3e-4) for n in actors]
     opt_c = [torch.optim.Adam(n.parameters(), lr=1e-3) for n in critics]
-    env = O.OracleVecEnv("coop_scalable", n_envs, 4, 3, L, seed=seed, store_f32=False)
+    env = O.OracleVecEnv(variant, n_envs, nb_car, P, L, seed=seed, store_f32=False)
     t0 = time.perf_counter()
     sds = [{k: v.detach().clone() for k, v in n.state_dict().items()} for n in actors]
-    b = PO.rollout_episode(env, *sds, seed, np.arange(n_envs), P, L)
+    b = PO.rollout_episode(env, *sds, seed, np.arange(n_envs), P, L, legacy_nb_car=legacy)
     rtg = PO.reward_to_go(b["rew"])
     t_roll = time.perf_counter() - t0
     n_samples = 0
@@ -226,12 +228,15 @@ def bind_to_gpu_numa_node(torch, local):
         return {"numa_node": None, "note": type(e).__name__}
 
 
-def run_ppo(mh, torch, dist, world, rank, dev, n_envs, iters, warm=1):
+def run_ppo(mh, torch, dist, world, rank, dev, n_envs, iters, warm=1, wl=("coop_scalable", 4, 3, 2)):
     """PPO samples/s (BASELINE.json metric, second half): one iteration = one 80-step episode in every env
     (Env_rollout.iterations_rand) + reward-to-go + 10 x (cross, wait) + 10 x choice update epochs (Algo_PPO.train)."""
-    env = mh.VecCrosswalkEnv("coop_scalable", n_envs, nb_car=4, nb_ped=3, nb_lines=2, seed=1234, env_id0=rank * n_envs, device=dev)
+    variant, nb_car, nb_ped, nb_lines = wl
+    env = mh.VecCrosswalkEnv(variant, n_envs, nb_car=nb_car, nb_ped=nb_ped, nb_lines=nb_lines, seed=1234, env_id0=rank * n_envs, device=dev)
     torch.manual_seed(0)
-    algo = mh.Algo_PPO(mh.Model_PPO, env, num_states_c=13, num_states_d=30, num_actions=1, mean=-1.0, std=3.0, nb_cars=4, dt=0.3)
+    C_slots = env.n_slots
+    D = 2 + (6 if variant == "coop_scalable" else 5) * (C_slots - 1) + 10
+    algo = mh.Algo_PPO(mh.Model_PPO, env, num_states_c=13, num_states_d=D, num_actions=1, mean=-1.0, std=3.0, nb_cars=nb_car, dt=0.3)
     r = algo.rollout
     ev = lambda: torch.cuda.Event(enable_timing=True)
     for _ in range(warm):
@@ -258,8 +263,9 @@ def run_ppo(mh, torch, dist, world, rank, dev, n_envs, iters, warm=1):
     fwd = lambda D, out: 2.0 * (D * 32 + 32 * 64 + 64 * 32 + 32 * out)
     n_c, n_w, n_d = [float(x) for x in r.counts()]
     ped_mean = float(env.get_state()["env_i"][:, 1].float().mean().item())       # existing pedestrians per env (current episode)
-    fl_update = 10.0 * ((n_c + n_w) * 3.0 * 2.0 * fwd(13, 1) + n_d * 3.0 * (fwd(30, 2) + fwd(30, 1)))
-    fl_roll = n_envs * (80.0 * 4 * ped_mean * fwd(13, 1) + 4 * 3 * fwd(30, 2))
+    fl_update = 10.0 * ((n_c + n_w) * 3.0 * 2.0 * fwd(13, 1) + n_d * 3.0 * (fwd(D, 2) + fwd(D, 1)))
+    pairs = C_slots * (ped_mean if variant == "coop_scalable" else nb_ped)     # the older drivers visit every pedestrian slot
+    fl_roll = n_envs * (80.0 * pairs * fwd(13, 1) + C_slots * nb_ped * fwd(D, 2))
     t = torch.tensor([t_roll + t_upd, t_roll, t_upd, float(samples), fl_update + fl_roll], dtype=torch.float64, device=dev)
     if world > 1:
         mx = t.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX); dist.all_reduce(t, op=dist.ReduceOp.SUM)
@@ -274,7 +280,9 @@ def run_ppo(mh, torch, dist, world, rank, dev, n_envs, iters, warm=1):
             "samples_per_iteration": samples / iters, "n_envs_per_gpu": n_envs, "update_epochs": "10 x (cross, wait) + 10 x choice",
             "gpu_launches": int(launches),
             "roofline": ppo_roofline(flops, tot_ms, world),
-            "config": "Coop-MH-PPO-scalable on Env_hybrid_multi_coop_scalable nb_car=4 nb_ped=3 nb_lines=2, %d envs/GPU x 80 steps" % n_envs}
+            "config": "%s on Env_hybrid_multi_%s nb_car=%d nb_ped=%d nb_lines=%d, %d envs/GPU x 80 steps (rollout loop replayed as a CUDA graph)" % (
+                {"coop_scalable": "Coop-MH-PPO-scalable", "coop": "Coop-MH-PPO.ipynb", "naif": "MH-PPO.ipynb"}.get(variant, "PPO"), variant,
+                nb_car, nb_ped, nb_lines, n_envs)}
 
 
 def workload_config(variant, nb_car, nb_ped, nb_lines, n_envs, state_bytes=None, flushed=True):
@@ -446,7 +454,12 @@ def main():
     flushed = flush is not None
     del st, env, flush, acts, act_h, obs_h
     torch.cuda.empty_cache()
-    ppo = run_ppo(mhppo_b200, torch, dist, world, rank, dev, args.ppo_envs, args.ppo_iters) if args.ppo_envs > 0 and args.ppo_iters > 0 else None
+    ppo = None
+    if args.ppo_envs > 0 and args.ppo_iters > 0:
+        if args.workload == "scalable_432":
+            ppo = run_ppo(mhppo_b200, torch, dist, world, rank, dev, args.ppo_envs, args.ppo_iters)
+        elif variant in ("coop", "naif", "stop"):       # the older drivers' PPO on their own env class, at the workload's env count
+            ppo = run_ppo(mhppo_b200, torch, dist, world, rank, dev, n_envs, max(args.ppo_iters, 5), warm=3, wl=(variant, nb_car, nb_ped, nb_lines))
     clocks = sampler.stop()        # sampled every 200 ms from the start of the device-timed region to the end of the PPO section
     t_dev = torch.tensor([dev_ms, e2e_s, active], dtype=torch.float64, device=dev)
     if world > 1:
@@ -489,7 +502,7 @@ def main():
                                     "env_steps_per_s": rate}
             if ppo is not None:
                 n_cpu = 256
-                r_ppo, dt_ppo, dt_roll, n_s = cpu_ppo_rate(n_cpu)
+                r_ppo, dt_ppo, dt_roll, n_s = cpu_ppo_rate(n_cpu, (variant, nb_car, nb_ped, nb_lines) if args.workload != "scalable_432" else ("coop_scalable", 4, 3, 2))
                 ppo["cpu_baseline"] = {"value": r_ppo, "unit": "PPO samples/s", "cores": cores, "kind": "port",
                                        "sample": "one iteration at %d envs (%d samples, %.1f s of which rollout %.1f s): vectorised numpy/torch "
                                                  "restatement of Env_rollout + Algo_PPO (oracle/ppo_oracle.py) over the C env port; the "

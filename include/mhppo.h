@@ -144,7 +144,10 @@ int64_t mhppo_launch_count(void);
 typedef struct mhppo_rollout_cfg {
     int32_t nb_ped, nb_lines;
     int32_t T;            /* steps per episode (80) */
-    int32_t reserved;
+    int32_t legacy_nb_car; /* 0: Coop-MH-PPO-scalable.py layout (C = 2*nb_lines slots of 7 floats, env row of 4).  > 0: the older
+                            * notebooks' layout on the coop / naif / stop env classes (Coop-MH-PPO.ipynb, MH-PPO.ipynb): C = this many
+                            * cars of 6 floats, env row of 3, D = 2+5*(C-1)+10, every pedestrian slot visited, closest pedestrian
+                            * seeded with slot 0 and not filtered on `exist` */
     int64_t n_envs;
     uint64_t seed;        /* same Philox key as the env */
     int64_t env_id0;
@@ -168,6 +171,14 @@ int mhppo_choice_act(const mhppo_rollout_cfg *cfg, const float *obs_dev, const f
 int mhppo_policy_act(const mhppo_rollout_cfg *cfg, const float *obs_dev, const float *net_cross_dev, const float *net_wait_dev,
                      const int8_t *action_d_dev, const float *light_dev, int32_t t, uint32_t iteration, float *actions_dev,
                      float *obs_c_dev, float *act_dev, float *logp_dev, void *stream);
+/* The whole T-step inner loop of Env_rollout.iterations_rand (PY:386-476) in one call: per step policy_act, then env.step
+ * with rewards / reward_light written into rew_dev / rl_dev [T][C][N] (no auto-reset: the episode ends at step T-1).
+ * use_graph != 0: from the second call with the same arguments on, the 2T launches are replayed as one CUDA graph on a
+ * stream owned by the library (launch-bound at small env counts); the caller's stream is ordered around it by events. */
+int mhppo_rollout_steps(void *env_handle, const mhppo_rollout_cfg *cfg, float *obs_dev, const float *net_cross_dev,
+                        const float *net_wait_dev, const int8_t *action_d_dev, const float *light_dev, uint32_t iteration,
+                        float *actions_dev, float *obs_c_dev, float *act_dev, float *logp_dev, float *rew_dev, float *rl_dev,
+                        uint8_t *done_dev, int32_t use_graph, void *stream);
 /* deterministic evaluation rollout, Env_rollout.iterations (PY:152-252).
  * choice_eval: argmax of the choice net per (car, ped) (PY:177-192) for the envs that re-decide: all when force != 0 (first
  *   step of an episode), else those whose state has ped_traffic != nb_ped (PY:222-224); other envs keep action_d.

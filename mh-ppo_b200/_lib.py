@@ -28,7 +28,7 @@ class EnvDims(C.Structure):
 
 
 class RolloutCfg(C.Structure):
-    _fields_ = [("nb_ped", C.c_int32), ("nb_lines", C.c_int32), ("T", C.c_int32), ("reserved", C.c_int32),
+    _fields_ = [("nb_ped", C.c_int32), ("nb_lines", C.c_int32), ("T", C.c_int32), ("legacy_nb_car", C.c_int32),
                 ("n_envs", C.c_int64), ("seed", C.c_uint64), ("env_id0", C.c_int64)]
 
 
@@ -60,6 +60,7 @@ SYMBOLS = {
     "mhppo_choice_eval": (C.c_int, [C.POINTER(RolloutCfg), C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "mhppo_policy_eval": (C.c_int, [C.POINTER(RolloutCfg)] + [C.c_void_p] * 4 + [C.c_float] * 4 + [C.c_void_p] * 3),
     "mhppo_policy_act": (C.c_int, [C.POINTER(RolloutCfg)] + [C.c_void_p] * 5 + [C.c_int32, C.c_uint32] + [C.c_void_p] * 5),
+    "mhppo_rollout_steps": (C.c_int, [C.c_void_p, C.POINTER(RolloutCfg)] + [C.c_void_p] * 5 + [C.c_uint32] + [C.c_void_p] * 7 + [C.c_int32, C.c_void_p]),
     "mhppo_returns": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mhppo_update_workspace_bytes": (C.c_int64, [C.c_int32]),
     "mhppo_value_stats": (C.c_int, [C.c_int32, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_int64, C.c_int64] + [C.c_void_p] * 6),

@@ -9,6 +9,7 @@
 #include "tc_kernels.cuh"
 #include "tc_grad.cuh"
 #include <cstdlib>
+#include <cstring>
 
 namespace mhppo {
 int api_fail(int code, const std::string &msg);      // mhppo_api.cu
@@ -55,7 +56,11 @@ template <int KP> static size_t smem_grad() {
 }
 static RolloutDims dims_of(const mhppo_rollout_cfg *c) {
     RolloutDims d;
-    d.P = c->nb_ped; d.L = c->nb_lines; d.C = 2 * c->nb_lines; d.n_obs = 7 * d.C + 4 + 9 * d.P; d.D = 2 + 6 * (d.C - 1) + 10;
+    d.P = c->nb_ped; d.L = c->nb_lines;
+    d.legacy = c->legacy_nb_car > 0 ? 1 : 0;
+    d.C = d.legacy ? c->legacy_nb_car : 2 * c->nb_lines;
+    d.car_w = d.legacy ? 6 : 7; d.env_w = d.legacy ? 3 : 4;
+    d.n_obs = d.car_w * d.C + d.env_w + 9 * d.P; d.D = 2 + (d.legacy ? 5 : 6) * (d.C - 1) + 10;
     d.N = c->n_envs; d.k0 = (uint32_t)c->seed; d.k1 = (uint32_t)(c->seed >> 32); d.env_id0 = c->env_id0;
     d.head = g_head;
     return d;
@@ -120,14 +125,14 @@ int mhppo_choice_act(const mhppo_rollout_cfg *cfg, const float *obs, const float
     return ck(cudaGetLastError(), "k_choice_act");
 }
 
-int mhppo_policy_act(const mhppo_rollout_cfg *cfg, const float *obs, const float *net_cross, const float *net_wait,
-                     const int8_t *action_d, const float *light, int32_t t, uint32_t iteration, float *actions, float *obs_c,
-                     float *act, float *logp, void *stream) {
+static int policy_act_impl(const mhppo_rollout_cfg *cfg, const float *obs, const float *net_cross, const float *net_wait,
+                           const int8_t *action_d, const float *light, int32_t t, uint32_t iteration, const uint32_t *iter_dev,
+                           float *actions, float *obs_c, float *act, float *logp, void *stream) {
     if (!cfg || !obs || !net_cross || !net_wait || !action_d || !light || !actions || !obs_c || !act || !logp)
         return api_fail(MHPPO_EINVAL, "null argument");
     const RolloutDims d = dims_of(cfg);
     ActIO io; io.obs = obs; io.action_d = action_d; io.light = light; io.actions = actions; io.obs_c = obs_c; io.act = act;
-    io.logp = logp; io.t = t; io.T = cfg->T; io.iteration = iteration;
+    io.logp = logp; io.t = t; io.T = cfg->T; io.iteration = iteration; io.iter_dev = iter_dev;
     if (use_tc(true)) {
         const int64_t items = ((d.N + 127) / 128) * d.C;
         const unsigned g2 = (unsigned)(items < 148 ? items : 148);       // persistent: one CTA per SM walks the (env block, car) items
@@ -141,6 +146,80 @@ int mhppo_policy_act(const mhppo_rollout_cfg *cfg, const float *obs, const float
     k_policy_act<<<grid, kFwdBlock, smem_fwd<16>(2), (cudaStream_t)stream>>>(d, net_cross, net_wait, io);
     api_count_launch();
     return ck(cudaGetLastError(), "k_policy_act");
+}
+
+int mhppo_policy_act(const mhppo_rollout_cfg *cfg, const float *obs, const float *net_cross, const float *net_wait,
+                     const int8_t *action_d, const float *light, int32_t t, uint32_t iteration, float *actions, float *obs_c,
+                     float *act, float *logp, void *stream) {
+    return policy_act_impl(cfg, obs, net_cross, net_wait, action_d, light, t, iteration, nullptr, actions, obs_c, act, logp, stream);
+}
+
+/* The T-step inner loop of Env_rollout.iterations_rand (PY:386-476) in one call: per step policy_act -> env.step, rewards and
+ * reward_light written straight into the rollout buffers.  160 launches per episode are launch-bound for small env counts
+ * (configs[1]: 4096 envs), so from the second call with the same arguments on the loop is replayed as ONE CUDA graph on a
+ * stream owned by this library (the iteration number of the noise contract is read from device memory by the graph's
+ * kernels); the caller's stream is ordered before and after it with events. */
+namespace {
+struct RolloutGraph {
+    void *env; mhppo_rollout_cfg cfg; const void *p[12]; HeadCfg head; int mlp_mode;
+    cudaGraphExec_t exec; cudaStream_t s; cudaEvent_t ev_in, ev_out; uint32_t *iter_dev; int calls;
+};
+static RolloutGraph g_rg = {};
+}
+
+int mhppo_rollout_steps(void *env, const mhppo_rollout_cfg *cfg, float *obs, const float *net_cross, const float *net_wait,
+                        const int8_t *action_d, const float *light, uint32_t iteration, float *actions, float *obs_c, float *act,
+                        float *logp, float *rew, float *rl, uint8_t *done, int32_t use_graph, void *stream) {
+    if (!env || !cfg || !obs || !rew || !rl || !done) return api_fail(MHPPO_EINVAL, "null argument");
+    const RolloutDims d = dims_of(cfg);
+    const int64_t N = d.N;
+    const int T = cfg->T, Cn = d.C;
+    cudaStream_t caller = (cudaStream_t)stream;
+    auto run = [&](cudaStream_t q, const uint32_t *iter_dev) -> int {
+        const mhppo_view none = { nullptr, 0, 0 };
+        for (int t = 0; t < T; ++t) {
+            int rc = policy_act_impl(cfg, obs, net_cross, net_wait, action_d, light, t, iteration, iter_dev, actions, obs_c, act, logp, q);
+            if (rc) return rc;
+            const int64_t off = (int64_t)t * Cn * N;
+            rc = mhppo_env_step(env, mhppo_view{ actions, 1, N }, mhppo_view{ obs, 1, N }, mhppo_view{ rew + off, 1, N },
+                                mhppo_view{ rl + off, 1, N }, done, 0, none, q);
+            if (rc) return rc;
+        }
+        return 0;
+    };
+    if (!use_graph) return run(caller, nullptr);
+    RolloutGraph &g = g_rg;
+    const void *key[12] = { obs, net_cross, net_wait, action_d, light, actions, obs_c, act, logp, rew, rl, done };
+    const bool same = g.exec && g.env == env && !memcmp(&g.cfg, cfg, sizeof(*cfg)) && !memcmp(g.p, key, sizeof(key)) &&
+                      !memcmp(&g.head, &g_head, sizeof(HeadCfg)) && g.mlp_mode == g_mlp_mode;
+    if (!g.s) {
+        if (ck(cudaStreamCreateWithFlags(&g.s, cudaStreamNonBlocking), "cudaStreamCreate")) return MHPPO_ECUDA;
+        cudaEventCreateWithFlags(&g.ev_in, cudaEventDisableTiming); cudaEventCreateWithFlags(&g.ev_out, cudaEventDisableTiming);
+        if (ck(cudaMalloc(&g.iter_dev, sizeof(uint32_t)), "cudaMalloc")) return MHPPO_ECUDA;
+    }
+    if (!same) {
+        // first call with these arguments: plain launches (they also set the kernels' shared-memory attributes), then capture
+        if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+        g.env = env; g.cfg = *cfg; memcpy(g.p, key, sizeof(key)); g.head = g_head; g.mlp_mode = g_mlp_mode; g.calls = 0;
+    }
+    if (g.calls++ == 0) return run(caller, nullptr);
+    if (ck(cudaEventRecord(g.ev_in, caller), "cudaEventRecord") || ck(cudaStreamWaitEvent(g.s, g.ev_in, 0), "cudaStreamWaitEvent")) return MHPPO_ECUDA;
+    if (ck(cudaMemcpyAsync(g.iter_dev, &iteration, sizeof(uint32_t), cudaMemcpyHostToDevice, g.s), "cudaMemcpyAsync")) return MHPPO_ECUDA;
+    if (!g.exec) {
+        cudaGraph_t graph = nullptr;
+        if (ck(cudaStreamBeginCapture(g.s, cudaStreamCaptureModeThreadLocal), "cudaStreamBeginCapture")) return MHPPO_ECUDA;
+        const int rc = run(g.s, g.iter_dev);
+        const cudaError_t e = cudaStreamEndCapture(g.s, &graph);
+        if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+        if (ck(e, "cudaStreamEndCapture")) return MHPPO_ECUDA;
+        const cudaError_t e2 = cudaGraphInstantiate(&g.exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ck(e2, "cudaGraphInstantiate")) { g.exec = nullptr; return MHPPO_ECUDA; }
+    }
+    if (ck(cudaGraphLaunch(g.exec, g.s), "cudaGraphLaunch")) return MHPPO_ECUDA;
+    for (int k = 0; k < 2 * T; ++k) api_count_launch();           // the graph's kernel nodes
+    if (ck(cudaEventRecord(g.ev_out, g.s), "cudaEventRecord") || ck(cudaStreamWaitEvent(caller, g.ev_out, 0), "cudaStreamWaitEvent")) return MHPPO_ECUDA;
+    return 0;
 }
 
 int mhppo_choice_eval(const mhppo_rollout_cfg *cfg, const float *obs, const float *net, int32_t force, int8_t *action_d, void *stream) {

@@ -16,8 +16,17 @@
 
 namespace mhppo {
 
+// Two feature layouts (chosen per rollout config, mhppo_rollout_cfg.legacy_nb_car):
+//   scalable  Coop-MH-PPO-scalable.py: C = 2*nb_lines car slots of 7 floats (with `exist`), env row of 4, pedestrians that do
+//             not exist are skipped by the continuous head (PY:440), 6 columns per other car in the choice features (the 6th
+//             is the OWN exist flag, PY:593), closest_ped_d filters on `exist` (PY:614-627);
+//   legacy    the two older notebooks (Coop-MH-PPO.ipynb on `coop`, MH-PPO.ipynb on `naif`; their PPO cells are identical):
+//             C = nb_car cars of 6 floats, env row of 3 (lines at index 2), every pedestrian slot is visited (NB2 cell 1,
+//             `for p in range(self.env.nb_ped)`), 5 columns per other car (NB2 obs_car_ped_d), closest_ped_d is seeded with
+//             pedestrian 0 and has no exist filter (NB2 closest_ped_d).
 struct RolloutDims {
-    int P, C, L, n_obs, D;      // D = 2 + 6*(C-1) + 8 + 2 (PY:111)
+    int P, C, L, n_obs, D;      // D = 2 + 6*(C-1) + 8 + 2 (PY:111); legacy: 2 + 5*(C-1) + 8 + 2
+    int car_w, env_w, legacy;
     int64_t N;
     uint32_t k0, k1;
     int64_t env_id0;
@@ -26,11 +35,15 @@ struct RolloutDims {
 
 // flat scalable observation (gym Dict key order car, env, ped; PY:543-554), component-major
 struct ObsView {
-    const float *o; int64_t N, n; int ped0, env0;
-    __device__ __forceinline__ float car(int i, int k) const { return o[(int64_t)(7 * i + k) * N + n]; }
+    const float *o; int64_t N, n; int ped0, env0, car_w, lines_k, legacy;
+    __device__ __forceinline__ float car(int i, int k) const { return o[(int64_t)(car_w * i + k) * N + n]; }
     __device__ __forceinline__ float env(int k) const { return o[(int64_t)(env0 + k) * N + n]; }
     __device__ __forceinline__ float ped(int p, int k) const { return o[(int64_t)(ped0 + 9 * p + k) * N + n]; }
 };
+
+__device__ __forceinline__ ObsView obs_view(const RolloutDims &d, const float *obs, int64_t n) {
+    return ObsView{obs, d.N, n, d.car_w * d.C + d.env_w, d.car_w * d.C, d.car_w, d.env_w - 1, d.legacy};
+}
 
 struct LaneGeom { float crossing, end_cross, dist_start, dist_end; };
 // Env_rollout.is_in_cross + leave_cross, PY:526-539 (fp32, reference operation order, no FMA)
@@ -52,7 +65,7 @@ __device__ __forceinline__ bool feat_c(const ObsView &v, int i, int p, float *x)
     const float Vc = v.car(i, 1), dVc = v.car(i, 2), cx = v.car(i, 3), line = v.car(i, 5);
     const float vpx = v.ped(p, 0), vpy = v.ped(p, 1), px = v.ped(p, 2), py = v.ped(p, 3), dl = v.ped(p, 4), ex = v.ped(p, 7),
                 dir = v.ped(p, 8);
-    const float e0 = v.env(0), e3 = v.env(3);
+    const float e0 = v.env(0), e3 = v.env(v.lines_k);
     const LaneGeom g = lane_geom(line, py, dir, e0, e3);
     const bool front = px > cx;
     const float dx = px - cx;
@@ -64,7 +77,7 @@ __device__ __forceinline__ bool feat_c(const ObsView &v, int i, int p, float *x)
 
 // Env_rollout.obs_car_ped_d, PY:574-611 -> D features (note car_data[6], the OWN exist flag, PY:593)
 __device__ __forceinline__ void feat_d(const ObsView &v, int C, int i, int p, float *x) {
-    const float Vc = v.car(i, 1), dVc = v.car(i, 2), cx = v.car(i, 3), line = v.car(i, 5), own_exist = v.car(i, 6);
+    const float Vc = v.car(i, 1), dVc = v.car(i, 2), cx = v.car(i, 3), line = v.car(i, 5), own_exist = v.legacy ? 0.f : v.car(i, 6);
     const float vpy = v.ped(p, 1), px = v.ped(p, 2), py = v.ped(p, 3), dl = v.ped(p, 4), dir = v.ped(p, 8);
     int o = 0;
     x[o++] = Vc; x[o++] = dVc;
@@ -72,9 +85,10 @@ __device__ __forceinline__ void feat_d(const ObsView &v, int C, int i, int p, fl
         if (k == i) continue;
         const float x2 = v.car(k, 3);
         x[o++] = v.car(k, 1); x[o++] = (px > x2) ? 1.f : 0.f; x[o++] = px - x2; x[o++] = v.car(k, 4);
-        x[o++] = v.car(k, 5) - line; x[o++] = own_exist;
+        x[o++] = v.car(k, 5) - line;
+        if (!v.legacy) x[o++] = own_exist;
     }
-    const float e0 = v.env(0), e3 = v.env(3);
+    const float e0 = v.env(0), e3 = v.env(v.lines_k);
     const LaneGeom g = lane_geom(line, py, dir, e0, e3);
     x[o++] = vpy; x[o++] = (px > cx) ? 1.f : 0.f; x[o++] = px - cx; x[o++] = dl; x[o++] = g.crossing; x[o++] = g.end_cross;
     x[o++] = g.dist_start; x[o++] = g.dist_end; x[o++] = e0; x[o++] = e3;
@@ -101,7 +115,7 @@ __global__ void __launch_bounds__(kFwdBlock, 2) k_choice_act(RolloutDims d, cons
     const int i = blockIdx.y;
     if (n >= d.N) return;
     float *x = rows + (size_t)threadIdx.x * kRowFwd;      // one in-place row per sample (odd stride: conflict-free)
-    const ObsView v{obs, d.N, n, 7 * d.C + 4, 7 * d.C};
+    const ObsView v = obs_view(d, obs, n);
     const float cx = v.car(i, 3);
     int best = 0; float best_a = 0.f, best_lp = 0.f; double dmin = 1000000.0;    // closest_ped_d, PY:614-627
     const float eps = 1.1920928955078125e-07f;
@@ -119,7 +133,7 @@ __global__ void __launch_bounds__(kFwdBlock, 2) k_choice_act(RolloutDims d, cons
         const float lp = logf(pa);
         action_d[(int64_t)(i * d.P + p) * d.N + n] = (int8_t)(2 * a - 1);
         const double dist = (double)(v.ped(p, 2) - cx);
-        if (dist < dmin && v.ped(p, 7) != 0.f) { dmin = dist; best = p; }
+        if (d.legacy ? (p == 0 || dist < dmin) : (dist < dmin && v.ped(p, 7) != 0.f)) { dmin = dist; best = p; }   // legacy: seeded with ped 0
         if (p == 0 || best == p) { best_a = (float)a; best_lp = lp; }
     }
     // the car's light and its choice sample come from the closest pedestrian (PY:416-422)
@@ -137,6 +151,7 @@ struct ActIO {
     float *actions;                 // [2C][N]: acc rows then light rows, the env-step kernel's input view
     float *obs_c, *act, *logp;      // rollout buffers
     int t, T; uint32_t iteration;
+    const uint32_t *iter_dev;       // if set, the iteration number is read from device memory (replayed CUDA graphs)
 };
 
 __global__ void __launch_bounds__(kFwdBlock, 2) k_policy_act(RolloutDims d, const float *__restrict__ net_cross,
@@ -153,13 +168,13 @@ __global__ void __launch_bounds__(kFwdBlock, 2) k_policy_act(RolloutDims d, cons
     const int i = blockIdx.y;
     if (n >= d.N) return;
     float *row = rows + (size_t)threadIdx.x * kRowFwd;   // one in-place row per sample (odd stride: conflict-free)
-    const ObsView v{io.obs, d.N, n, 7 * d.C + 4, 7 * d.C};
+    const ObsView v = obs_view(d, io.obs, n);
     float mean = d.head.acc_hi;                           // car_b[1,0], PY:436
     float st[13], x[13];
     feat_c(v, i, 0, st);                                 // state_c_tensor starts as ped 0's features, PY:437
     for (int p = 0; p < d.P; ++p) {
         const bool ex = feat_c(v, i, p, x);
-        if (!ex) continue;                               // PY:440
+        if (!ex && !d.legacy) continue;                  // PY:440 (the older notebooks visit every slot)
         const int sel = (io.action_d[(int64_t)(i * d.P + p) * d.N + n] <= 0) ? 0 : 1;   // cross | wait, PY:441-446
 #pragma unroll
         for (int k = 0; k < 13; ++k) row[k] = x[k];
@@ -172,7 +187,8 @@ __global__ void __launch_bounds__(kFwdBlock, 2) k_policy_act(RolloutDims d, cons
             for (int k = 0; k < 13; ++k) st[k] = x[k];
         }
     }
-    const PhiloxBlock b = policy_block(d, n, (uint32_t)(io.t * d.C + i), 1u | (io.iteration << 8));
+    const uint32_t iteration = io.iter_dev ? *io.iter_dev : io.iteration;
+    const PhiloxBlock b = policy_block(d, n, (uint32_t)(io.t * d.C + i), 1u | (iteration << 8));
     const double z = sqrt(-2.0 * log(1.0 - u53(b.w0, b.w1))) * cos(2.0 * 3.141592653589793 * u53(b.w2, b.w3));
     const float a = mean + d.head.sigma * (float)z;               // MultivariateNormal(mean, variance I).sample()
     const float lp = -((a - mean) * (a - mean)) * d.head.inv_2var - d.head.logp_c;   // -(a-mu)^2 / (2 var) - ln(2 pi var)/2
@@ -199,7 +215,7 @@ __global__ void __launch_bounds__(kFwdBlock, 2) k_choice_eval(RolloutDims d, con
     const int i = blockIdx.y;
     if (n >= d.N) return;
     float *x = rows + (size_t)threadIdx.x * kRowFwd;
-    const ObsView v{obs, d.N, n, 7 * d.C + 4, 7 * d.C};
+    const ObsView v = obs_view(d, obs, n);
     if (!force && v.env(1) == (float)d.P) return;                                  // PY:222: state["env"][1] != nb_ped
     for (int p = 0; p < d.P; ++p) {
         for (int k = 0; k < KP; ++k) x[k] = 0.f;
@@ -236,7 +252,7 @@ __global__ void __launch_bounds__(kFwdBlock, 2) k_policy_eval(RolloutDims d, con
     const int i = blockIdx.y;
     if (n >= d.N) return;
     float *row = rows + (size_t)threadIdx.x * kRowFwd;
-    const ObsView v{io.obs, d.N, n, 7 * d.C + 4, 7 * d.C};
+    const ObsView v = obs_view(d, io.obs, n);
     float a = io.acc_hi;                                 // car_b[1,0], PY:197
     float x[13];
     for (int p = 0; p < d.P; ++p) {

@@ -92,13 +92,13 @@ __global__ void __launch_bounds__(128) k_policy_act_tc(RolloutDims d, const floa
     const bool live = n < d.N;
     const int64_t nn = live ? n : d.N - 1;
     const int i = (int)(item / nblk);
-    const ObsView v{io.obs, d.N, nn, 7 * d.C + 4, 7 * d.C};
+    const ObsView v = obs_view(d, io.obs, nn);
     float mean = d.head.acc_hi;                           // car_b[1,0], PY:436
     float st[13], x[KP];
     feat_c(v, i, 0, st);                                 // state_c_tensor starts as ped 0's features, PY:437
     x[13] = x[14] = x[15] = 0.f;
     for (int p = 0; p < d.P; ++p) {
-        const bool ex = feat_c(v, i, p, x) && live;      // PY:440
+        const bool ex = (feat_c(v, i, p, x) || d.legacy) && live;      // PY:440
         const int sel = (io.action_d[(int64_t)(i * d.P + p) * d.N + nn] <= 0) ? 0 : 1;
         const int need_cross = __syncthreads_or(ex && sel == 0), need_wait = __syncthreads_or(ex && sel == 1);
         float out = 0.f;
@@ -124,7 +124,8 @@ __global__ void __launch_bounds__(128) k_policy_act_tc(RolloutDims d, const floa
         }
     }
     if (live) {
-        const PhiloxBlock b = policy_block(d, n, (uint32_t)(io.t * d.C + i), 1u | (io.iteration << 8));
+        const uint32_t iteration = io.iter_dev ? *io.iter_dev : io.iteration;
+        const PhiloxBlock b = policy_block(d, n, (uint32_t)(io.t * d.C + i), 1u | (iteration << 8));
         const double z = sqrt(-2.0 * log(1.0 - u53(b.w0, b.w1))) * cos(2.0 * 3.141592653589793 * u53(b.w2, b.w3));
         const float a = mean + d.head.sigma * (float)z;
         const float lp = -((a - mean) * (a - mean)) * d.head.inv_2var - d.head.logp_c;

@@ -76,7 +76,9 @@ class Algo_PPO:
         if not hasattr(self, "value_std"):
             self.value_std = 0.5                                                                                         # PY:726
         self.value_std_d = 0.1                                                                                           # PY:727 (unused by the reference's Categorical)
-        self.rollout = Env_rollout(env, nc, self.max_steps, self.dt)
+        self.rollout = Env_rollout(env, env.n_slots, self.max_steps, self.dt)
+        if self.num_states_d != self.rollout.shape_env_d:
+            raise ValueError("num_states_d = %s, but the choice features of this env have %d columns" % (self.num_states_d, self.rollout.shape_env_d))
         self.rollout.value_std = self.value_std
         self.ep_reward_cross, self.ep_reward_wait, self.ep_reward_choice, self.ep_scenario_balance = [], [], [], []
         L = _lib.lib()
@@ -192,7 +194,9 @@ class Algo_PPO:
             raise RuntimeError("a tcgen05 kernel of the update timed out on its mbarrier; the parameters of this update are not "
                                "trustworthy (reload a checkpoint; MHPPO_MLP=ffma selects the CUDA-core kernels)")
 
-    _TRACE = "load_model/parameters/pappo-scalable-coop-{num_algo:02d}-{name}-step-{epoch:03d}000.npy"
+    # file-name stems of the three drivers: PY:908 / NB2 (coop) / NB1 (naif, "acc6")
+    _STEM = {"coop_scalable": "pappo-scalable-coop", "coop": "pappo-coop", "naif": "pappo-acc6", "stop": "pappo-acc6"}
+    _TRACE = "load_model/parameters/{stem}-{num_algo:02d}-{name}-step-{epoch:03d}000.npy"
 
     def train(self, nb_loop, verbose=False, root=".", save_traces=True):
         """Training loop (PY:854-917); ends by writing the four learning-curve traces with the reference's file names
@@ -217,7 +221,8 @@ class Algo_PPO:
             for name, arr in (("reward_cross", np.array(self.ep_reward_cross)), ("reward_wait", np.array(self.ep_reward_wait)),
                               ("reward_choice", np.array(self.ep_reward_choice)),
                               ("scenario_balance", np.array(self.ep_scenario_balance).reshape((-1, 2)))):
-                path = os.path.join(root, self._TRACE.format(num_algo=self.num_algo, epoch=int(self.total_loop / 1000), name=name))
+                path = os.path.join(root, self._TRACE.format(stem=self._STEM[self.env.variant], num_algo=self.num_algo,
+                                                             epoch=int(self.total_loop / 1000), name=name))
                 os.makedirs(os.path.dirname(path), exist_ok=True)
                 np.save(path, arr)
 
@@ -235,7 +240,7 @@ class Algo_PPO:
         return cross, wait, choice, (int(t[1]), int(t[3]), int(t[5]))
 
     # -- checkpoints: same file names and state_dict layout as the reference (PY:935-1001) ------------------------
-    _PATH = "load_model/weights/pappo-scalable-coop-{name}-{num_algo:02d}-{kind}-step-{epoch:03d}0.pth"
+    _PATH = "load_model/weights/{stem}-{name}-{num_algo:02d}-{kind}-step-{epoch:03d}0.pth"
 
     def evaluate(self, nbr_episodes, choix=False, **kw):
         """Testing (PY:738-747): the deterministic rollout of every env for `nbr_episodes` episodes.  Returns the dense
@@ -250,13 +255,13 @@ class Algo_PPO:
 
     def saving(self, root="."):
         for name, kind, net in self._nets():
-            path = os.path.join(root, self._PATH.format(name=name, kind=kind, num_algo=self.num_algo, epoch=int(self.total_loop / 10)))
+            path = os.path.join(root, self._PATH.format(stem=self._STEM[self.env.variant], name=name, kind=kind, num_algo=self.num_algo, epoch=int(self.total_loop / 10)))
             os.makedirs(os.path.dirname(path), exist_ok=True)
             torch.save(net.state_dict(), path)
 
     def loading(self, num_algo, total_loop, root="."):
         self.num_algo, self.total_loop = num_algo, total_loop
         for name, kind, net in self._nets():
-            path = os.path.join(root, self._PATH.format(name=name, kind=kind, num_algo=num_algo, epoch=int(total_loop / 10)))
+            path = os.path.join(root, self._PATH.format(stem=self._STEM[self.env.variant], name=name, kind=kind, num_algo=num_algo, epoch=int(total_loop / 10)))
             net.load_state_dict(torch.load(path, map_location="cpu"))
         self.sync_parameters()

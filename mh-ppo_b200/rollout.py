@@ -18,14 +18,18 @@ from ._lib import RolloutCfg, View, check
 
 class Env_rollout:
     def __init__(self, env, nb_cars, max_steps, dt, seed=None):
-        if env.variant != "coop_scalable":
-            raise NotImplementedError("the PPO rollout kernels implement Coop-MH-PPO-scalable.py (scalable env class)")
+        # scalable: Coop-MH-PPO-scalable.py.  coop / naif / stop (6-float car rows, 3-float env row): the two older drivers,
+        # Coop-MH-PPO.ipynb (coop) and MH-PPO.ipynb (naif), whose PPO cells are identical ("legacy" feature layout)
+        if env.variant not in ("coop_scalable", "coop", "naif", "stop"):
+            raise NotImplementedError("no PPO driver of the reference runs on the %s env class (its observation has the extra "
+                                      "car_follow key)" % env.variant)
+        self.legacy = env.variant != "coop_scalable"
         self.env, self.nb_cars, self.max_steps, self.dt = env, nb_cars, max_steps, dt
         self._L = _lib.lib()
         N, Cn, P, T = env.n_envs, env.n_slots, env.nb_ped, max_steps
         self.N, self.C, self.P, self.T = N, Cn, P, T
         self.shape_env = 2 + 9 + 2                       # PY:110
-        self.shape_env_d = 2 + 6 * (Cn - 1) + 8 + 2      # PY:111
+        self.shape_env_d = 2 + (5 if self.legacy else 6) * (Cn - 1) + 8 + 2      # PY:111 / NB2 cell 1 (5 columns per other car)
         dev = env.device
         S, M = T * Cn * N, Cn * N
         self.S, self.M = S, M
@@ -37,8 +41,10 @@ class Env_rollout:
         self.actions = f(2 * Cn, N)                      # env action buffer, component-major
         self.route = torch.zeros(Cn, N, dtype=torch.int8, device=dev)
         self.exist = torch.zeros(Cn, N, dtype=torch.int8, device=dev)
-        self._cfg = RolloutCfg(nb_ped=P, nb_lines=env.nb_lines, T=T, n_envs=N, seed=env._seed, env_id0=env._env_id0)
+        self._cfg = RolloutCfg(nb_ped=P, nb_lines=env.nb_lines, T=T, legacy_nb_car=Cn if self.legacy else 0, n_envs=N, seed=env._seed,
+                               env_id0=env._env_id0)
         self.iteration = 0
+        self.use_graph = True                            # replay the T-step loop as a CUDA graph (mhppo_rollout_steps)
         self.value_std = 0.5                             # exploration variance of the Gaussian head (Algo_PPO.value_std, PY:726)
 
     def _set_head(self, actor):
@@ -62,23 +68,19 @@ class Env_rollout:
             raise ValueError("the cross and wait actors must share mean / std (PY:711-714)")
         self._set_head(actor_net_cross)
         env.reset()
-        self.exist.copy_(env.get_state()["car_i"][:, :, 1].t().to(torch.int8))               # cars_exist, PY:380
+        if self.legacy:
+            self.exist.fill_(1)                          # every car exists in the older drivers (no cars_exist test)
+        else:
+            self.exist.copy_(env.get_state()["car_i"][:, :, 1].t().to(torch.int8))           # cars_exist, PY:380
         check(L.mhppo_choice_act(C.byref(cfg), env._obs.data_ptr(), actor_net_choice.flat.data_ptr(), self.iteration,
                                  self.action_d.data_ptr(), self.light.data_ptr(), self.obs_d.data_ptr(), self.act_d.data_ptr(),
                                  self.logp_d.data_ptr(), st))
-        was_auto = env.autoreset
-        env.autoreset = False                           # the episode ends exactly at step T-1; the next call resets
-        none = View(None, 0, 0)
-        for t in range(T):
-            check(L.mhppo_policy_act(C.byref(cfg), env._obs.data_ptr(), actor_net_cross.flat.data_ptr(),
-                                     actor_net_wait.flat.data_ptr(), self.action_d.data_ptr(), self.light.data_ptr(), t,
-                                     self.iteration, self.actions.data_ptr(), self.obs_c.data_ptr(), self.act.data_ptr(),
-                                     self.logp.data_ptr(), st))
-            off = t * Cn * N * 4
-            check(L.mhppo_env_step(env._h, View(self.actions.data_ptr(), 1, N), View(env._obs.data_ptr(), 1, N),
-                                   View(self.rew.data_ptr() + off, 1, N), View(self.rl.data_ptr() + off, 1, N),
-                                   env._done.data_ptr(), 0, none, st))
-        env.autoreset = was_auto
+        # the T-step loop (policy_act -> env.step, no auto-reset: the episode ends exactly at step T-1; the next call resets)
+        # runs inside the library: one call, replayed as a CUDA graph from the second iteration on
+        check(L.mhppo_rollout_steps(env._h, C.byref(cfg), env._obs.data_ptr(), actor_net_cross.flat.data_ptr(),
+                                    actor_net_wait.flat.data_ptr(), self.action_d.data_ptr(), self.light.data_ptr(), self.iteration,
+                                    self.actions.data_ptr(), self.obs_c.data_ptr(), self.act.data_ptr(), self.logp.data_ptr(),
+                                    self.rew.data_ptr(), self.rl.data_ptr(), env._done.data_ptr(), int(self.use_graph), st))
         # trajectory routing (PY:489-502): existing car i goes to the cross buffer if action_d[i] <= 0, where i indexes the
         # flat (car x ped) decision array -- the reference's own quirk (SURVEY.md hard part 6) -- else to the wait buffer
         flat_d = self.action_d[:Cn]                      # rows 0..C-1 of the (car*P + ped) array
@@ -93,8 +95,10 @@ class Env_rollout:
           obs [E,T,n_obs,N] (state before each step), acts [E,T,C,N], rews [E,T,C,N], reward_light [E,T,C,N],
           action_d int8 [E,T,C*P,N] (+-1 decisions in force at each step), waiting [E,T,P,N] (pedestrian.waiting_time
           after each step).  `reference_batches(out, n)` rebuilds the reference's return values for env n."""
+        if self.legacy:
+            raise NotImplementedError("the deterministic evaluation rollout is built for Coop-MH-PPO-scalable.py only")
         if choix:
-            raise NotImplementedError("choix_test (PY:128-150) is an analysis helper outside the hot path")
+            self.choix_test()
         env, L, cfg, st = self.env, self._L, self._cfg, self._stream()
         N, Cn, P, T, dev = self.N, self.C, self.P, self.T, env.device
         self._set_head(actor_net_cross)

@@ -26,10 +26,15 @@ import torch
 F32 = np.float32
 
 
-def obs_layout(nb_ped, nb_lines):
-    """Slices of the flat scalable observation (gym Dict key order car, env, ped; PY:543-554)."""
+def obs_layout(nb_ped, nb_lines, legacy_nb_car=0):
+    """Slices of the flat observation (gym Dict key order car, env, ped; PY:543-554).  legacy_nb_car = 0: the scalable
+    script (2*nb_lines car slots of 7 floats, env row of 4).  legacy_nb_car > 0: the two older notebooks on the coop / naif
+    env classes (Coop-MH-PPO.ipynb / MH-PPO.ipynb, identical PPO cells): nb_car cars of 6 floats, env row of 3 (lines last)."""
+    if legacy_nb_car:
+        size_car = 6 * legacy_nb_car
+        return dict(size_car=size_car, cw=6, size_env=3, lines_k=2, ped0=size_car + 3, C=legacy_nb_car, P=nb_ped, legacy=True)
     size_car = 7 * 2 * nb_lines
-    return dict(size_car=size_car, size_cardata=7, size_env=4, size_peddata=9, ped0=size_car + 4, C=2 * nb_lines, P=nb_ped)
+    return dict(size_car=size_car, cw=7, size_env=4, lines_k=3, ped0=size_car + 4, C=2 * nb_lines, P=nb_ped, legacy=False)
 
 
 def _lane(car_line, ped_pos, ped_dir, cross_lines, lines):
@@ -45,52 +50,61 @@ def _lane(car_line, ped_pos, ped_dir, cross_lines, lines):
     return crossing, dist_start.astype(F32), end_cross, dist_end.astype(F32)
 
 
-def obs_car_ped(obs, i, p, nb_ped, nb_lines):
-    """Env_rollout.obs_car_ped, PY:541-572.  obs [N, n_obs] float32 -> (features [N,13] float32, exist [N])."""
-    L = obs_layout(nb_ped, nb_lines)
+def obs_car_ped(obs, i, p, nb_ped, nb_lines, legacy_nb_car=0):
+    """Env_rollout.obs_car_ped, PY:541-572 (same arithmetic in the older notebooks, on their 6 / 3-float rows).
+    obs [N, n_obs] float32 -> (features [N,13] float32, exist [N])."""
+    L = obs_layout(nb_ped, nb_lines, legacy_nb_car)
     obs = np.asarray(obs, F32)
-    car = obs[:, i * 7:(i + 1) * 7]
+    cw, lk = L["cw"], L["lines_k"]
+    car = obs[:, i * cw:(i + 1) * cw]
     ped = obs[:, L["ped0"] + p * 9: L["ped0"] + (p + 1) * 9]
-    env = obs[:, L["size_car"]: L["size_car"] + 4]
-    crossing, dist_start, end_cross, dist_end = _lane(car[:, 5], ped[:, 3], ped[:, 8], env[:, 0], env[:, 3])
+    env = obs[:, L["size_car"]: L["size_car"] + L["size_env"]]
+    crossing, dist_start, end_cross, dist_end = _lane(car[:, 5], ped[:, 3], ped[:, 8], env[:, 0], env[:, lk])
     front = ped[:, 2] > car[:, 3]
     dx = ped[:, 2] - car[:, 3]
     with np.errstate(divide="ignore", invalid="ignore"):
         ttc = np.minimum(F32(10.0), dx / np.maximum(car[:, 1] - ped[:, 0], F32(0.01))) * front + F32(10.0) * (~front)
     f = np.stack([car[:, 1], car[:, 2], ped[:, 1], front.astype(F32), dx, ped[:, 4], crossing.astype(F32), end_cross.astype(F32),
-                  dist_start, dist_end, ttc.astype(F32), env[:, 0], env[:, 3]], axis=1).astype(F32)
+                  dist_start, dist_end, ttc.astype(F32), env[:, 0], env[:, lk]], axis=1).astype(F32)
     return f, ped[:, 7]
 
 
-def obs_car_ped_d(obs, i, p, nb_ped, nb_lines):
-    """Env_rollout.obs_car_ped_d, PY:574-611 -> [N, 2+6(2L-1)+8+2] (note car_data[6], the OWN exist flag, PY:593)."""
-    L = obs_layout(nb_ped, nb_lines)
+def obs_car_ped_d(obs, i, p, nb_ped, nb_lines, legacy_nb_car=0):
+    """Env_rollout.obs_car_ped_d, PY:574-611 -> [N, 2+6(2L-1)+8+2] (note car_data[6], the OWN exist flag, PY:593);
+    the older notebooks have 5 columns per other car (no exist flag) -> [N, 2+5(nb_car-1)+8+2]."""
+    L = obs_layout(nb_ped, nb_lines, legacy_nb_car)
     obs = np.asarray(obs, F32)
-    car = obs[:, i * 7:(i + 1) * 7]
+    cw, lk = L["cw"], L["lines_k"]
+    car = obs[:, i * cw:(i + 1) * cw]
     ped = obs[:, L["ped0"] + p * 9: L["ped0"] + (p + 1) * 9]
-    env = obs[:, L["size_car"]: L["size_car"] + 4]
+    env = obs[:, L["size_car"]: L["size_car"] + L["size_env"]]
     cols = [car[:, 1], car[:, 2]]
     for k in range(L["C"]):
         if k == i:
             continue
-        c2 = obs[:, k * 7:(k + 1) * 7]
-        cols += [c2[:, 1], (ped[:, 2] > c2[:, 3]).astype(F32), ped[:, 2] - c2[:, 3], c2[:, 4], c2[:, 5] - car[:, 5], car[:, 6]]
-    crossing, dist_start, end_cross, dist_end = _lane(car[:, 5], ped[:, 3], ped[:, 8], env[:, 0], env[:, 3])
+        c2 = obs[:, k * cw:(k + 1) * cw]
+        cols += [c2[:, 1], (ped[:, 2] > c2[:, 3]).astype(F32), ped[:, 2] - c2[:, 3], c2[:, 4], c2[:, 5] - car[:, 5]]
+        if not L["legacy"]:
+            cols.append(car[:, 6])
+    crossing, dist_start, end_cross, dist_end = _lane(car[:, 5], ped[:, 3], ped[:, 8], env[:, 0], env[:, lk])
     cols += [ped[:, 1], (ped[:, 2] > car[:, 3]).astype(F32), ped[:, 2] - car[:, 3], ped[:, 4], crossing.astype(F32),
-             end_cross.astype(F32), dist_start, dist_end, env[:, 0], env[:, 3]]
+             end_cross.astype(F32), dist_start, dist_end, env[:, 0], env[:, lk]]
     return np.stack(cols, axis=1).astype(F32), ped[:, 7]
 
 
-def closest_ped_d(obs, i, nb_ped, nb_lines):
-    """Env_rollout.closest_ped_d, PY:614-627: argmin of the SIGNED ped_x - car_x over existing peds."""
-    L = obs_layout(nb_ped, nb_lines)
+def closest_ped_d(obs, i, nb_ped, nb_lines, legacy_nb_car=0):
+    """Env_rollout.closest_ped_d, PY:614-627: argmin of the SIGNED ped_x - car_x over existing peds.  The older notebooks
+    seed the minimum with pedestrian 0 and do not look at `exist`."""
+    L = obs_layout(nb_ped, nb_lines, legacy_nb_car)
     obs = np.asarray(obs, F32)
     best = np.zeros(obs.shape[0], np.int64)
     dmin = np.full(obs.shape[0], 1000000.0, np.float64)
+    if L["legacy"]:
+        dmin = (obs[:, L["ped0"] + 2] - obs[:, i * L["cw"] + 3]).astype(np.float64)
     for p in range(nb_ped):
         ped = obs[:, L["ped0"] + p * 9: L["ped0"] + (p + 1) * 9]
-        d = (ped[:, 2] - obs[:, i * 7 + 3]).astype(np.float64)
-        take = (d < dmin) & (ped[:, 7] != 0)
+        d = (ped[:, 2] - obs[:, i * L["cw"] + 3]).astype(np.float64)
+        take = (d < dmin) if L["legacy"] else ((d < dmin) & (ped[:, 7] != 0))
         dmin = np.where(take, d, dmin)
         best = np.where(take, p, best)
     return best
@@ -114,7 +128,7 @@ def mlp_forward(sd, x, model_type, mean=-1.0, std=3.0):
 LOG_PI_HALF = 0.5 * math.log(math.pi)
 
 
-def continuous_step(obs, action_d, sd_cross, sd_wait, z, nb_ped, nb_lines, acc_hi=2.0):
+def continuous_step(obs, action_d, sd_cross, sd_wait, z, nb_ped, nb_lines, acc_hi=2.0, legacy_nb_car=0):
     """Per-step action selection of iterations_rand, PY:434-453, for every env and car slot.
 
     obs [N,n_obs] f32; action_d [N, C*P] in {-1,+1}; z [N,C] standard normal noise.
@@ -123,13 +137,15 @@ def continuous_step(obs, action_d, sd_cross, sd_wait, z, nb_ped, nb_lines, acc_h
     """
     obs = np.asarray(obs, F32)
     N = obs.shape[0]
-    C, P = 2 * nb_lines, nb_ped
+    C, P = (legacy_nb_car or 2 * nb_lines), nb_ped
     mean = np.full((N, C), acc_hi, F32)
     state = np.zeros((N, C, 13), F32)
     for i in range(C):
-        state[:, i], _ = obs_car_ped(obs, i, 0, nb_ped, nb_lines)
+        state[:, i], _ = obs_car_ped(obs, i, 0, nb_ped, nb_lines, legacy_nb_car)
         for p in range(P):
-            f, exist = obs_car_ped(obs, i, p, nb_ped, nb_lines)
+            f, exist = obs_car_ped(obs, i, p, nb_ped, nb_lines, legacy_nb_car)
+            if legacy_nb_car:
+                exist = np.ones_like(exist)                             # the older notebooks visit every pedestrian slot
             with torch.no_grad():
                 m_cross = mlp_forward(sd_cross, f, 1).numpy()[:, 0]
                 m_wait = mlp_forward(sd_wait, f, 1).numpy()[:, 0]
@@ -144,7 +160,7 @@ def continuous_step(obs, action_d, sd_cross, sd_wait, z, nb_ped, nb_lines, acc_h
     return mean, a, logp, state
 
 
-def discrete_step(obs, sd_choice, u, nb_ped, nb_lines):
+def discrete_step(obs, sd_choice, u, nb_ped, nb_lines, legacy_nb_car=0):
     """Episode-start decision of iterations_rand, PY:400-428.  u [N, C*P] uniforms in [0,1).
 
     Categorical(probs).sample() is restated as `action = 1 if u >= p0 else 0`.
@@ -153,14 +169,14 @@ def discrete_step(obs, sd_choice, u, nb_ped, nb_lines):
     """
     obs = np.asarray(obs, F32)
     N = obs.shape[0]
-    C, P = 2 * nb_lines, nb_ped
+    C, P = (legacy_nb_car or 2 * nb_lines), nb_ped
     acts = np.zeros((N, C * P), np.int64)
     logps = np.zeros((N, C * P), F32)
     feats = []
     eps = float(np.finfo(np.float32).eps)
     for i in range(C):
         for p in range(P):
-            f, _ = obs_car_ped_d(obs, i, p, nb_ped, nb_lines)
+            f, _ = obs_car_ped_d(obs, i, p, nb_ped, nb_lines, legacy_nb_car)
             feats.append(f)
             with torch.no_grad():
                 pr = mlp_forward(sd_choice, f, 2).numpy()
@@ -169,7 +185,7 @@ def discrete_step(obs, sd_choice, u, nb_ped, nb_lines):
             acts[:, i * P + p] = a
             logps[:, i * P + p] = np.log(pa).astype(F32)
     feats = np.stack(feats, axis=1)
-    closest = np.stack([closest_ped_d(obs, i, nb_ped, nb_lines) for i in range(C)], axis=1)
+    closest = np.stack([closest_ped_d(obs, i, nb_ped, nb_lines, legacy_nb_car) for i in range(C)], axis=1)
     idx = np.arange(C)[None, :] * P + closest
     rows = np.arange(N)[:, None]
     return acts, logps, feats, acts[rows, idx], logps[rows, idx], feats[rows, idx], closest
@@ -358,18 +374,21 @@ def policy_uniform(index, env_id, seed, iteration=0):
     return _u53(w[0], w[1])
 
 
-def rollout_episode(env, sd_cross, sd_wait, sd_choice, seed, env_ids, nb_ped, nb_lines, T=80, iteration=0):
+def rollout_episode(env, sd_cross, sd_wait, sd_choice, seed, env_ids, nb_ped, nb_lines, T=80, iteration=0, legacy_nb_car=0):
     """One episode per env of Env_rollout.iterations_rand (PY:357-516) on a vectorised env oracle
     (oracle.OracleVecEnv, scalable class).  Returns the rollout buffers in the vectorised layout:
       obs_c [T,C,N,13], act [T,C,N], logp [T,C,N], rew [T,C,N], route [C,N] (0 cross / 1 wait / -1 car absent),
       obs_d [C,N,D], act_d [C,N], logp_d [C,N], rew_d [C,N] (min over the episode of reward_light, PY:461)."""
-    C, P = 2 * nb_lines, nb_ped
+    C, P = (legacy_nb_car or 2 * nb_lines), nb_ped
     env_ids = np.asarray(env_ids, np.int64)
     N = env_ids.shape[0]
     obs = env.reset()
-    exist = env.get_state()["car_i"][:, :, 1].astype(bool)              # cars_exist, PY:380
+    exist = env.get_state()["car_i"][:, :C, 1].astype(bool)             # cars_exist, PY:380 (all cars in the older notebooks)
+    if legacy_nb_car:
+        exist = np.ones_like(exist)
     u = np.stack([policy_uniform(k, env_ids, seed, iteration) for k in range(C * P)], axis=1)
-    acts_d, logps_d, feats_d, light_a, light_lp, light_f, _ = discrete_step(obs, sd_choice, u.astype(np.float32), nb_ped, nb_lines)
+    acts_d, logps_d, feats_d, light_a, light_lp, light_f, _ = discrete_step(obs, sd_choice, u.astype(np.float32), nb_ped, nb_lines,
+                                                                            legacy_nb_car)
     action_d = (2 * acts_d - 1).astype(np.float64)                      # PY:423
     light = (2 * light_a - 1).astype(np.float64)                        # PY:424
     buf = dict(obs_c=np.zeros((T, C, N, 13), F32), act=np.zeros((T, C, N), F32), logp=np.zeros((T, C, N), F32),
@@ -377,7 +396,7 @@ def rollout_episode(env, sd_cross, sd_wait, sd_choice, seed, env_ids, nb_ped, nb
     ep_rew = np.zeros((N, C), np.float64)
     for t in range(T):
         z = np.stack([policy_normal(t * C + i, env_ids, seed, iteration) for i in range(C)], axis=1)
-        mean, a, logp, state = continuous_step(obs, action_d, sd_cross, sd_wait, z, nb_ped, nb_lines)
+        mean, a, logp, state = continuous_step(obs, action_d, sd_cross, sd_wait, z, nb_ped, nb_lines, legacy_nb_car=legacy_nb_car)
         obs, rew, rl, done = env.step(np.concatenate([a.astype(np.float64), light], axis=1))
         ep_rew = np.minimum(ep_rew, rl)                                 # PY:461
         buf["obs_c"][t] = state.transpose(1, 0, 2)

@@ -19,7 +19,21 @@ import refdriver as rd  # noqa: E402
 PY = os.path.join(rd.REF_ROOT, "Coop-MH-PPO-scalable.py")
 
 
-def load_namespace():
+NB_COOP = os.path.join(rd.REF_ROOT, "Coop-MH-PPO.ipynb")     # on the coop env class
+NB_NAIF = os.path.join(rd.REF_ROOT, "MH-PPO.ipynb")          # on the naif env class (same PPO cell)
+
+
+def _source_lines(path):
+    """The PPO definitions: the script itself, or the first code cell of a notebook."""
+    if path.endswith(".ipynb"):
+        import json
+        cell = next(c for c in json.load(open(path))["cells"] if c["cell_type"] == "code")
+        return "".join(cell["source"]).split("\n")
+    return open(path).read().split("\n")
+
+
+def load_namespace(path=None):
+    path = path or PY
     for name in ("matplotlib", "matplotlib.pyplot", "matplotlib.animation"):
         if name not in sys.modules:
             m = types.ModuleType(name)
@@ -29,10 +43,10 @@ def load_namespace():
     sys.modules["matplotlib"].animation = sys.modules["matplotlib.animation"]
     if rd.REF_ROOT not in sys.path:
         sys.path.insert(0, rd.REF_ROOT)
-    src = open(PY).read().split("\n")
+    src = _source_lines(path)
     cut = next(i for i, l in enumerate(src) if l.startswith("#5) Computing part"))
     ns = {"__name__": "ref_ppo"}
-    exec(compile("\n".join(src[:cut]), PY, "exec"), ns)
+    exec(compile("\n".join(src[:cut]), path, "exec"), ns)
     return ns
 
 
@@ -42,10 +56,13 @@ def make_algo(ns, variant, nb_car, nb_ped, nb_lines, seed=0):
     env = rd.make_env(variant, nb_car, nb_ped, nb_lines)
     ns["env"] = env
     ns["nb_lines"] = nb_lines
+    ns["nb_car"] = nb_car                                # global read by the older notebooks' Env_rollout.__init__
     ns["print"] = lambda *a, **k: None
     torch.manual_seed(seed)
     num_states_c = 2 + 9 + 2
     num_states_d = 2 + (6 * (2 * nb_lines - 1)) + 8 + 2
+    if variant != "coop_scalable":                       # the older notebooks' driver cell: 5 columns per other car
+        num_states_d = 2 + (5 * (nb_car - 1)) + 8 + 2
     mean = (rd.CAR_B[1, 0] + rd.CAR_B[0, 0]) / 2.0
     std = (rd.CAR_B[1, 0] - rd.CAR_B[0, 0]) / 2.0
     env._mh_rng.set_stream(seed, 0, 0)

@@ -115,3 +115,30 @@ def test_eval_oracle_reproduces_shipped_checkpoint_111_episodes(oracle_mod):
         np.testing.assert_allclose(b["acts"][:, 0], want["acts"], rtol=1e-5, atol=1e-5)
         np.testing.assert_allclose(b["rew"][:, 0], want["rew"], rtol=1e-5, atol=1e-5)
         np.testing.assert_allclose(b["rl"][:, 0], want["rl"], rtol=1e-5, atol=1e-5)
+
+
+import pytest
+
+
+@pytest.mark.parametrize("name", ["coop_212", "naif_121"])
+def test_legacy_rollout_oracle_reproduces_notebook_episodes(oracle_mod, name):
+    """The older drivers' feature layout (Coop-MH-PPO.ipynb on coop, MH-PPO.ipynb on naif): oracle vs episodes recorded from
+    the notebooks' unmodified first code cell (tools/gen_golden_legacy.py)."""
+    from oracle import ppo_oracle as PO
+    z = np.load(os.path.join(GOLDEN_DIR, "ppo_rollout_%s.npz" % name))
+    c, p, l = [int(x) for x in z["cfg"]]
+    variant = str(z["variant"])
+    sds = [_sd(z, n) for n in ("cross", "wait", "choice")]
+    for e, (seed, env_id) in enumerate(z["streams"]):
+        seed, env_id = int(seed), int(env_id)
+        venv = oracle_mod.OracleVecEnv(variant, 1, c, p, l, seed=seed, env_id0=env_id, store_f32=False, n_threads=1)
+        b = PO.rollout_episode(venv, *sds, seed, [env_id], p, l, legacy_nb_car=c)
+        want = {k.split(".", 1)[1]: z[k] for k in z.files if k.startswith("ep%d." % e)}
+        for nm, r in (("cross", 0), ("wait", 1)):
+            cars = [i for i in range(c) if b["route"][i, 0] == r]
+            obs = np.concatenate([b["obs_c"][:, i, 0] for i in cars]) if cars else np.zeros((0, 13), np.float32)
+            np.testing.assert_allclose(obs, want["obs_" + nm], rtol=2e-5, atol=2e-5)
+            got = np.concatenate([b["act"][:, i, 0] for i in cars]) if cars else np.zeros(0)
+            np.testing.assert_allclose(got, want["acts_" + nm], rtol=2e-5, atol=2e-5)
+        np.testing.assert_allclose(np.stack([b["obs_d"][i, 0] for i in range(c)]), want["obs_choice"], rtol=1e-5, atol=1e-5)
+        np.testing.assert_array_equal(np.array([b["act_d"][i, 0] for i in range(c)]), want["acts_choice"])

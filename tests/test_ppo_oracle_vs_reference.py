@@ -152,3 +152,38 @@ def test_eval_rollout_matches_reference(ref):
         np.testing.assert_allclose(b["rl"][:, 0], want["rl"], rtol=2e-5, atol=2e-5)
         np.testing.assert_allclose(b["waiting"][:, 0], want["waiting"], rtol=0, atol=1e-9)
     assert regimes == {1, 80}
+
+
+@pytest.mark.parametrize("nb,variant,cfg", [("coop", "coop", (2, 1, 2)), ("coop", "coop", (3, 3, 3)), ("naif", "naif", (1, 2, 1)), ("naif", "naif", (2, 2, 2))],
+                         ids=["coop_212", "coop_333", "naif_121", "naif_222"])
+def test_legacy_layout_rollout_matches_the_notebooks(nb, variant, cfg):
+    """The two older drivers (Coop-MH-PPO.ipynb on `coop` = BASELINE configs[1], MH-PPO.ipynb on `naif` = configs[0]; same
+    PPO cell): their first code cell is loaded UNMODIFIED and whole rollout episodes are compared with the oracle's legacy
+    layout (6-float car rows, 3-float env row, 5 columns per other car, every pedestrian slot visited, closest pedestrian
+    seeded with slot 0)."""
+    import ref_rollout
+    import refppo
+    from oracle import oracle as O
+    from oracle import ppo_oracle as PO
+    ns = refppo.load_namespace(refppo.NB_COOP if nb == "coop" else refppo.NB_NAIF)
+    c, p, l = cfg
+    algo, env = refppo.make_algo(ns, variant, c, p, l, seed=1)
+    assert algo.actor_net_choice.layer1.weight.shape[1] == 2 + 5 * (c - 1) + 10
+    sds = [_sd(n) for n in (algo.actor_net_cross, algo.actor_net_wait, algo.actor_net_choice)]
+    for seed, env_id in [(777, 5), (901, 123), (5, 1), (6, 2)]:
+        want = ref_rollout.reference_episode(ns, algo, env, seed, env_id)
+        venv = O.OracleVecEnv(variant, 1, c, p, l, seed=seed, env_id0=env_id, store_f32=False, n_threads=1)
+        b = PO.rollout_episode(venv, *sds, seed, [env_id], p, l, legacy_nb_car=c)
+        for name, r in (("cross", 0), ("wait", 1)):
+            cars = [i for i in range(c) if b["route"][i, 0] == r]
+            obs = np.concatenate([b["obs_c"][:, i, 0] for i in cars]) if cars else np.zeros((0, 13), np.float32)
+            np.testing.assert_allclose(obs, want["obs_" + name], rtol=2e-5, atol=2e-5)
+            for key, mine in (("acts", "act"), ("logp", "logp"), ("rews", "rew")):
+                got = np.concatenate([b[mine][:, i, 0] for i in cars]) if cars else np.zeros(0)
+                np.testing.assert_allclose(got, want[key + "_" + name], rtol=2e-5, atol=2e-5)
+            rtg = np.concatenate([PO.reward_to_go(b["rew"][:, i, 0]) for i in cars]) if cars else np.zeros(0)
+            np.testing.assert_allclose(rtg, want["rtg_" + name], rtol=2e-5, atol=2e-5)
+        np.testing.assert_allclose(np.stack([b["obs_d"][i, 0] for i in range(c)]), want["obs_choice"], rtol=1e-5, atol=1e-5)
+        np.testing.assert_array_equal(np.array([b["act_d"][i, 0] for i in range(c)]), want["acts_choice"])
+        np.testing.assert_allclose(np.array([b["logp_d"][i, 0] for i in range(c)]), want["logp_choice"], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(np.array([b["rew_d"][i, 0] for i in range(c)]), want["rews_choice"], rtol=1e-6, atol=1e-9)

@@ -93,7 +93,7 @@ def reference_episode(ns, algo, env, seed, env_id, iteration=0):
             out["logp_" + name] = np.array(getattr(r, "batch_log_probs_" + name), np.float64).reshape(-1)
             out["rews_" + name] = np.array(getattr(r, "batch_rews_" + name), np.float64).reshape(-1)
         out["rtg_cross"], out["rtg_wait"], out["rtg_choice"] = [x.numpy().reshape(-1) for x in rt]
-        out["car_exist"] = np.array([c.exist for c in env.cars])
+        out["car_exist"] = np.array([getattr(c, "exist", True) for c in env.cars])
         return out
     finally:
         ns["MultivariateNormal"], ns["Categorical"] = real
