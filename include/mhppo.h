@@ -190,6 +190,17 @@ int mhppo_choice_eval(const mhppo_rollout_cfg *cfg, const float *obs_dev, const 
 int mhppo_policy_eval(const mhppo_rollout_cfg *cfg, const float *obs_dev, const float *net_cross_dev, const float *net_wait_dev,
                       const int8_t *action_d_dev, float dt, float speed_limit, float acc_lo, float acc_hi, float *actions_dev,
                       float *act_dev, void *stream);
+/* Episode statistics of the evaluation records (the analysis cell get_average, PY:1550-1675, and the waiting-time histogram input
+ * PY:1390-1403) on the device.  obs_rec: the dense record of Env_rollout.iterations, [E][T][n_obs][N] (state before each step).
+ * ped_out [2][E][P][N]: waiting time on the kerb, crossing time, seconds (PY:1591-1601).  car_out [8][E][C][N]: time to 25 m past the
+ * pedestrians (PY:1622-1631), free-flow time (25 - x0)/v0 (PY:1612), light at the last row (PY:1620), light after the first step
+ * (PY:1613), could-stop flag (-1 if light1 >= 0, else 0 / 1, PY:1613-1617), number / sum / sum of squares of the 25 m passage times
+ * (PY:1624-1625).  sums [E][N][8] = rows, sum v0, sum v0^2, sum |a0|, sum a0, sum a0^2, sum |vp0|, sum vp0^2 (PY:1552-1562);
+ * yield_speed [E][N][3] = n, sum v, sum v^2 over the rows of cars with light1 == 1 (PY:1621).  The printed means / standard
+ * deviations / scenario frequencies are reductions of these arrays (host mirror: Env_rollout.get_average). */
+int mhppo_episode_stats(const float *obs_rec_dev, int32_t E, int32_t T, int32_t n_cars, int32_t n_ped, int32_t car_w, int32_t env_w,
+                        int64_t N, float dt, float *ped_out_dev, float *car_out_dev, double *sums_dev, double *yield_speed_dev,
+                        void *stream);
 /* Env_rollout.futur_rewards (PY:658-684): reverse scan rtg_t = r_t + gamma*rtg_{t+1}, zero bootstrap; and the
  * episodic choice reward min(0, min_t reward_light) (PY:461).  CN = C*N */
 int mhppo_returns(const float *rew_dev, const float *rl_dev, int32_t T, int64_t CN, double gamma, float *rtg_dev,

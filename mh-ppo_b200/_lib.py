@@ -61,6 +61,7 @@ SYMBOLS = {
     "mhppo_policy_eval": (C.c_int, [C.POINTER(RolloutCfg)] + [C.c_void_p] * 4 + [C.c_float] * 4 + [C.c_void_p] * 3),
     "mhppo_policy_act": (C.c_int, [C.POINTER(RolloutCfg)] + [C.c_void_p] * 5 + [C.c_int32, C.c_uint32] + [C.c_void_p] * 5),
     "mhppo_rollout_steps": (C.c_int, [C.c_void_p, C.POINTER(RolloutCfg)] + [C.c_void_p] * 5 + [C.c_uint32] + [C.c_void_p] * 7 + [C.c_int32, C.c_void_p]),
+    "mhppo_episode_stats": (C.c_int, [C.c_void_p] + [C.c_int32] * 6 + [C.c_int64, C.c_float] + [C.c_void_p] * 5),
     "mhppo_returns": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mhppo_update_workspace_bytes": (C.c_int64, [C.c_int32]),
     "mhppo_value_stats": (C.c_int, [C.c_int32, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_int64, C.c_int64] + [C.c_void_p] * 6),

@@ -8,6 +8,7 @@
 #include "ppo_update.cuh"
 #include "tc_kernels.cuh"
 #include "tc_grad.cuh"
+#include "stats.cuh"
 #include <cstdlib>
 #include <cstring>
 
@@ -257,6 +258,18 @@ int mhppo_returns(const float *rew, const float *rl, int32_t T, int64_t CN, doub
     k_returns<<<(unsigned)((CN + 255) / 256), 256, 0, (cudaStream_t)stream>>>(rew, rl, T, CN, gamma, rtg, rew_d);
     api_count_launch();
     return ck(cudaGetLastError(), "k_returns");
+}
+
+int mhppo_episode_stats(const float *obs_rec, int32_t E, int32_t T, int32_t n_cars, int32_t n_ped, int32_t car_w, int32_t env_w, int64_t N,
+                        float dt, float *ped_out, float *car_out, double *sums, double *yield_speed, void *stream) {
+    if (!obs_rec || !ped_out || !car_out || !sums || !yield_speed) return api_fail(MHPPO_EINVAL, "null argument");
+    if (E < 1 || T < 2 || n_cars < 1 || n_ped < 1 || N < 1) return api_fail(MHPPO_EINVAL, "bad dimensions");
+    StatsDims d; d.E = E; d.T = T; d.C = n_cars; d.P = n_ped; d.car_w = car_w; d.env_w = env_w; d.n_obs = car_w * n_cars + env_w + 9 * n_ped; d.N = N;
+    StatsOut o; o.ped = ped_out; o.car = car_out; o.sums = sums; o.yield_speed = yield_speed;
+    const dim3 grid((unsigned)((N + 127) / 128), (unsigned)E);
+    k_episode_stats<<<grid, 128, 0, (cudaStream_t)stream>>>(d, obs_rec, dt, o);
+    api_count_launch();
+    return ck(cudaGetLastError(), "k_episode_stats");
 }
 
 int mhppo_set_gaussian_head(float mean, float std, float variance, float acc_hi) {

@@ -156,6 +156,65 @@ class Env_rollout:
                 wt.append(wait[e, T - 1])
         return obs, acts, rews_c, torch.cat(rews_d), torch.cat(wt)
 
+    def get_average(self, out):
+        """The reference's episode statistics (analysis cell `get_average`, PY:1550-1675; waiting-time histogram input
+        PY:1390-1403) of an evaluation record `out` = iterations(...), computed on the device: one kernel walks every
+        (episode, env) record once (mhppo_episode_stats), the means / standard deviations / scenario frequencies are torch
+        reductions of its per-episode arrays.  Returns a dict with the cell's own names, plus `waiting_times` (seconds, one
+        entry per episode and pedestrian slot: what the reference histograms)."""
+        obs = out["obs"].contiguous()
+        E, T, n_obs, N = obs.shape
+        Cn, P, dev = self.C, self.P, obs.device
+        cw, ew = (6, 3) if self.legacy else (7, 4)
+        ped = torch.zeros(2, E, P, N, device=dev); car = torch.zeros(8, E, Cn, N, device=dev)
+        sums = torch.zeros(E, N, 8, dtype=torch.float64, device=dev); ys = torch.zeros(E, N, 3, dtype=torch.float64, device=dev)
+        check(self._L.mhppo_episode_stats(obs.data_ptr(), E, T, Cn, P, cw, ew, N, float(self.dt), ped.data_ptr(), car.data_ptr(),
+                                          sums.data_ptr(), ys.data_ptr(), self._stream()))
+        d = lambda t: t.double()
+
+        def mstd(n, s, ss):                                   # mean and unbiased std (torch.std) from moments
+            n, s, ss = float(n), float(s), float(ss)
+            if n < 1:
+                return float("nan"), float("nan")
+            m = s / n
+            return m, (max(ss - n * m * m, 0.0) / (n - 1)) ** 0.5 if n > 1 else float("nan")
+
+        def mstd_t(x):
+            x = d(x).reshape(-1)
+            return (float(x.mean()) if x.numel() else float("nan")), (float(x.std()) if x.numel() > 1 else float("nan"))
+
+        S = sums.sum(dim=(0, 1)).cpu()
+        res = {}
+        res["mean_speed"], res["sqrt_speed"] = mstd(S[0], S[1], S[2])
+        res["mean_acc"] = float(S[3] / S[0]); res["sqrt_acc"] = mstd(S[0], S[4], S[5])[1]
+        res["mean_speed_p"], res["sqrt_speed_p"] = mstd(S[0], S[6], S[7])
+        Y = ys.sum(dim=(0, 1)).cpu()
+        res["mean_speed_cars"], res["sqrt_speed_cars"] = mstd(Y[0], Y[1], Y[2])
+        wait, pleave = ped[0], ped[1]                         # [E, P, N]
+        leave, free, decision, light1, could, en, es, ess = car
+        FI = torch.cat([d(pleave), d(leave)], dim=1); FN = torch.cat([d(pleave) - d(wait), d(free)], dim=1)      # [E, P + C, N]
+        res["interaction_cost"] = float((FI.max(dim=1).values - FN.max(dim=1).values).mean())
+        res["max_finish_compare"] = float((FI - FN).mean())
+        y = light1 == 1
+        res["mean_temp_cars"], res["std_temp_cars"] = mstd(d(en)[y].sum(), d(es)[y].sum(), d(ess)[y].sum())
+        res["mean_all_temp_cars"], res["std_all_temp_cars"] = mstd_t(leave)
+        res["mean_temp_peds"], res["std_temp_peds"] = mstd_t(pleave)
+        n_ep = float(E * N)
+        res["yield_decision"] = float((decision == 1).sum()) / n_ep
+        res["go_first_decision"] = float((decision == -1).sum()) / n_ep
+        w = d(wait).reshape(-1)
+        res["mean_waiting"], res["std_waiting"] = float(w.mean()), float(w.std(unbiased=False))
+        cs = could[could >= 0]
+        res["could_stop"] = float(d(cs).mean()) if cs.numel() else float("nan")
+        res["n_episodes"] = int(n_ep)
+        if Cn == 2:
+            s2 = decision.sum(dim=1)
+            res["scenario_11"] = float((s2 == 2).sum()) / n_ep; res["scenario_m1m1"] = float((s2 == -2).sum()) / n_ep
+            res["scenario_m11"] = float(((decision[:, 0] == -1) & (decision[:, 1] == 1)).sum()) / n_ep
+            res["scenario_1m1"] = float(((decision[:, 0] == 1) & (decision[:, 1] == -1)).sum()) / n_ep
+        res["waiting_times"] = wait.permute(2, 0, 1).reshape(-1)          # env-major, like back-to-back episodes of one env
+        return res
+
     def futur_rewards(self):
         """Expected future rewards (PY:658-684) for every trajectory + the episodic choice reward (PY:461, 504)."""
         check(self._L.mhppo_returns(self.rew.data_ptr(), self.rl.data_ptr(), self.T, self.M, 0.99, self.rtg.data_ptr(),

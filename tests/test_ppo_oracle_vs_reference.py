@@ -187,3 +187,53 @@ def test_legacy_layout_rollout_matches_the_notebooks(nb, variant, cfg):
         np.testing.assert_array_equal(np.array([b["act_d"][i, 0] for i in range(c)]), want["acts_choice"])
         np.testing.assert_allclose(np.array([b["logp_d"][i, 0] for i in range(c)]), want["logp_choice"], rtol=1e-5, atol=1e-6)
         np.testing.assert_allclose(np.array([b["rew_d"][i, 0] for i in range(c)]), want["rews_choice"], rtol=1e-6, atol=1e-9)
+
+
+def _reference_get_average_prints(ep_car, ep_ped, ep_cross, nb_car, nb_ped):
+    """Execute the reference's own `get_average` text (PY:1550-1675) and collect what it prints.  The CO2 helper needs
+    LDV.csv, which the reference does not ship: it is stubbed out; `states` / `env` are the globals the cell reads."""
+    import re
+    import types
+    src = open(os.path.join(rd.REF_ROOT, "Coop-MH-PPO-scalable.py")).read().split("\n")
+    a = next(i for i, l in enumerate(src) if l.startswith("def get_average("))
+    b = next(i for i in range(a + 1, len(src)) if src[i].startswith("get_average("))
+    printed = []
+    ns = {"torch": torch, "np": np, "env": types.SimpleNamespace(nb_car=nb_car, nb_ped=nb_ped), "states": torch.zeros(len(ep_cross), 10),
+          "info_co2": lambda *a, **k: None, "LDV": None, "print": lambda *a, **k: printed.append(" ".join(str(x) for x in a))}
+    exec(compile("\n".join(src[a:b]), "get_average", "exec"), ns)
+    ns["get_average"](torch.as_tensor(ep_car), torch.as_tensor(ep_ped), torch.as_tensor(ep_cross))
+    nums = [[float(x) for x in re.findall(r"-?\d+\.\d*(?:e-?\d+)?|nan|-?inf", l.split(":", 1)[-1] if ":" in l else l)] for l in printed]
+    return printed, nums
+
+
+@pytest.mark.parametrize("cfg", [(4, 3, 2), (2, 2, 1)], ids=["432", "221"])
+def test_stats_oracle_matches_reference_cell(cfg):
+    """oracle/stats_oracle.py against the reference's get_average cell on evaluation episodes of the reference itself."""
+    import refppo
+    from oracle import stats_oracle as SO
+    c, p, l = cfg
+    ns = refppo.load_namespace()
+    algo, env = refppo.make_algo(ns, "coop_scalable", c, p, l, seed=3)
+    env._mh_rng.set_stream(42, 7, 0)
+    states = algo.rollout.iterations(algo.actor_net_cross, algo.actor_net_wait, algo.actor_net_choice, 6)[0].numpy()
+    Cn = 2 * l
+    assert Cn == c                                        # the cell reshapes by env.nb_car (PY:1372): only meaningful when nb_car == 2*nb_lines
+    ep_car = states[:, :7 * Cn].reshape(-1, Cn, 7)
+    ep_ped = states[:, 7 * Cn + 4:].reshape(-1, p, 9)
+    ep_cross = states[:, 7 * Cn]
+    printed, nums = _reference_get_average_prints(ep_car, ep_ped, ep_cross, c, p)
+    o = SO.get_average(ep_car, ep_ped, ep_cross, c, p)
+    flat = [v for row in nums for v in row]
+    want = [o["mean_speed"], o["sqrt_speed"], o["mean_acc"], o["sqrt_acc"], o["mean_speed_p"], o["sqrt_speed_p"], o["mean_speed_cars"],
+            o["sqrt_speed_cars"], o["interaction_cost"], o["max_finish_compare"], o["mean_temp_cars"], o["std_temp_cars"], o["mean_all_temp_cars"],
+            o["std_all_temp_cars"], o["mean_temp_peds"], o["std_temp_peds"], o["yield_decision"], o["go_first_decision"], o["mean_waiting"],
+            o["std_waiting"], o["could_stop"]]
+    if c == 2:
+        want += [o["scenario_11"], o["scenario_m1m1"], o["scenario_m11"], o["scenario_1m1"]]
+    # the labels "(voiture 1)", "voiture 1 a 25 metres" contribute the digits 1 / 25 only as integers: the regex keeps decimals only
+    assert len(flat) == len(want), (printed, flat, want)
+    for got, w in zip(flat, want):
+        if np.isnan(w) or np.isinf(w):                   # absent cars have v = 0: their free-flow time (25 - x)/v is inf (PY:1612)
+            assert (np.isnan(got) and np.isnan(w)) or got == w
+        else:
+            assert abs(got - w) <= 6e-3 + 1e-4 * abs(w), (printed, flat, want)      # the cell prints 2 - 4 decimals
