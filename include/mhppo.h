@@ -85,6 +85,19 @@ int mhppo_env_get_dims(void *handle, mhppo_env_dims *dims);
  * mask_dev: uint8[n_envs] or NULL (= all). obs receives the first observation of reset envs only. */
 int mhppo_env_reset(void *handle, const uint8_t *mask_dev, mhppo_view obs_dev, void *stream);
 
+/* State injection of the reference (fixed scenarios: choix_test PY:629-633, reset_distrib NA:903-913), for the envs with
+ * mask_dev[n] != 0 (NULL = all).  One parameter row per env, device memory:
+ *   reset_pedestrian (SC:948-955; CO:895, ST:904, C4:913, C42:929): params [N][9] = speed_x, speed_y, pos_x, pos_y, dl, leave, CZ,
+ *     exist, direction.  Like the reference it first rebuilds EVERY pedestrian as a placeholder (their constructor draws are
+ *     consumed from the env's stream), then applies pedestrian.reset_ped (SC:106-137) to slot num_ped; `leave` / `CZ` are stored
+ *     as truth values.  naif (NA:897-898, 100-135): params = speed_x, speed_y, pos_x, pos_y, dl, direction, cross, -, - ; no
+ *     rebuild; `cross` becomes the env's crossing width.
+ *   reset_cars (SC:957-958 -> car.reset_car SC:583-587): params [N][4] = speed_x, pos_x, light, line (0 <= line < nb_lines: the
+ *     kernels evaluate the lane predicates once per lane of the crossing).
+ * Call mhppo_env_observe afterwards for the observation (the reference calls get_state(), PY:172-173). */
+int mhppo_env_reset_pedestrian(void *handle, int32_t num_ped, const float *params_dev, const uint8_t *mask_dev, void *stream);
+int mhppo_env_reset_cars(void *handle, int32_t num_car, const float *params_dev, const uint8_t *mask_dev, void *stream);
+
 /* Crosswalk_hybrid_multi_*.get_state (SC:960-969): observation of the current state without stepping (after an
  * import_state / state injection).  As in the reference, get_data folds the current gap into every pedestrian's
  * running-min `delta` (SC:457), i.e. the call is not idempotent on that one field. */
@@ -115,7 +128,8 @@ int mhppo_env_reset_host(void *handle, float *obs_host, void *stream);
  *   ped_i [N,P,9] t0/dt,waiting_time/dt,crossing_time/dt,time_stop,line_pos,direction,gender,age,flags
  *   env_f [N,1]   cross (fp64)                env_i [N,4] step_idx,ped_traffic,car_traffic,rng_ctr
  * flags bits: 0 exist,1 is_crossing,2 decision,3 at_crossing,4 ped_left,5 ped_in_cross,
- * 6 ped_not_waiting,7 accident,8 worst_scenario_accident,9 follow_rule,10 stop,11 need_to_stop.
+ * 6 ped_not_waiting,7 accident,8 worst_scenario_accident,9 follow_rule,10 stop,11 need_to_stop,
+ * 12 ratio_eps (set by reset_ped: x follows y with ratio v0x / (v0y + 1e-3), SC:111, instead of v0x / v0y, SC:73).
  * All pointers are device memory. */
 int mhppo_env_export_state(void *handle, float *car_f_dev, int32_t *car_i_dev, float *ped_f_dev,
                            int32_t *ped_i_dev, double *env_f_dev, int64_t *env_i_dev, void *stream);

@@ -42,7 +42,8 @@ enum { V_STOP = 0, V_NAIF = 1, V_COOP = 2, V_4CARS = 3, V_4CARS2 = 4, V_SCAL = 5
 enum : uint32_t {
     PF_EXIST = 1u << 0, PF_CROSSING = 1u << 1, PF_DECISION = 1u << 2, PF_AT_CROSSING = 1u << 3,
     PF_LEFT = 1u << 4, PF_IN_CROSS = 1u << 5, PF_NOT_WAITING = 1u << 6, PF_ACCIDENT = 1u << 7,
-    PF_WORST_ACC = 1u << 8, PF_FOLLOW = 1u << 9, PF_STOP = 1u << 10, PF_NEED_STOP = 1u << 11
+    PF_WORST_ACC = 1u << 8, PF_FOLLOW = 1u << 9, PF_STOP = 1u << 10, PF_NEED_STOP = 1u << 11,
+    PF_RATIO_EPS = 1u << 12     // pedestrian.reset_ped replaced the constructor's ratio v0x / v0y (SC:73) by v0x / (v0y + 1e-3) (SC:111)
 };
 
 // compile-time behaviour table of the six env files ("Behavioural deltas")
@@ -328,4 +329,43 @@ MH_NOINLINE void reset_env(const EnvConst &c, EnvR<MC, MP> &e) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// State injection: Crosswalk_*.reset_pedestrian (SC:948-955; CO:895, ST:904, C4:913, C42:929) rebuilds EVERY
+// pedestrian as a placeholder (the constructors' draws are consumed) and then runs pedestrian.reset_ped (SC:106-137) on slot
+// num_ped with q = (speed_x, speed_y, pos_x, pos_y, dl, leave, CZ, exist, direction); `leave` / `CZ` are kept as truth values.
+// naif (NA:897-898 -> NA:100-135): no rebuild, q = (speed_x, speed_y, pos_x, pos_y, dl, direction, cross); the new cross becomes
+// the env's (its only caller, reset_distrib NA:903-913, sets env.cross to the same value and resets every pedestrian).
+template <int V, int MC, int MP>
+MH_HD void inject_pedestrian(const EnvConst &c, EnvR<MC, MP> &e, int num_ped, const float *q) {
+    typedef VT<V> T;
+    PedR &p = e.ped[num_ped];
+    if (T::naif) {
+        e.cross = (double)q[6];                                                      // NA:101-102
+        const double W = (double)c.L * e.cross;
+        p.dir = (int)q[5];                                                           // NA:103
+        p.v0x = (double)q[0]; p.v0y = (double)q[1] * (double)p.dir;                  // NA:104
+        p.Spx = (double)q[2]; p.Spy = ((double)q[3] - W / 2.0) * (double)p.dir;      // NA:106
+        p.delta = (double)q[4];
+        p.fl = (p.fl | PF_EXIST) & ~(PF_LEFT | PF_IN_CROSS);                         // NA:116-120
+    } else {
+        const double W = (double)c.L * e.cross;
+        for (int j = 0; j < c.nP; ++j) ped_init<V>(c, W, e.cross, e.ped[j], false, e.rng);   // SC:949-951
+        p.v0x = (double)q[0]; p.v0y = (double)q[1]; p.Spx = (double)q[2]; p.Spy = (double)q[3];   // SC:107-110
+        p.dir = (int)q[8];                                                           // SC:115
+        p.delta = (double)q[4];
+        p.fl &= ~(PF_EXIST | PF_LEFT | PF_IN_CROSS);
+        if (q[7] != 0.f) p.fl |= PF_EXIST;
+        if (q[5] != 0.f) p.fl |= PF_LEFT;
+        if (q[6] != 0.f) p.fl |= PF_IN_CROSS;                                        // SC:117-123
+    }
+    p.Vpx = p.v0x; p.Vpy = p.v0y;
+    p.fl |= PF_RATIO_EPS | PF_CROSSING;                                              // SC:111, 124
+    p.lpos = (p.dir < 0) ? c.L : ((p.dir > 0) ? -1 : 0);                             // SC:116
+    e.rng.skip(1);                                                                   // SC:125: CG_score draws, the value is dead
+    p.t0c = 0;                                                                       // SC:127
+}
+// reset_cars -> car.reset_car (SC:957-958, 583-587): q = (speed_x, pos_x, light, line)
+MH_HD void inject_car(CarR &k, const float *q) {
+    k.Sc = (double)q[1]; k.Vc = (double)q[0]; k.light = (double)q[2]; k.line = (int)q[3];
+}
+
 }  // namespace mhppo

@@ -65,15 +65,33 @@ __global__ void __launch_bounds__(kEnvBlock) k_env_observe(const __grid_constant
     store_env<MC, MP>(a, c, n, e);
 }
 
+// reset_pedestrian / reset_cars of the reference (SC:948-958) for the masked envs; params: one row per env
+template <int V, int MC, int MP>
+__global__ void __launch_bounds__(kEnvBlock) k_env_inject(const __grid_constant__ EnvArena a, const __grid_constant__ EnvConst c,
+                                                          const __grid_constant__ RngKey key, int what, int slot, const float *params,
+                                                          const uint8_t *mask) {
+    const int64_t n = (int64_t)blockIdx.x * kEnvBlock + threadIdx.x;
+    if (n >= a.N) return;
+    if (mask && !mask[n]) return;
+    EnvR<MC, MP> e;
+    load_env<MC, MP>(a, c, n, e);
+    const uint64_t gid = (uint64_t)(key.env_id0 + n);
+    e.rng.env_lo = (uint32_t)gid; e.rng.env_hi = (uint32_t)(gid >> 32); e.rng.k0 = key.k0; e.rng.k1 = key.k1;
+    if (what == 0) inject_pedestrian<V, MC, MP>(c, e, slot, params + n * 9);
+    else inject_car(e.car[slot], params + n * 4);
+    store_env<MC, MP>(a, c, n, e);
+}
+
 // ---- instantiation table -----------------------------------------------------------------------
 struct EnvKernelEntry {
     int variant, mc, mp, step_smem;
     void (*step)(EnvArena, EnvConst, RngKey, StepIO);
     void (*reset)(EnvArena, EnvConst, RngKey, const uint8_t *, mhppo_view);
     void (*observe)(EnvArena, EnvConst, mhppo_view);
+    void (*inject)(EnvArena, EnvConst, RngKey, int, int, const float *, const uint8_t *);
 };
 
-#define MHPPO_ENV_ENTRY(V, MC, MP) { V, MC, MP, (int)sizeof(StepShared<MC>), k_env_step<V, MC, MP>, k_env_reset<V, MC, MP>, k_env_observe<V, MC, MP> }
+#define MHPPO_ENV_ENTRY(V, MC, MP) { V, MC, MP, (int)sizeof(StepShared<MC>), k_env_step<V, MC, MP>, k_env_reset<V, MC, MP>, k_env_observe<V, MC, MP>, k_env_inject<V, MC, MP> }
 
 // each env_inst_*.cu defines one of these
 const EnvKernelEntry *env_table_stop(int *n);

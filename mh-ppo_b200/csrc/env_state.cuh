@@ -8,7 +8,7 @@
 //   ped_a[slot][env] = (Sp_x, Sp_y, Vp_x, Vp_y)
 //   ped_b[slot][env] = (v0x, v0y, cross_stop, delta)
 //   ped_c[slot][env] = (worst_dl, counts{t0/dt:8, waiting/dt:8, crossing/dt:8, time_stop:8},
-//                       bits{12 flags, gender:1, age:2, dir+1:2, line_pos+1:5, y_kerb:1, y_lane:1}, spare)
+//                       bits{12 flags, gender:1, age:2, dir+1:2, line_pos+1:5, y_kerb:1, y_lane:1, ratio_eps:1}, spare)
 //   env_e[env]       = (cross as fp64 in two words, {step_idx:8, ped_traffic:8, car_traffic:8}, philox_ctr)
 //                      cross is the one geometry parameter every threshold derives from (W = L*cross,
 //                      lane edges); it stays fp64 so those expressions round exactly as in the reference
@@ -83,10 +83,10 @@ MH_HD uint32_t pack_env_word(int step, int ped_traffic, int car_traffic) {
 
 MH_HD uint32_t pack_ped_bits(const PedR &p) {
     return (p.fl & 0xFFFu) | ((uint32_t)(p.gender & 1) << 12) | ((uint32_t)(p.age & 3) << 13) |
-           ((uint32_t)((p.dir + 1) & 3) << 15) | ((uint32_t)((p.lpos + 1) & 31) << 17);
+           ((uint32_t)((p.dir + 1) & 3) << 15) | ((uint32_t)((p.lpos + 1) & 31) << 17) | (((p.fl >> 12) & 1u) << 24);   // bit 24: PF_RATIO_EPS
 }
 MH_HD void unpack_ped_bits(uint32_t b, PedR &p) {
-    p.fl = b & 0xFFFu; p.gender = (int)((b >> 12) & 1u); p.age = (int)((b >> 13) & 3u);
+    p.fl = (b & 0xFFFu) | (((b >> 24) & 1u) << 12); p.gender = (int)((b >> 12) & 1u); p.age = (int)((b >> 13) & 3u);
     p.dir = (int)((b >> 15) & 3u) - 1; p.lpos = (int)((b >> 17) & 31u) - 1;
 }
 MH_HD uint32_t pack_ped_counts(const PedR &p) {

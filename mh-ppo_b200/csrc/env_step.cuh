@@ -311,7 +311,7 @@ MH_HD void ped_step_stream(const EnvConst &c, const Geo &g, PedR &p, const CarSl
             p.fl &= ~PF_NEED_STOP;
             p.Vpx = 0.0; p.Vpy = 0.0; p.t0c += 1;
         } else if (!change_line || new_choice) {                                     // SC:382-387
-            const double ratio = p.v0x / p.v0y;                                      // SC:73
+            const double ratio = p.v0x / ((p.fl & PF_RATIO_EPS) ? (p.v0y + 1e-3) : p.v0y);   // SC:73 (SC:111 after reset_ped)
             p.Spy = ny; p.Vpy = nv;
             p.Spx = p.Spx + p.Vpy * ratio * dt;
             p.Vpx = p.Vpy * ratio;

@@ -220,6 +220,23 @@ int mhppo_env_reset(void *handle, const uint8_t *mask_dev, mhppo_view obs_dev, v
     return MHPPO_OK;
 }
 
+static int inject(void *handle, int what, int slot, int n_slots, const float *params, const uint8_t *mask, void *stream) {
+    EnvHandle *h = (EnvHandle *)handle;
+    if (!h || !params) return fail(MHPPO_EINVAL, "null argument");
+    if (slot < 0 || slot >= n_slots) return fail(MHPPO_EINVAL, "slot index out of range");
+    auto fn = h->k->inject;
+    fn<<<grid_for(h->a.N), kEnvBlock, 0, (cudaStream_t)stream>>>(h->a, h->c, h->key, what, slot, params, mask);
+    g_launches.fetch_add(1);
+    CK(cudaGetLastError());
+    return MHPPO_OK;
+}
+int mhppo_env_reset_pedestrian(void *handle, int32_t num_ped, const float *params_dev, const uint8_t *mask_dev, void *stream) {
+    return inject(handle, 0, num_ped, handle ? ((EnvHandle *)handle)->c.nP : 0, params_dev, mask_dev, stream);
+}
+int mhppo_env_reset_cars(void *handle, int32_t num_car, const float *params_dev, const uint8_t *mask_dev, void *stream) {
+    return inject(handle, 1, num_car, handle ? ((EnvHandle *)handle)->c.nC : 0, params_dev, mask_dev, stream);
+}
+
 int mhppo_env_observe(void *handle, mhppo_view obs_dev, void *stream) {
     EnvHandle *h = (EnvHandle *)handle;
     if (!h) return fail(MHPPO_EINVAL, "null handle");

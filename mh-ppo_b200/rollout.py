@@ -87,8 +87,27 @@ class Env_rollout:
         self.route.copy_(torch.where(self.exist != 0, (flat_d > 0).to(torch.int8), torch.full_like(flat_d, -1)))
         self.iteration += 1
 
+    def choix_test(self):
+        """The fixed test scenario of the reference (PY:629-633): pedestrian 0 at (0, -1) walking at 1.25 m/s, car 0 at -45 m
+        in lane 0 and car 1 at -22 m in lane 1, both keeping their speed.  As under gym 0.26 (whose wrappers do not forward
+        attribute writes) `self.env.cross = 3.` does not reach the env: the crossing width stays the episode's."""
+        env = self.env
+        v = env.flat_obs[:, 1].clone()                        # self.env.state["car"][1]
+        env.reset_pedestrian(0, 0.0, 1.25, 0.0, -1.0, 0, -1, 3.0, True, 1)
+        env.reset_cars(0, v, -45.0, 0.0, 0.0)
+        if env.n_slots > 1:
+            env.reset_cars(1, v, -22.0, 0.0, 1.0)
+        return env.observe()                                  # state = self.env.get_state(), PY:173
+
+    def iterations_dataset(self, actor_net_cross, actor_net_wait, actor_net_choice, snapshot, **kw):
+        """Env_rollout.iterations_dataset (PY:255-355): one deterministic evaluation episode from every scenario of a stored
+        dataset.  The reference unpickles a list of deep-copied envs (`test_data_23.pickle`, not shipped); here the dataset
+        is a snapshot file of VecCrosswalkEnv.save_state (one scenario per env)."""
+        self.env.load_state(snapshot)
+        return self.iterations(actor_net_cross, actor_net_wait, actor_net_choice, 1, start="current", **kw)
+
     def iterations(self, actor_net_cross, actor_net_wait, actor_net_choice, nbr_episodes, choix=False, record_obs=True,
-                   record_waiting=True):
+                   record_waiting=True, start="reset"):
         """Deterministic evaluation rollout (PY:152-252): `nbr_episodes` episodes in every env, argmax decisions (re-taken
         every step while ped_traffic != nb_ped), accelerations = min over all pedestrian slots of the cross / wait net or
         the speed-recovery action, capped by (10 - v)/dt.  Returns a dict of CUDA tensors, episode-major:
@@ -97,8 +116,6 @@ class Env_rollout:
           after each step).  `reference_batches(out, n)` rebuilds the reference's return values for env n."""
         if self.legacy:
             raise NotImplementedError("the deterministic evaluation rollout is built for Coop-MH-PPO-scalable.py only")
-        if choix:
-            self.choix_test()
         env, L, cfg, st = self.env, self._L, self._cfg, self._stream()
         N, Cn, P, T, dev = self.N, self.C, self.P, self.T, env.device
         self._set_head(actor_net_cross)
@@ -115,7 +132,12 @@ class Env_rollout:
         none = View(None, 0, 0)
         lo, hi = float(env.car_b[0, 0]), float(env.car_b[1, 0])
         for e in range(E):
-            env.reset()
+            if start == "current" and e == 0:
+                env.observe()                            # state = self.env.get_state(), PY:275
+            else:
+                env.reset()
+                if choix:
+                    self.choix_test()                    # PY:171-173
             for t in range(T):
                 check(L.mhppo_choice_eval(C.byref(cfg), env._obs.data_ptr(), actor_net_choice.flat.data_ptr(), int(t == 0),
                                           self.action_d.data_ptr(), st))

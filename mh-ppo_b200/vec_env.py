@@ -184,6 +184,47 @@ class VecCrosswalkEnv:
                                              self._stream()))
         torch.cuda.current_stream(dev).synchronize()   # `t` must outlive the kernel
 
+    # -- state injection (fixed scenarios: choix_test PY:629-633, reset_distrib NA:903-913) ----------------------------
+    def _params(self, vals, width):
+        a = torch.zeros(self.n_envs, width, device=self.device)
+        for k, v in enumerate(vals):
+            a[:, k] = torch.as_tensor(v, dtype=torch.float32, device=self.device) if not isinstance(v, (int, float, bool)) else float(v)
+        return a
+
+    def _mask(self, mask):
+        return None if mask is None else torch.as_tensor(mask).to(device=self.device, dtype=torch.uint8).contiguous()
+
+    def reset_pedestrian(self, num_ped, *vals, mask=None):
+        """env.reset_pedestrian(num_ped, speed_x, speed_y, pos_x, pos_y, dl, leave, CZ, exist, direction) (SC:948-955) in the
+        masked envs (default: all); every value a scalar or an [N] array.  naif: (num_ped, speed_x, speed_y, pos_x, pos_y, dl,
+        direction, cross) (NA:897).  Like the reference it rebuilds every pedestrian as a placeholder first (not in naif)."""
+        want = 7 if self.variant == "naif" else 9
+        if len(vals) != want:
+            raise TypeError("reset_pedestrian of %s takes %d values after num_ped" % (self.variant, want))
+        prm, m = self._params(vals, 9), self._mask(mask)
+        check(self._L.mhppo_env_reset_pedestrian(self._h, int(num_ped), prm.data_ptr(), None if m is None else m.data_ptr(), self._stream()))
+        torch.cuda.current_stream(self.device).synchronize()      # prm / m must outlive the kernel
+
+    def reset_cars(self, num_car, speed_x, pos_x, light, line, mask=None):
+        """env.reset_cars(num_car, speed_x, pos_x, light, line) (SC:957-958)."""
+        prm, m = self._params((speed_x, pos_x, light, line), 4), self._mask(mask)
+        check(self._L.mhppo_env_reset_cars(self._h, int(num_car), prm.data_ptr(), None if m is None else m.data_ptr(), self._stream()))
+        torch.cuda.current_stream(self.device).synchronize()
+
+    def reset_distrib(self, state_distrib, mask=None):
+        """naif's reset_distrib (NA:903-913): state_distrib [N, 5*nb_ped + nb_car + 1] = per pedestrian (speed_x, speed_y, pos_x,
+        pos_y, direction sign), per car its position, then the crossing width; cars restart at 10 m/s, light 0, line = index."""
+        if self.variant != "naif":
+            raise NotImplementedError("reset_distrib exists on the naif env class only (NA:903)")
+        sd = torch.as_tensor(state_distrib, dtype=torch.float32, device=self.device).reshape(self.n_envs, -1)
+        P, Cn = self.nb_ped, self.nb_car
+        cross = sd[:, Cn + 5 * P]
+        for i in range(P):
+            d = torch.where(sd[:, 5 * i + 4] >= 0, 1.0, -1.0)
+            self.reset_pedestrian(i, sd[:, 5 * i], sd[:, 5 * i + 1], sd[:, 5 * i + 2], sd[:, 5 * i + 3], 0.0, d, cross, mask=mask)
+        for i in range(Cn):
+            self.reset_cars(i, 10.0, sd[:, i + 5 * P], 0.0, float(i), mask=mask)
+
     # -- scenario snapshots (the reference pickles copy.deepcopy(env) per scenario, PY:255-277, 1873-1883) ----------
     def save_state(self, path):
         """Write the canonical state dump of every env (include/mhppo.h "state dump") plus the constructor arguments to

@@ -28,7 +28,7 @@
 #define PI 3.141592653589793 /* math.pi */
 
 enum { F_EXIST = 0, F_IS_CROSSING, F_DECISION, F_AT_CROSSING, F_PED_LEFT, F_PED_IN_CROSS,
-       F_NOT_WAITING, F_ACCIDENT, F_WORST_ACC, F_FOLLOW_RULE, F_STOP, F_NEED_TO_STOP };
+       F_NOT_WAITING, F_ACCIDENT, F_WORST_ACC, F_FOLLOW_RULE, F_STOP, F_NEED_TO_STOP, F_RATIO_EPS };
 
 typedef struct {
     double Ac, Vc, Sc, light, pa, es, Ts;
@@ -40,6 +40,7 @@ typedef struct {
     int t0c, waitc, crossc, time_stop, line_pos, dir, gender, age;
     int exist, is_crossing, decision, at_crossing, ped_left, ped_in_cross, not_waiting, accident,
         worst_acc, follow_rule, stop, need_to_stop;
+    int ratio_eps;          /* set by reset_ped: ratio = v0x / (v0y + 1e-3) (SC:111) instead of the constructor's v0x / v0y (SC:73) */
 } OPed;
 
 typedef struct {
@@ -312,7 +313,7 @@ static void ped_step(Ctx *x, OPed *p, double time, int n, const double *Vc, cons
                 p->Vpx = 0.0; p->Vpy = 0.0;
                 p->t0c += 1;
             } else if ((!change_line) || (change_line && new_choice)) {   /* SC:382-387 */
-                double ratio = p->v0x / p->v0y;                            /* SC:73 */
+                double ratio = p->ratio_eps ? p->v0x / (p->v0y + 1e-3) : p->v0x / p->v0y;   /* SC:73 / SC:111 */
                 p->Spy = new_spy; p->Vpy = new_vpy;
                 p->Spx = p->Spx + p->Vpy * ratio * dt;
                 p->Vpx = p->Vpy * ratio;
@@ -646,6 +647,57 @@ static void env_reset(const OHandle *h, OEnv *e, float *obs) {
     store_round(h, e);
 }
 
+/* State injection.
+ * reset_pedestrian, SC:948-955 (CO:895-902, ST:904-911, C4:913-920, C42:929-936): EVERY pedestrian is rebuilt as a placeholder
+ * (constructor draws consumed, SC:949-951), then pedestrian.reset_ped (SC:106-137) on slot num_ped with
+ * q = (speed_x, speed_y, pos_x, pos_y, dl, leave, CZ, exist, direction); `leave` / `CZ` are stored as their truth value.
+ * naif (NA:897-898 -> NA:100-135): no rebuild, q = (speed_x, speed_y, pos_x, pos_y, dl, direction, cross): the pedestrian's cross
+ * becomes `cross` (here: the env's, which every pedestrian shares), speed_y and pos_y are relative to the direction / kerb. */
+static void env_reset_pedestrian(const OHandle *h, OEnv *e, int num_ped, const double *q) {
+    Ctx x = { h, e };
+    const mho_cfg *c = &h->c; const int L = c->nb_lines;
+    OPed *p = &e->ped[num_ped];
+    if (c->variant == MHO_NAIF) {
+        e->cross = q[6];                                                   /* NA:101-102 */
+        const double W = L * e->cross;
+        p->dir = (int)q[5];                                                /* NA:103 */
+        p->v0x = q[0]; p->v0y = q[1] * p->dir;                             /* NA:104 */
+        p->Spx = q[2]; p->Spy = (q[3] - W / 2.) * p->dir;                  /* NA:106 */
+        p->delta = q[4]; p->exist = 1; p->ped_left = 0; p->ped_in_cross = 0;   /* NA:115-120 */
+    } else {
+        for (int j = 0; j < c->nb_ped; ++j) ped_init(&x, &e->ped[j], 0, 0);    /* SC:949-951 */
+        p->v0x = q[0]; p->v0y = q[1]; p->Spx = q[2]; p->Spy = q[3];        /* SC:107-110 */
+        p->dir = (int)q[8];                                                /* SC:115 */
+        p->delta = q[4]; p->exist = q[7] != 0.0; p->ped_left = q[5] != 0.0; p->ped_in_cross = q[6] != 0.0;   /* SC:117-123 */
+    }
+    p->Vpx = p->v0x; p->Vpy = p->v0y;
+    p->ratio_eps = 1;                                                      /* SC:111 */
+    p->line_pos = L * (p->dir < 0) - 1 * (p->dir > 0);                     /* SC:116 */
+    p->is_crossing = 1;                                                    /* SC:124 */
+    (void)cg_score(&x, p, L * e->cross);                                   /* SC:125: the value is dead, the draw is not */
+    p->t0c = 0;                                                            /* SC:127 */
+    store_round(h, e);
+}
+/* reset_cars -> car.reset_car, SC:957-958, 583-587: q = (speed_x, pos_x, light, line) */
+static void env_reset_car(const OHandle *h, OEnv *e, int num_car, const double *q) {
+    OCar *c = &e->car[num_car];
+    c->Sc = q[1]; c->Vc = q[0]; c->light = q[2]; c->line = (int)q[3];
+    store_round(h, e);
+}
+void mho_reset_pedestrian(void *hh, int num_ped, const double *params, const uint8_t *mask) {
+    OHandle *h = (OHandle *)hh;
+    for (int64_t n = 0; n < h->N; ++n) if (!mask || mask[n]) env_reset_pedestrian(h, &h->env[n], num_ped, params + n * 9);
+}
+void mho_reset_cars(void *hh, int num_car, const double *params, const uint8_t *mask) {
+    OHandle *h = (OHandle *)hh;
+    for (int64_t n = 0; n < h->N; ++n) if (!mask || mask[n]) env_reset_car(h, &h->env[n], num_car, params + n * 4);
+}
+/* get_state, SC:960-969: the observation of the current state (all car slots are handed to get_data, as in reset) */
+void mho_observe(void *hh, float *obs) {
+    OHandle *h = (OHandle *)hh;
+    for (int64_t n = 0; n < h->N; ++n) { Ctx x = { h, &h->env[n] }; write_obs(&x, obs + n * h->nobs, 1); store_round(h, &h->env[n]); }
+}
+
 /* step, SC:789-878 (CO:745-832, C4:783-844, C42:799-860) */
 static int env_step(const OHandle *h, OEnv *e, const double *act, float *obs, double *rewards,
                     double *reward_light) {
@@ -841,6 +893,7 @@ static unsigned pack_flags(const OPed *p) {
     f |= (unsigned)(p->not_waiting != 0) << F_NOT_WAITING; f |= (unsigned)(p->accident != 0) << F_ACCIDENT;
     f |= (unsigned)(p->worst_acc != 0) << F_WORST_ACC; f |= (unsigned)(p->follow_rule != 0) << F_FOLLOW_RULE;
     f |= (unsigned)(p->stop != 0) << F_STOP; f |= (unsigned)(p->need_to_stop != 0) << F_NEED_TO_STOP;
+    f |= (unsigned)(p->ratio_eps != 0) << F_RATIO_EPS;
     return f;
 }
 
@@ -890,6 +943,7 @@ void mho_set_state(void *hh, const double *car_f, const int32_t *car_i, const do
             p->not_waiting = (fl >> F_NOT_WAITING) & 1; p->accident = (fl >> F_ACCIDENT) & 1;
             p->worst_acc = (fl >> F_WORST_ACC) & 1; p->follow_rule = (fl >> F_FOLLOW_RULE) & 1;
             p->stop = (fl >> F_STOP) & 1; p->need_to_stop = (fl >> F_NEED_TO_STOP) & 1;
+            p->ratio_eps = (fl >> F_RATIO_EPS) & 1;
         }
         e->cross = env_f[n];
         e->step_idx = (int)env_i[n * 4 + 0]; e->ped_traffic = (int)env_i[n * 4 + 1];

@@ -53,6 +53,9 @@ def lib():
         L.mho_step.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int, vp]
         L.mho_get_state.argtypes = [vp] * 7
         L.mho_set_state.argtypes = [vp] * 7
+        L.mho_reset_pedestrian.argtypes = [vp, C.c_int, vp, vp]
+        L.mho_reset_cars.argtypes = [vp, C.c_int, vp, vp]
+        L.mho_observe.argtypes = [vp, vp]
         L.mho_philox.argtypes = [C.c_uint32, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint32 * 4)]
         for f in ("mho_n_slots", "mho_n_lead", "mho_n_action", "mho_n_obs"):
             getattr(L, f).argtypes = [C.POINTER(Cfg)]
@@ -121,6 +124,29 @@ class OracleVecEnv:
         if want_term_obs:
             return obs, rew, rl, done.astype(bool), term
         return obs, rew, rl, done.astype(bool)
+
+    def _params(self, vals, width):
+        a = np.zeros((self.N, width), np.float64)
+        for k, v in enumerate(vals):
+            a[:, k] = np.asarray(v, np.float64)
+        return a
+
+    def reset_pedestrian(self, num_ped, *vals, mask=None):
+        """env.reset_pedestrian(num_ped, speed_x, speed_y, pos_x, pos_y, dl, leave, CZ, exist, direction) (SC:948-955; naif:
+        (.., dl, direction, cross), NA:897) in the masked envs; every value a scalar or an [N] array."""
+        m = None if mask is None else np.ascontiguousarray(mask, np.uint8)
+        lib().mho_reset_pedestrian(self._h, int(num_ped), _ptr(self._params(vals, 9)), _ptr(m))
+
+    def reset_cars(self, num_car, *vals, mask=None):
+        """env.reset_cars(num_car, speed_x, pos_x, light, line) (SC:957-958)."""
+        m = None if mask is None else np.ascontiguousarray(mask, np.uint8)
+        lib().mho_reset_cars(self._h, int(num_car), _ptr(self._params(vals, 4)), _ptr(m))
+
+    def observe(self):
+        """env.get_state() (SC:960-969)."""
+        obs = np.empty((self.N, self.n_obs), np.float32)
+        lib().mho_observe(self._h, _ptr(obs))
+        return obs
 
     def get_state(self):
         N, Cn, P = self.N, self.C, self.P

@@ -111,6 +111,9 @@ def extract_state(env):
                           (F_FOLLOW_RULE, "follow_rule"), (F_STOP, "stop"), (F_NEED_TO_STOP, "need_to_stop")):
             if bool(getattr(p, name, False)):
                 flags |= 1 << bit
+        # reset_ped (SC:111) replaces the constructor's ratio v0x / v0y (SC:73) by v0x / (v0y + 1e-3): canonical flag bit 12
+        if p.initial_speed[1] != 0 and p.ratio != p.initial_speed[0] / p.initial_speed[1]:
+            flags |= 1 << 12
         ped_i[j] = [int(round(p.t0 / dt)), int(round(p.waiting_time / dt)), int(round(p.crossing_time / dt)),
                     int(p.time_stop), int(p.line_pos), int(p.direction), int(p.gender), int(p.age), flags]
     env_f = np.array([env.cross], np.float64)

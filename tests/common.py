@@ -80,3 +80,42 @@ def compare_vec_envs(ref_env, got_env, n_steps, rng, rtol=1e-5, autoreset=True, 
                 assert_equal("state." + k, sr[k], to_np(sg[k]), ctx)
             for k in FLT_KEYS:
                 assert_close("state." + k, sr[k], to_np(sg[k]), rtol, atol, ctx=ctx)
+
+
+def inject_and_compare(ref_env, got_env, variant, rng, n_steps=80, rtol=1e-5, to_np=lambda x: np.asarray(x)):
+    """State injection (reset_pedestrian / reset_cars / get_state, SC:948-969) with per-env parameters into half of the envs
+    of two vectorised envs after a common reset, then `n_steps` free-running steps: ints bit-exact, floats within rtol."""
+    N = ref_env.N
+    ref_env.reset(); got_env.reset()
+    mask = (np.arange(N) % 2 == 0).astype(np.uint8)
+    f32 = lambda a: np.asarray(a, np.float32)
+    if variant == "naif":
+        cross = f32(rng.uniform(2.5, 3.0, N))
+        for j in range(ref_env.P):
+            vals = (f32(rng.uniform(-0.05, 0.05, N)), f32(rng.uniform(0.75, 1.75, N)), f32(rng.uniform(0, 4, N)), f32(rng.uniform(-3, -0.5, N)),
+                    0.0, f32(rng.choice([-1.0, 1.0], N)), cross, 0.0, 0.0)
+            ref_env.reset_pedestrian(j, *vals[:7], mask=mask); got_env.reset_pedestrian(j, *vals[:7], mask=mask)
+    else:
+        d = f32(rng.choice([-1.0, 1.0], N))
+        vals = (f32(rng.uniform(-0.05, 0.05, N)), f32(rng.uniform(0.75, 1.75, N)) * d, f32(rng.uniform(0, 4, N)), f32(rng.uniform(-3.5, -1.0, N)) * d,
+                0.0, 0.0, 0.0, 1.0, d)
+        ref_env.reset_pedestrian(0, *vals, mask=mask); got_env.reset_pedestrian(0, *vals, mask=mask)
+    for i in range(min(2, ref_env.C)):
+        lanes = int(ref_env.cfg.nb_lines)
+        cv = (f32(rng.uniform(5, 10, N)), f32(rng.uniform(-50, -15, N)), 0.0, float(i % 2) if lanes > 1 else 0.0)   # a valid lane: line < nb_lines
+        ref_env.reset_cars(i, *cv, mask=mask); got_env.reset_cars(i, *cv, mask=mask)
+    assert_close("obs(get_state)", ref_env.observe(), to_np(got_env.observe()), rtol, ATOL_F32)
+    for t in range(n_steps):
+        a = random_actions(rng, N, ref_env.n_action)
+        ro, rr, rl, rd = ref_env.step(a.astype(np.float64), autoreset=False)
+        go, gr, gl, gd = got_env.step(a, autoreset=False)
+        ctx = "(step %d after injection)" % t
+        assert_close("obs", ro, to_np(go), rtol, ATOL_F32, ctx=ctx)
+        assert_close("rewards", rr, to_np(gr), rtol, ATOL_F32, ctx=ctx)
+        assert_close("reward_light", rl, to_np(gl), rtol, ATOL_F32, ctx=ctx)
+        if t % 8 == 0 or t == n_steps - 1:
+            sr, sg = ref_env.get_state(), got_env.get_state()
+            for k in INT_KEYS:
+                assert_equal("state." + k, sr[k], to_np(sg[k]), ctx)
+            for k in FLT_KEYS:
+                assert_close("state." + k, sr[k], to_np(sg[k]), rtol, ATOL_F32, ctx=ctx)

@@ -22,6 +22,16 @@ class CudaEnv:
         _, rew, done, _, _ = self.env.step(a)
         return (self.env.flat_obs.cpu().numpy(), rew.cpu().numpy(), self.env.reward_light.cpu().numpy(), done.cpu().numpy())
 
+    def reset_pedestrian(self, num_ped, *vals, mask=None):
+        self.env.reset_pedestrian(num_ped, *[torch.as_tensor(np.asarray(v, np.float32)).cuda() if np.ndim(v) else v for v in vals], mask=mask)
+
+    def reset_cars(self, num_car, *vals, mask=None):
+        self.env.reset_cars(num_car, *[torch.as_tensor(np.asarray(v, np.float32)).cuda() if np.ndim(v) else v for v in vals], mask=mask)
+
+    def observe(self):
+        self.env.observe()
+        return self.env.flat_obs.cpu().numpy()
+
     def get_state(self):
         return {k: v.cpu().numpy() for k, v in self.env.get_state().items()}
 

@@ -41,6 +41,30 @@ static void sim_step(Sim *s, mhppo_view actions, mhppo_view obs, mhppo_view rewa
     for (int64_t n = 0; n < s->a.N; ++n) env_step_thread<V, MC, MP, 1>(s->a, s->c, key, io, n, cars, 0);   // the kernel's thread body
 }
 
+template <int V, int MC, int MP>
+static void sim_inject(Sim *s, int what, int slot, const float *params, const uint8_t *mask) {
+    for (int64_t n = 0; n < s->a.N; ++n) {                                    // body of k_env_inject
+        if (mask && !mask[n]) continue;
+        EnvR<MC, MP> e;
+        load_env<MC, MP>(s->a, s->c, n, e);
+        const uint64_t gid = (uint64_t)(s->env_id0 + n);
+        e.rng.env_lo = (uint32_t)gid; e.rng.env_hi = (uint32_t)(gid >> 32); e.rng.k0 = s->k0; e.rng.k1 = s->k1;
+        if (what == 0) inject_pedestrian<V, MC, MP>(s->c, e, slot, params + n * 9);
+        else inject_car(e.car[slot], params + n * 4);
+        store_env<MC, MP>(s->a, s->c, n, e);
+    }
+}
+template <int V, int MC, int MP>
+static void sim_observe(Sim *s, mhppo_view obs) {
+    for (int64_t n = 0; n < s->a.N; ++n) {                                    // body of k_env_observe
+        EnvR<MC, MP> e;
+        load_env<MC, MP>(s->a, s->c, n, e);
+        ViewOut out{obs.ptr + n * obs.env_stride, obs.comp_stride};
+        write_obs<V, MC, MP>(s->c, e, true, out);
+        store_env<MC, MP>(s->a, s->c, n, e);
+    }
+}
+
 #define DISPATCH(FN, ...)                                                                          \
     do {                                                                                           \
         const int key = s->variant * 10000 + s->mc * 100 + s->mp;                                  \
@@ -90,5 +114,9 @@ void hs_import(void *h, float *car_f, int32_t *car_i, float *ped_f, int32_t *ped
     Sim *s = (Sim *)h; DumpPtrs d{car_f, car_i, ped_f, ped_i, env_f, env_i};
     for (int64_t n = 0; n < s->a.N; ++n) import_one(s->a, s->c, n, d);
 }
+int hs_inject(void *h, int what, int slot, const float *params, const uint8_t *mask) {
+    Sim *s = (Sim *)h; DISPATCH(sim_inject, s, what, slot, params, mask); return 0;
+}
+int hs_observe(void *h, View obs) { Sim *s = (Sim *)h; DISPATCH(sim_observe, s, obs); return 0; }
 int hs_sizeof_envconst(void) { return (int)sizeof(EnvConst); }
 }

@@ -64,6 +64,8 @@ def lib():
         L.hs_destroy.argtypes = [C.c_void_p]
         L.hs_reset.argtypes = [C.c_void_p, C.c_void_p, View]
         L.hs_step.argtypes = [C.c_void_p, View, View, View, View, C.c_void_p, C.c_int, View]
+        L.hs_inject.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.hs_observe.argtypes = [C.c_void_p, View]
         L.hs_export.argtypes = [C.c_void_p] * 7
         L.hs_import.argtypes = [C.c_void_p] * 7
         assert L.hs_sizeof_envconst() == C.sizeof(EnvConst)
@@ -115,6 +117,24 @@ class HostSimEnv:
                              done.ctypes.data, int(autoreset), _view(term, self.soa)) == 0
         out = (self._ret(obs), self._ret(rew), self._ret(rl), done.astype(bool))
         return out + (self._ret(term),) if want_term_obs else out
+
+    def _inject(self, what, slot, vals, width, mask):
+        a = np.zeros((self.N, width), np.float32)
+        for k, v in enumerate(vals):
+            a[:, k] = np.asarray(v, np.float32)
+        m = None if mask is None else np.ascontiguousarray(mask, np.uint8)
+        assert lib().hs_inject(self._h, what, int(slot), a.ctypes.data, None if m is None else m.ctypes.data) == 0
+
+    def reset_pedestrian(self, num_ped, *vals, mask=None):
+        self._inject(0, num_ped, vals, 9, mask)
+
+    def reset_cars(self, num_car, *vals, mask=None):
+        self._inject(1, num_car, vals, 4, mask)
+
+    def observe(self):
+        obs = self._buf(self.n_obs)
+        assert lib().hs_observe(self._h, _view(obs, self.soa)) == 0
+        return self._ret(obs)
 
     def get_state(self):
         N, Cn, P = self.N, self.C, self.P

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-from common import ALL_CONFIGS, ATOL_F32, EXTRA_CONFIGS, FLT_KEYS, INT_KEYS, assert_close, assert_equal, compare_vec_envs, random_actions
+from common import ALL_CONFIGS, ATOL_F32, EXTRA_CONFIGS, FLT_KEYS, INT_KEYS, assert_close, assert_equal, compare_vec_envs, inject_and_compare, random_actions
 from conftest import golden_files, load_golden
 
 pytestmark = pytest.mark.gpu
@@ -225,3 +225,16 @@ def test_snapshot_file_roundtrip(tmp_path):
     c = mhppo_b200.VecCrosswalkEnv("coop", N, nb_car=2, nb_ped=1, nb_lines=2, seed=11)
     with pytest.raises(ValueError):
         c.load_state(str(tmp_path / "snap.npz"))
+
+
+@pytest.mark.parametrize("cfg", [("coop_scalable", 4, 3, 2), ("coop_scalable", 1, 1, 1), ("coop", 2, 2, 2), ("stop", 2, 3, 2), ("naif", 2, 2, 2),
+                                 ("coop_4cars", 2, 2, 2), ("coop_4cars2", 2, 2, 2)], ids=lambda c: "%s_%d%d%d" % c)
+def test_state_injection_matches_oracle(oracle_mod, cuda_env_cls, cfg):
+    """reset_pedestrian / reset_cars / get_state (SC:948-969, NA:897-901) through the C ABI (mhppo_env_reset_pedestrian,
+    mhppo_env_reset_cars, mhppo_env_observe) with per-env parameters on half of 2048 envs, then 80 free-running steps
+    against the oracle (whose injection is pinned against the unmodified reference, tests/test_oracle_vs_reference.py)."""
+    v, c, p, l = cfg
+    N = 2048
+    ref = oracle_mod.OracleVecEnv(v, N, c, p, l, seed=7, env_id0=900, store_f32=True)
+    got = cuda_env_cls(v, N, c, p, l, seed=7, env_id0=900)
+    inject_and_compare(ref, got, v, np.random.default_rng(1))

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 import hostsim as H
-from common import ALL_CONFIGS, assert_close, compare_vec_envs
+from common import ALL_CONFIGS, assert_close, compare_vec_envs, inject_and_compare
 from conftest import golden_files, load_golden
 
 
@@ -35,3 +35,14 @@ def test_hostsim_tracks_reference_golden(path):
             assert_close("rewards", g["rewards"][ep, t], rew[0], 1e-4, 1e-4, ctx)
             assert_close("reward_light", g["reward_light"][ep, t], rl[0], 1e-4, 1e-4, ctx)
             assert bool(done[0]) == bool(g["done"][ep, t])
+
+
+@pytest.mark.parametrize("cfg", [("coop_scalable", 4, 3, 2), ("coop", 2, 2, 2), ("stop", 2, 3, 2), ("naif", 2, 2, 2), ("coop_4cars", 2, 2, 2),
+                                 ("coop_4cars2", 2, 2, 2)], ids=lambda c: "%s_%d%d%d" % c)
+def test_hostsim_state_injection_matches_oracle(oracle_mod, cfg):
+    """reset_pedestrian / reset_cars / get_state of the kernel logic (env_core.cuh inject_*, write_obs) vs the oracle."""
+    v, c, p, l = cfg
+    N = 512
+    ref = oracle_mod.OracleVecEnv(v, N, c, p, l, seed=7, env_id0=900, store_f32=True)
+    got = H.HostSimEnv(v, N, c, p, l, seed=7, env_id0=900)
+    inject_and_compare(ref, got, v, np.random.default_rng(1))

@@ -18,3 +18,69 @@ def test_live_reference_episode(cfg):
     for ep in range(4):
         errs = pin_oracle.compare_episode(*cfg, seed=77 + ep, env_id=5 * ep + 1, rng=rng, light_mode=["episode", "step"][ep % 2])
         assert not errs, errs[:3]
+
+
+@pytest.mark.parametrize("cfg", [("coop_scalable", 4, 3, 2), ("coop", 2, 2, 2), ("stop", 2, 3, 2), ("coop_4cars", 2, 2, 2), ("naif", 2, 2, 2)],
+                         ids=lambda c: "%s_%d%d%d" % c)
+def test_state_injection_matches_reference(cfg):
+    """reset_pedestrian / reset_cars / get_state (SC:948-969, NA:897-901): the scenario of the reference's choix_test
+    (PY:629-633) injected into the unmodified reference and into the oracle, then 80 free-running steps."""
+    from oracle import oracle as O
+    variant, c, p, l = cfg
+    rng = np.random.default_rng(5)
+    for ep in range(3):
+        seed, env_id = 300 + ep, 11 * ep + 2
+        env = rd.make_env(variant, c, p, l)
+        env._mh_rng.set_stream(seed, env_id, 0)
+        env.reset()
+        ora = O.OracleVecEnv(variant, 1, c, p, l, seed=seed, env_id0=env_id, store_f32=False, n_threads=1)
+        ora.reset()
+        v0 = float(env.state["car"][1])
+        if variant == "naif":
+            pargs = (0, 0.03 * ep, 1.25, 0.3, -1.0, 0, 1 if ep % 2 else -1, 2.75)         # (.., dl, direction, cross), NA:897
+        else:
+            pargs = (0, 0.03 * ep, 1.25 if ep % 2 == 0 else -1.1, 0.2, -1.0 if ep % 2 == 0 else 1.5, 0, -1, 3.0, True, 1 if ep % 2 == 0 else -1)   # PY:631
+        if variant == "naif":
+            # naif's reset_ped gives the PEDESTRIAN its own cross (NA:101); its only caller, reset_distrib (NA:903-913), sets
+            # env.cross to the same value and resets every pedestrian -- the env-wide form is what the vectorised state holds
+            env.cross = pargs[-1]
+            for j in range(1, p):
+                qa = (j, 0.01, 1.0 + 0.1 * j, 1.0 * j, -2.0, 0, -1 if ep % 2 else 1, pargs[-1])
+                env.reset_pedestrian(*qa); ora.reset_pedestrian(*qa)
+        env.reset_pedestrian(*pargs)
+        env.reset_cars(0, v0, -45, 0., 0.)
+        ora.reset_pedestrian(*pargs)
+        ora.reset_cars(0, v0, -45, 0., 0.)
+        if c > 1:
+            env.reset_cars(1, v0, -22, 0., 1. if l > 1 else 0.)
+            ora.reset_cars(1, v0, -22, 0., 1. if l > 1 else 0.)
+        obs_r = rd.flat_obs(env.get_state())
+        obs_o = ora.observe()[0]
+        # `leave` / `CZ` are stored as given by the reference (-1, 3.0) and as their truth value here: the two observation
+        # entries differ until the next step recomputes them (boolean_ped_position, SC:266-275)
+        ped0 = len(obs_r) - 9 * p
+        keep = np.ones(len(obs_r), bool); keep[[ped0 + 5, ped0 + 6]] = False
+        np.testing.assert_allclose(obs_o[keep], obs_r[keep], rtol=1e-6, atol=1e-6)
+        s_r, s_o = rd.extract_state(env), ora.get_state()
+        # flag bit 12 (ratio = v0x / (v0y + 1e-3), SC:111) cannot be read off the reference when v0x == 0 (both ratios are 0)
+        fmask = ~(1 << 12) if pargs[1] == 0 else -1
+        for k in ("car_f", "car_i", "ped_f", "ped_i", "env_f", "env_i"):
+            a, b = np.asarray(s_r[k], np.float64), np.asarray(s_o[k][0], np.float64)
+            if k == "ped_f" and variant in ("naif", "coop_4cars"):
+                b = b.copy(); b[:, 6] = a[:, 6]
+            if k == "ped_i":
+                a, b = a.copy(), b.copy()
+                a[:, 8] = a[:, 8].astype(np.int64) & fmask; b[:, 8] = b[:, 8].astype(np.int64) & fmask
+            np.testing.assert_allclose(b, a, rtol=1e-9, atol=1e-9, err_msg=k)
+        acts = rd.random_actions(rng, variant, c, l, 80, "episode")
+        for t in range(80 - 1):
+            o_r, rew_r, done_r, _, _ = env.step(np.asarray(acts[t], np.float64))
+            o_o, rew_o, rl_o, done_o = ora.step(acts[t][None])
+            np.testing.assert_allclose(o_o[0], rd.flat_obs(o_r), rtol=1e-6, atol=1e-6, err_msg="obs step %d" % t)
+            np.testing.assert_allclose(rew_o[0], np.asarray(rew_r, np.float64), rtol=1e-9, atol=1e-9)
+            np.testing.assert_allclose(rl_o[0], np.asarray(env.reward_light, np.float64), rtol=1e-9, atol=1e-9)
+            s_r, s_o = rd.extract_state(env), ora.get_state()
+            po, pr = s_o["ped_i"][0].copy(), s_r["ped_i"].copy()
+            po[:, 8] &= fmask; pr[:, 8] &= fmask
+            np.testing.assert_array_equal(po, pr, err_msg="ped_i step %d" % t)
+            np.testing.assert_array_equal(s_o["env_i"][0], s_r["env_i"])

@@ -419,3 +419,31 @@ def test_episode_statistics_match_oracle(mh, cfg):
         else:
             assert abs(g - w) <= 1e-5 * max(1.0, abs(w)), (k, g, w)
     np.testing.assert_allclose(np.sort(got["waiting_times"].cpu().numpy()), np.sort(want["waiting_times"]), rtol=1e-5, atol=1e-5)
+
+
+def test_choix_test_scenario_and_dataset_rollout(mh, tmp_path):
+    """choix_test (PY:629-633) through Env_rollout.iterations(choix=True), and iterations_dataset (PY:255-355) from a scenario
+    snapshot file: the fixed scenario is in place at the first recorded step, and a rollout restarted from the snapshot of
+    that state reproduces the episode bit for bit."""
+    if mh.mlp_mode != "auto":
+        pytest.skip("one mode is enough")
+    algo, env = _algo(mh, 64, 4, 10)
+    r = algo.rollout
+    env.reset()
+    obs = r.choix_test()
+    assert torch.all(obs["ped"][:, 2] == 0.0) and torch.all(obs["ped"][:, 3] == -1.0) and torch.all(obs["ped"][:, 1] == 1.25)   # ped 0 at (0, -1), 1.25 m/s
+    st = env.get_state()                                   # (an absent car still shows its placeholder row in the observation, SC:652-655)
+    assert torch.all(st["car_f"][:, 0, 2] == -45.0) and torch.all(st["car_f"][:, 1, 2] == -22.0) and torch.all(st["car_i"][:, 1, 0] == 1)
+    ex0 = st["car_i"][:, 0, 1] != 0
+    assert torch.all(obs["car"][ex0, 3] == -45.0) and torch.all(obs["car"][~ex0, 3] == -1000.0)
+    assert torch.all(obs["ped"][:, 7] == 1.0) and torch.all(obs["ped"][:, 9 + 7] == 0.0)           # the other pedestrians are placeholders again
+    path = str(tmp_path / "scenarios.npz")
+    env.save_state(path)
+    a = r.iterations(algo.actor_net_cross, algo.actor_net_wait, algo.actor_net_choice, 1, start="current")
+    b = r.iterations_dataset(algo.actor_net_cross, algo.actor_net_wait, algo.actor_net_choice, path)
+    for k in ("acts", "rews", "reward_light", "action_d"):
+        assert torch.equal(a[k], b[k]), k
+    # observations: get_state folds the current gap into the running-min delta (SC:457) once more on the reload; same values here
+    assert torch.equal(a["obs"][0, 1:], b["obs"][0, 1:])
+    c = r.iterations(algo.actor_net_cross, algo.actor_net_wait, algo.actor_net_choice, 2, choix=True)
+    assert torch.all(c["obs"][:, 0, 7 * 4 + 4 + 3, :] == -1.0) and torch.all(c["obs"][:, 0, 7 * 4 + 4 + 1, :] == 1.25)
