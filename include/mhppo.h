@@ -233,6 +233,13 @@ int mhppo_ppo_grad(int32_t n_in, int32_t head, const float *x_dev, int32_t D, in
                    int64_t CN, const float *net_dev, const float *act_dev, const float *logp_old_dev, const float *rtg_dev,
                    const float *V_dev, float adv_mean, float adv_inv_std, float inv_n, float f0, float f1, float *grad_dev,
                    double *loss_dev, void *workspace_dev, void *stream);
+/* mhppo_ppo_grad with the advantage statistics taken from DEVICE memory: adv_stats_dev = (sum A, sum A^2, n) over the whole batch
+ * (the output of mhppo_critic_grad_stats, all-reduced over the ranks); mean and 1 / (unbiased std + 1e-10) (PY:787) are derived
+ * inside the kernel, so an epoch needs no host round trip. */
+int mhppo_ppo_grad_dev(int32_t n_in, int32_t head, const float *x_dev, int32_t D, int64_t S, const int32_t *idx_dev, int64_t K,
+                       int64_t CN, const float *net_dev, const float *act_dev, const float *logp_old_dev, const float *rtg_dev,
+                       const float *V_dev, const double *adv_stats_dev, float inv_n, float f0, float f1, float *grad_dev,
+                       double *loss_dev, void *workspace_dev, void *stream);
 /* critic pass of one epoch in a single kernel: ppo_grad with head 0 that also returns V = critic(s) (PY:785) and the
  * advantage statistics (sum A, sum A^2, n) of A = rtg - V, so an epoch is critic_grad_stats -> [all-reduce stats] ->
  * ppo_grad (actor) -> [all-reduce grads] -> adam, adam; V and the statistics are those of the critic before its step,
@@ -243,6 +250,11 @@ int mhppo_critic_grad_stats(int32_t n_in, const float *x_dev, int32_t D, int64_t
 /* torch.optim.Adam defaults (PY:719-724); step counts from 1; grad_scale multiplies the gradient first */
 int mhppo_adam(float *param_dev, const float *grad_dev, float *m_dev, float *v_dev, int32_t n, float lr, float beta1,
                float beta2, float eps, int32_t step, float grad_scale, void *stream);
+
+/* the actor's and the critic's Adam step of one epoch in one launch (they act on different nets, PY:810-815) */
+int mhppo_adam2(float *p0_dev, const float *g0_dev, float *m0_dev, float *v0_dev, int32_t n0, float lr0, int32_t step0, float *p1_dev,
+                const float *g1_dev, float *m1_dev, float *v1_dev, int32_t n1, float lr1, int32_t step1, float beta1, float beta2,
+                float eps, void *stream);
 
 /* Self-test of the tcgen05 / TMEM building blocks behind the policy GEMMs: D[128,N] = A[128,K] * B[N,K]^T on one CTA,
  * mode 0 = one tf32 pass, mode 1 = 3xTF32 split accumulation.  (N,K) in {(64,32),(32,64),(64,16),(16,32)}. */

@@ -71,6 +71,10 @@ SYMBOLS = {
                                           C.c_float] + [C.c_void_p] * 6),
     "mhppo_ppo_grad": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_int64, C.c_int64]
                        + [C.c_void_p] * 5 + [C.c_float] * 5 + [C.c_void_p] * 4),
+    "mhppo_ppo_grad_dev": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_int64, C.c_int64]
+                           + [C.c_void_p] * 6 + [C.c_float] * 3 + [C.c_void_p] * 4),
+    "mhppo_adam2": (C.c_int, [C.c_void_p] * 4 + [C.c_int32, C.c_float, C.c_int32] + [C.c_void_p] * 4 + [C.c_int32, C.c_float, C.c_int32]
+                    + [C.c_float] * 3 + [C.c_void_p]),
     "mhppo_tc_failures": (C.c_int, []),
     "mhppo_set_mlp_mode": (C.c_int, [C.c_int32]),
     "mhppo_set_gaussian_head": (C.c_int, [C.c_float, C.c_float, C.c_float, C.c_float]),

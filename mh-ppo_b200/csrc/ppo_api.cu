@@ -327,7 +327,7 @@ int mhppo_value_stats(int32_t n_in, const float *x, int32_t D, int64_t S, const 
 static int ppo_grad_impl(int32_t n_in, int32_t head, const float *x, int32_t D, int64_t S, const int32_t *idx, int64_t K, int64_t CN,
                          const float *net, const float *act, const float *logp_old, const float *rtg, const float *V, float adv_mean,
                          float adv_inv_std, float inv_n, float f0, float f1, float *grad, double *loss, float *V_out, double *stats3,
-                         void *workspace, void *stream) {
+                         const double *adv_stats_dev, void *workspace, void *stream) {
     if (!x || !net || !rtg || !grad || !loss || !workspace) return api_fail(MHPPO_EINVAL, "null argument");
     if (head < 0 || head > 2) return api_fail(MHPPO_EINVAL, "head must be 0, 1 or 2");
     if (head != 0 && (!act || !logp_old || !V)) return api_fail(MHPPO_EINVAL, "actor heads need act, logp_old and V");
@@ -338,23 +338,30 @@ static int ppo_grad_impl(int32_t n_in, int32_t head, const float *x, int32_t D, 
     const Workspace w = carve(workspace, kp);
     LossArgs la; la.act = act; la.logp_old = logp_old; la.rtg = rtg; la.V = V; la.adv_mean = adv_mean; la.adv_inv_std = adv_inv_std;
     la.inv_n = inv_n; la.f0 = f0; la.f1 = f1; la.V_out = V_out; la.spartial = stats3 ? w.spartial : nullptr;
-    la.head = g_head;
+    la.head = g_head; la.stats_dev = adv_stats_dev;
     cudaStream_t s = (cudaStream_t)stream;
     int rc = (kp == 16) ? launch_grad<16>(head, ss, net, la, w, s) : ((kp == 32) ? launch_grad<32>(head, ss, net, la, w, s) : launch_grad<56>(head, ss, net, la, w, s));
     if (rc) return rc;
     const int npar = net_params(kp);
-    k_reduce_partials<<<(npar + 255) / 256, 256, 0, s>>>(w.gpartial, kGradGrid, npar, grad);
-    k_reduce_scalars<<<1, 32, 0, s>>>(w.lpartial, kGradGrid, 1, loss);
-    api_count_launch(); api_count_launch();
-    if (stats3) { k_reduce_scalars<<<1, 32, 0, s>>>(w.spartial, kGradGrid, 3, stats3); api_count_launch(); }
-    return ck(cudaGetLastError(), "k_reduce_partials");
+    k_reduce_all<<<(npar + 255) / 256, 256, 0, s>>>(w.gpartial, kGradGrid, npar, grad, w.lpartial, loss, w.spartial, stats3);
+    api_count_launch();
+    return ck(cudaGetLastError(), "k_reduce_all");
 }
 
 int mhppo_ppo_grad(int32_t n_in, int32_t head, const float *x, int32_t D, int64_t S, const int32_t *idx, int64_t K, int64_t CN,
                    const float *net, const float *act, const float *logp_old, const float *rtg, const float *V, float adv_mean,
                    float adv_inv_std, float inv_n, float f0, float f1, float *grad, double *loss, void *workspace, void *stream) {
     return ppo_grad_impl(n_in, head, x, D, S, idx, K, CN, net, act, logp_old, rtg, V, adv_mean, adv_inv_std, inv_n, f0, f1, grad, loss,
-                         nullptr, nullptr, workspace, stream);
+                         nullptr, nullptr, nullptr, workspace, stream);
+}
+
+int mhppo_ppo_grad_dev(int32_t n_in, int32_t head, const float *x, int32_t D, int64_t S, const int32_t *idx, int64_t K, int64_t CN,
+                       const float *net, const float *act, const float *logp_old, const float *rtg, const float *V,
+                       const double *adv_stats_dev, float inv_n, float f0, float f1, float *grad, double *loss, void *workspace,
+                       void *stream) {
+    if (!adv_stats_dev) return api_fail(MHPPO_EINVAL, "null argument");
+    return ppo_grad_impl(n_in, head, x, D, S, idx, K, CN, net, act, logp_old, rtg, V, 0.f, 0.f, inv_n, f0, f1, grad, loss, nullptr, nullptr,
+                         adv_stats_dev, workspace, stream);
 }
 
 int mhppo_critic_grad_stats(int32_t n_in, const float *x, int32_t D, int64_t S, const int32_t *idx, int64_t K, int64_t CN,
@@ -362,7 +369,7 @@ int mhppo_critic_grad_stats(int32_t n_in, const float *x, int32_t D, int64_t S, 
                             void *workspace, void *stream) {
     if (!V || !stats3) return api_fail(MHPPO_EINVAL, "null argument");
     return ppo_grad_impl(n_in, 0, x, D, S, idx, K, CN, critic, nullptr, nullptr, rtg, nullptr, 0.f, 0.f, inv_n, 0.f, 0.f, grad, loss, V,
-                         stats3, workspace, stream);
+                         stats3, nullptr, workspace, stream);
 }
 
 int mhppo_adam(float *p, const float *g, float *m, float *v, int32_t n, float lr, float beta1, float beta2, float eps, int32_t step,
@@ -373,6 +380,20 @@ int mhppo_adam(float *p, const float *g, float *m, float *v, int32_t n, float lr
     k_adam<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, beta1, beta2, step_size, inv_sqrt_bc2, eps, grad_scale);
     api_count_launch();
     return ck(cudaGetLastError(), "k_adam");
+}
+
+int mhppo_adam2(float *p0, const float *g0, float *m0, float *v0, int32_t n0, float lr0, int32_t step0, float *p1, const float *g1,
+                float *m1, float *v1, int32_t n1, float lr1, int32_t step1, float beta1, float beta2, float eps, void *stream) {
+    if (!p0 || !g0 || !m0 || !v0 || !p1 || !g1 || !m1 || !v1 || n0 <= 0 || n1 <= 0 || step0 < 1 || step1 < 1) return api_fail(MHPPO_EINVAL, "bad argument");
+    auto mk = [&](float *p, const float *g, float *m, float *v, int n, float lr, int step) {
+        const double bc1 = 1.0 - std::pow((double)beta1, (double)step), bc2 = 1.0 - std::pow((double)beta2, (double)step);
+        AdamArgs a; a.p = p; a.g = g; a.m = m; a.v = v; a.n = n; a.step_size = (float)((double)lr / bc1); a.inv_sqrt_bc2 = (float)(1.0 / std::sqrt(bc2));
+        return a;
+    };
+    const int nmax = n0 > n1 ? n0 : n1;
+    k_adam2<<<dim3((nmax + 255) / 256, 2), 256, 0, (cudaStream_t)stream>>>(mk(p0, g0, m0, v0, n0, lr0, step0), mk(p1, g1, m1, v1, n1, lr1, step1), beta1, beta2, eps);
+    api_count_launch();
+    return ck(cudaGetLastError(), "k_adam2");
 }
 
 }  // extern "C"

@@ -92,7 +92,19 @@ struct LossArgs {
     float *V_out;                              // critic only, optional: V[s] of this forward pass and the advantage statistics
     double *spartial;                          //   [grid][3] partial (sum A, sum A^2, n) with A = rtg - V (replaces k_value_stats)
     HeadCfg head;                              // Gaussian head (HEAD == 1)
+    const double *stats_dev;                   // actor heads, optional: (sum A, sum A^2, n) of the whole (all-rank) batch in device
+                                               //   memory; adv_mean / adv_inv_std are then derived in the kernel (no host round trip)
 };
+
+// advantage normalisation of PY:787 from the partial sums: mean, 1 / (unbiased std + 1e-10) (Algo_PPO.combine_stats)
+__device__ __forceinline__ void resolve_adv_stats(LossArgs &la) {
+    if (!la.stats_dev) return;
+    const double sA = la.stats_dev[0], sAA = la.stats_dev[1], n = la.stats_dev[2];
+    if (n < 1.0) { la.adv_mean = 0.f; la.adv_inv_std = 0.f; return; }
+    const double mean = sA / n;
+    const double var = (n > 1.0) ? fmax(sAA - n * mean * mean, 0.0) / (n - 1.0) : nan("");
+    la.adv_mean = (float)mean; la.adv_inv_std = (float)(1.0 / (sqrt(var) + 1e-10));
+}
 
 // ---- register-tiled dense layers for the fused kernel -------------------------------------------------
 // The first version read one weight per FFMA from shared memory (a 128-bit broadcast load feeds 4 FFMAs of
@@ -380,6 +392,7 @@ template <int KP, int HEAD>
 __global__ void __launch_bounds__(kMlpBlock, 1) k_ppo_grad(SampleSet ss, const float *__restrict__ net, LossArgs la,
                                                            float *__restrict__ gpartial /* [grid][net_params] */,
                                                            double *__restrict__ lpartial /* [grid] */) {
+    resolve_adv_stats(la);
     extern __shared__ __align__(16) float smem[];
     typedef GradCfg<KP> G;
     constexpr int R = G::R, ROW = G::ROW;
@@ -462,6 +475,22 @@ __global__ void __launch_bounds__(256) k_reduce_partials(const float *__restrict
     for (int b = 0; b < nblocks; ++b) acc += gpartial[(size_t)b * npar + i];
     grad[i] = acc;
 }
+// gradient partials, loss partials and (optionally) the advantage-statistics partials of one ppo_grad launch in ONE kernel
+__global__ void __launch_bounds__(256) k_reduce_all(const float *__restrict__ gpartial, int nblocks, int npar, float *__restrict__ grad,
+                                                    const double *__restrict__ lpartial, double *__restrict__ loss,
+                                                    const double *__restrict__ spartial, double *__restrict__ stats) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i < npar) {
+        float acc = 0.f;
+        for (int b = 0; b < nblocks; ++b) acc += gpartial[(size_t)b * npar + i];
+        grad[i] = acc;
+    }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x >= 252) {               // four idle-ish lanes of the last block: the scalars
+        const int j = threadIdx.x - 252;                                    // 0: loss, 1..3: sum A, sum A^2, n
+        if (j == 0) { double acc = 0.0; for (int b = 0; b < nblocks; ++b) acc += lpartial[b]; *loss = acc; }
+        else if (stats) { double acc = 0.0; for (int b = 0; b < nblocks; ++b) acc += spartial[(size_t)b * 3 + (j - 1)]; stats[j - 1] = acc; }
+    }
+}
 __global__ void k_reduce_scalars(const double *__restrict__ partial, int nblocks, int width, double *__restrict__ out) {
     const int j = threadIdx.x;
     if (j >= width) return;
@@ -481,6 +510,19 @@ __global__ void __launch_bounds__(256) k_adam(float *__restrict__ p, const float
     const float vi = beta2 * v[i] + (1.0f - beta2) * gi * gi;            // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
     m[i] = mi; v[i] = vi;
     p[i] = p[i] - step_size * (mi / (sqrtf(vi) * inv_sqrt_bc2 + eps));
+}
+
+// both Adam steps of one epoch (actor and critic of a pair act on different nets, PY:810-815) in one launch
+struct AdamArgs { float *p; const float *g; float *m, *v; int n; float step_size, inv_sqrt_bc2; };
+__global__ void __launch_bounds__(256) k_adam2(AdamArgs a0, AdamArgs a1, float beta1, float beta2, float eps) {
+    const AdamArgs a = blockIdx.y ? a1 : a0;
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= a.n) return;
+    const float gi = a.g[i];
+    const float mi = beta1 * a.m[i] + (1.0f - beta1) * gi;
+    const float vi = beta2 * a.v[i] + (1.0f - beta2) * gi * gi;
+    a.m[i] = mi; a.v[i] = vi;
+    a.p[i] = a.p[i] - a.step_size * (mi / (sqrtf(vi) * a.inv_sqrt_bc2 + eps));
 }
 
 }  // namespace mhppo

@@ -89,6 +89,7 @@ template <int HEAD>
 __global__ void __launch_bounds__(kTcGradBlock, 1) k_ppo_grad_tc(SampleSet ss, const float *__restrict__ net, LossArgs la,
                                                               float *__restrict__ gpartial, double *__restrict__ lpartial,
                                                               int *__restrict__ fail_flag) {
+    resolve_adv_stats(la);
     constexpr int KP = 16, ROW = kTcGradRow, NG = kTcGradW / 64, NT = kTcGradBlock;
     typedef WgradAcc<KP, NG> WG;
     extern __shared__ __align__(1024) float smem[];

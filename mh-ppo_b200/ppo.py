@@ -88,6 +88,13 @@ class Algo_PPO:
         self._loss = torch.zeros(2, dtype=torch.float64, device=dev)
         self.last_losses = {}
         self._sel_cache = {}
+        # one contiguous gradient buffer per (actor, critic) pair: a single all-reduce per epoch carries both
+        self._gbuf = {}
+        for name, actor, critic in (("cross", self.actor_net_cross, self.critic_net_cross), ("wait", self.actor_net_wait, self.critic_net_wait),
+                                    ("choice", self.actor_net_choice, self.critic_net_choice)):
+            g = torch.zeros(actor.n_param + critic.n_param, device=dev)
+            actor.grad, critic.grad = g[:actor.n_param], g[actor.n_param:]
+            self._gbuf[id(actor)] = g
         self.sync_parameters()
 
     def sync_parameters(self):
@@ -147,14 +154,20 @@ class Algo_PPO:
         check(L.mhppo_critic_grad_stats(13, r.obs_c.data_ptr(), 13, r.S, idx.data_ptr(), K, r.M, critic.flat.data_ptr(),
                                         r.rtg.data_ptr(), 1.0 / n, critic.grad.data_ptr(), self._loss.data_ptr() + 8,
                                         r.V.data_ptr(), self._stats.data_ptr(), ws, st))
-        mean, inv_std, n2 = combine_stats(allreduce_sum_(self._stats).cpu())
-        assert n2 == n, (n2, n)
-        check(L.mhppo_ppo_grad(13, 1, r.obs_c.data_ptr(), 13, r.S, idx.data_ptr(), K, r.M, actor.flat.data_ptr(),
-                               r.act.data_ptr(), r.logp.data_ptr(), r.rtg.data_ptr(), r.V.data_ptr(), mean, inv_std, 1.0 / n,
-                               0.0, 0.0, actor.grad.data_ptr(), self._loss.data_ptr(), ws, st))
-        allreduce_sum_(actor.grad); allreduce_sum_(critic.grad)
-        opti_actor.step(); opti_critic.step()
+        allreduce_sum_(self._stats)                          # (sum A, sum A^2, n) over all ranks; normalised inside the actor kernel
+        check(L.mhppo_ppo_grad_dev(13, 1, r.obs_c.data_ptr(), 13, r.S, idx.data_ptr(), K, r.M, actor.flat.data_ptr(),
+                                   r.act.data_ptr(), r.logp.data_ptr(), r.rtg.data_ptr(), r.V.data_ptr(), self._stats.data_ptr(), 1.0 / n,
+                                   0.0, 0.0, actor.grad.data_ptr(), self._loss.data_ptr(), ws, st))
+        self._step_pair(actor, critic, opti_actor, opti_critic)
         return True
+
+    def _step_pair(self, actor, critic, opti_actor, opti_critic):
+        """All-reduce the pair's packed gradients (one collective) and take both Adam steps in one launch (PY:810-815)."""
+        allreduce_sum_(self._gbuf[id(actor)])
+        actor.step += 1; critic.step += 1
+        check(_lib.lib().mhppo_adam2(actor.flat.data_ptr(), actor.grad.data_ptr(), actor.m.data_ptr(), actor.v.data_ptr(), actor.n_param,
+                                     opti_actor.lr, actor.step, critic.flat.data_ptr(), critic.grad.data_ptr(), critic.m.data_ptr(),
+                                     critic.v.data_ptr(), critic.n_param, opti_critic.lr, critic.step, 0.9, 0.999, 1e-8, self._stream()))
 
     # -- one epoch of train_model_d (PY:818-851) on the choice buffer -------------------------------------------
     def train_model_d(self, actor, critic, opti_actor, opti_critic):
@@ -167,18 +180,24 @@ class Algo_PPO:
         check(L.mhppo_critic_grad_stats(D, r.obs_d.data_ptr(), D, r.M, idx.data_ptr(), K, r.M, critic.flat.data_ptr(),
                                         r.rew_d.data_ptr(), 1.0 / n, critic.grad.data_ptr(), self._loss.data_ptr() + 8,
                                         r.V_d.data_ptr(), self._stats.data_ptr(), ws, st))
-        ex = r.exist.view(-1) != 0
-        cnt = torch.stack([(ex & (r.act_d == 0)).sum(), (ex & (r.act_d == 1)).sum()]).double()
-        mean, inv_std, n2 = combine_stats(allreduce_sum_(self._stats).cpu())
-        assert n2 == n, (n2, n)
-        cnt = allreduce_sum_(cnt).cpu()
-        f0, f1 = float(cnt[0]) / n, float(cnt[1]) / n
-        check(L.mhppo_ppo_grad(D, 2, r.obs_d.data_ptr(), D, r.M, idx.data_ptr(), K, r.M, actor.flat.data_ptr(),
-                               r.act_d.data_ptr(), r.logp_d.data_ptr(), r.rew_d.data_ptr(), r.V_d.data_ptr(), mean, inv_std,
-                               1.0 / n, f0, f1, actor.grad.data_ptr(), self._loss.data_ptr(), ws, st))
-        allreduce_sum_(actor.grad); allreduce_sum_(critic.grad)
-        opti_actor.step(); opti_critic.step()
+        allreduce_sum_(self._stats)
+        f0, f1 = self._action_fractions(n)
+        check(L.mhppo_ppo_grad_dev(D, 2, r.obs_d.data_ptr(), D, r.M, idx.data_ptr(), K, r.M, actor.flat.data_ptr(),
+                                   r.act_d.data_ptr(), r.logp_d.data_ptr(), r.rew_d.data_ptr(), r.V_d.data_ptr(), self._stats.data_ptr(),
+                                   1.0 / n, f0, f1, actor.grad.data_ptr(), self._loss.data_ptr(), ws, st))
+        self._step_pair(actor, critic, opti_actor, opti_critic)
         return True
+
+    def _action_fractions(self, n):
+        """Fractions of the choice samples (all ranks) whose action is 0 / 1: the (M, M) broadcast of PY:834-842 collapses to
+        them.  Fixed for the epochs of an update: counted once per rollout."""
+        if "f01" not in self._sel_cache:
+            r = self.rollout
+            ex = r.exist.view(-1) != 0
+            cnt = torch.stack([(ex & (r.act_d == 0)).sum(), (ex & (r.act_d == 1)).sum()]).double()
+            cnt = allreduce_sum_(cnt).cpu()
+            self._sel_cache["f01"] = (float(cnt[0]) / n, float(cnt[1]) / n)
+        return self._sel_cache["f01"]
 
     def update(self, epochs=10):
         """The update half of train() (PY:866-882): 10 x (cross, wait) then 10 x choice."""
