@@ -2,14 +2,14 @@
 // backward-data on the 5th-generation tensor cores (13-input nets: cross / wait actors and critics).
 //
 // Same contract as k_ppo_grad<16, HEAD> (ppo_update.cuh), which stays as the exact-fp32 cross-check and serves the wider
-// choice nets.  One persistent 384-thread CTA per SM walks 128-sample tiles; in warps 0-3 thread = sample = TMEM lane.
+// choice nets.  One persistent 256-thread CTA per SM walks 128-sample tiles; in warps 0-3 thread = sample = TMEM lane.
 //   forward       D[128 x J] = A[128 x K] * W[J x K]^T         (tc_mlp.cuh: 3xTF32, hi/lo operand tiles, fp32 in TMEM)
 //   (layers 1-3; the 32 -> 4 output layer and its backward-data are 2 x 128 FFMAs per sample on the CUDA cores)
 //   backward-data dIn[128 x K] = delta[128 x J] * W[J x K]     = the same MMA shapes with B = the FLAT transposed weights
 //                 Wt[k][j] read as an [N = K rows][reduction = J] K-major tile (BwdTiles)
 //   weight grad   dWt[k][j] += sum_s in[s][k] * delta[s][j]    FFMA register tiles (WgradAcc) on fp32 rows in shared memory:
 //                 the reduction runs over samples, which a tf32 MMA could only read from 128B-swizzled MN-major tiles
-//                 (tc.cuh); it runs on eight dedicated warps CONCURRENTLY with the chain of backward-data MMAs and their
+//                 (tc.cuh); it runs on four dedicated warps CONCURRENTLY with the chain of backward-data MMAs and their
 //                 epilogues (ReLU masks kept in registers from the forward pass) on the other four.
 // Every epilogue writes its row twice: fp32 into the row buffer (weight gradient) and hi/lo into the next A operand tile.
 #pragma once
@@ -72,7 +72,7 @@ constexpr int kTcGradRow = 16 + H1 + H2 + H3 + OP;       // 148 floats: 16-byte 
 constexpr int kTcGradNetFloats = (tcm::NetTiles<16>::FLOATS + 255) & ~255;
 constexpr size_t kTcGradSmemFloats = (size_t)kTcGradNetFloats + BwdTiles::FLOATS + (size_t)2 * 128 * kTcGradRow;      // two row buffers
 
-// Warp-specialised CTA: warps 0-3 ("E", thread = sample = TMEM lane) issue the MMAs and run the epilogues; warps 4-11 ("W")
+// Warp-specialised CTA: warps 0-3 ("E", thread = sample = TMEM lane) issue the MMAs and run the epilogues; warps 4-7 ("W")
 // only accumulate the weight gradient.  The two groups hand the row buffer back and forth through named barriers:
 //   R_l (E -> W): the rows now hold what the weight gradient of layer l needs;  F_l (W -> E): layer l has been read, its
 //   input-activation columns may be overwritten by the delta of the layer below.
