@@ -53,14 +53,19 @@ def algorithmic_bytes(variant, nb_car, nb_ped, nb_lines):
     return 2 * S + 8 * C_act + 8 * C + 4 * obs + 4, C, obs
 
 
+TRAFFIC_FILES = ("round2_env_step_ncu_metrics.json", "round1_env_step_ncu_metrics.json")      # newest capture first
+
+
 def recorded_traffic(n_envs):
     """dram__bytes_read.sum + dram__bytes_write.sum of k_env_step from the committed ncu --set full capture."""
-    p = os.path.join(ROOT, "profiles", "round1_env_step_ncu_metrics.json")
-    try:
-        d = json.load(open(p))
-        return d["traffic_bytes_per_launch"] if int(d["n_envs"]) == int(n_envs) else None
-    except Exception:
-        return None
+    for name in TRAFFIC_FILES:
+        try:
+            d = json.load(open(os.path.join(ROOT, "profiles", name)))
+            if int(d["n_envs"]) == int(n_envs):
+                return d["traffic_bytes_per_launch"], "profiles/%s (ncu --set full, bytes per launch)" % name
+        except Exception:
+            continue
+    return None, None
 
 
 def measured_peaks():
@@ -483,8 +488,9 @@ def main():
             "active_agents_per_env": active, "wall_s_timed_region": wall, "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": recorded_traffic(n_envs) if args.workload == "scalable_432" else None,
-                         "traffic_source": "profiles/round1_env_step_ncu_metrics.json (ncu --set full, bytes per launch)", "algorithmic_bytes_per_env_step": B, "peak_source": peak_src,
+                         "traffic": recorded_traffic(n_envs)[0] if args.workload == "scalable_432" else None,
+                         "traffic_source": recorded_traffic(n_envs)[1] if args.workload == "scalable_432" else None,
+                         "algorithmic_bytes_per_env_step": B, "peak_source": peak_src,
                          "kernel": "k_env_step<%s>" % variant},
             "e2e": {"value": world * n_envs * Ke / e2e_s * active, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": Ke, "pcie_gbs_per_gpu": (h2d + d2h) * Ke / e2e_s / 1e9, "host_binding": host_binding,
