@@ -46,8 +46,20 @@ static int *fail_flag() {
 static size_t smem_tc(int nets) {
     return sizeof(float) * ((size_t)nets * ((tcm::NetTiles<16>::FLOATS + 255) & ~255) + 2 * 128 * H2) + 1024;
 }
-constexpr int kGradGrid = 148;       // k_ppo_grad: one persistent CTA per SM (its tile fills shared memory)
-constexpr int kUpdateGrid = 296;     // gradient partials of the update kernels: 148 SMs x 2 (CTAs of k_value_stats, teams of k_ppo_grad)
+constexpr int kGradGridMax = 148;    // k_ppo_grad: one persistent CTA per SM (its tile fills shared memory); B200 has 148 SMs
+constexpr int kUpdateGridMax = 296;  // rows of the partial buffers in the workspace: 2 per SM (CTAs of k_value_stats)
+// grids follow the SM count of the current device (a smaller part runs fewer persistent CTAs, never more than the workspace holds)
+static int sm_count() {
+    static int n[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+    if (!n[dev]) { int v = 0; cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev); n[dev] = v > 0 ? v : kGradGridMax; }
+    return n[dev];
+}
+static int grad_grid() { const int n = sm_count(); return n < kGradGridMax ? n : kGradGridMax; }
+static int update_grid() { const int n = 2 * sm_count(); return n < kUpdateGridMax ? n : kUpdateGridMax; }
+#define kGradGrid grad_grid()
+#define kUpdateGrid update_grid()
 
 template <int KP> static size_t smem_fwd(int nets) {
     return sizeof(float) * ((size_t)nets * ((net_params(KP) + 3) & ~3) + (size_t)kFwdBlock * kRowFwd);
@@ -70,10 +82,10 @@ struct Workspace { float *gpartial; double *lpartial; double *spartial; };
 static Workspace carve(void *ws, int KP) {
     Workspace w;
     w.gpartial = (float *)ws;
-    size_t off = sizeof(float) * (size_t)kUpdateGrid * net_params(KP);
+    size_t off = sizeof(float) * (size_t)kUpdateGridMax * net_params(KP);
     off = (off + 15) & ~(size_t)15;
     w.lpartial = (double *)((char *)ws + off);
-    w.spartial = w.lpartial + kUpdateGrid;
+    w.spartial = w.lpartial + kUpdateGridMax;
     return w;
 }
 }  // namespace mhppo
@@ -136,7 +148,7 @@ static int policy_act_impl(const mhppo_rollout_cfg *cfg, const float *obs, const
     io.logp = logp; io.t = t; io.T = cfg->T; io.iteration = iteration; io.iter_dev = iter_dev;
     if (use_tc(true)) {
         const int64_t items = ((d.N + 127) / 128) * d.C;
-        const unsigned g2 = (unsigned)(items < 148 ? items : 148);       // persistent: one CTA per SM walks the (env block, car) items
+        const unsigned g2 = (unsigned)(items < sm_count() ? items : sm_count());       // persistent: one CTA per SM walks the (env block, car) items
         SET_SMEM(k_policy_act_tc, smem_tc(2));
         k_policy_act_tc<<<g2, 128, smem_tc(2), (cudaStream_t)stream>>>(d, net_cross, net_wait, io, fail_flag());
         api_count_launch();
@@ -293,7 +305,7 @@ int mhppo_tc_failures(void) {      /* 1 if any tensor-core kernel timed out wait
 int64_t mhppo_update_workspace_bytes(int32_t n_in) {
     const int kp = padded_in(n_in);
     if (kp < 0) return -1;
-    return (int64_t)(sizeof(float) * (size_t)kUpdateGrid * net_params(kp) + 16 + sizeof(double) * (size_t)kUpdateGrid * 4);
+    return (int64_t)(sizeof(float) * (size_t)kUpdateGridMax * net_params(kp) + 16 + sizeof(double) * (size_t)kUpdateGridMax * 4);
 }
 
 static int make_set(SampleSet &ss, const float *x, int32_t D, int64_t S, const int32_t *idx, int64_t K, int64_t CN) {
