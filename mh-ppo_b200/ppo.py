@@ -268,6 +268,11 @@ class Algo_PPO:
         self.rollout.reset()
         return self.rollout.iterations(self.actor_net_cross, self.actor_net_wait, self.actor_net_choice, nbr_episodes, choix=choix, **kw)
 
+    def evaluate_dataset(self, snapshot, **kw):
+        """Testing on a stored scenario dataset (PY:749-758): one deterministic episode from every scenario of the snapshot file
+        (the reference unpickles `test_data_23.pickle`, a list of deep-copied envs; here a VecCrosswalkEnv.save_state file)."""
+        return self.rollout.iterations_dataset(self.actor_net_cross, self.actor_net_wait, self.actor_net_choice, snapshot, **kw)
+
     def _nets(self):
         return [("cross", "actor", self.actor_net_cross), ("wait", "actor", self.actor_net_wait), ("choice", "actor", self.actor_net_choice),
                 ("cross", "critic", self.critic_net_cross), ("wait", "critic", self.critic_net_wait), ("choice", "critic", self.critic_net_choice)]
@@ -277,6 +282,18 @@ class Algo_PPO:
             path = os.path.join(root, self._PATH.format(stem=self._STEM[self.env.variant], name=name, kind=kind, num_algo=self.num_algo, epoch=int(self.total_loop / 10)))
             os.makedirs(os.path.dirname(path), exist_ok=True)
             torch.save(net.state_dict(), path)
+
+    def loading_curriculum(self, num_actor, num_algo, total_loop, root="."):
+        """Load ONE (actor, critic) pair from another configuration's checkpoint (PY:957-984): num_actor 0 cross, 1 wait,
+        2 choice; `num_algo` names the configuration the files were trained on (curriculum over nb_ped / nb_car / nb_lines)."""
+        self.total_loop = total_loop
+        name = {0: "cross", 1: "wait", 2: "choice"}[int(num_actor)]
+        for n, kind, net in self._nets():
+            if n == name:
+                path = os.path.join(root, self._PATH.format(stem=self._STEM[self.env.variant], name=n, kind=kind, num_algo=num_algo,
+                                                            epoch=int(total_loop / 10)))
+                net.load_state_dict(torch.load(path, map_location="cpu"))
+        self.sync_parameters()
 
     def loading(self, num_algo, total_loop, root="."):
         self.num_algo, self.total_loop = num_algo, total_loop

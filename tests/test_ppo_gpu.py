@@ -273,6 +273,11 @@ def test_train_loop_writes_reference_named_traces_and_checkpoints(mh, tmp_path):
     algo2.loading(algo.num_algo, algo.total_loop, root=str(tmp_path))
     for (_, _, a), (_, _, b) in zip(algo._nets(), algo2._nets()):
         assert torch.equal(a.flat, b.flat)
+    algo3, _ = _algo(mh, 256, 3, 100)                     # loading_curriculum (PY:957-984): one pair only
+    before = algo3.actor_net_cross.flat.clone()
+    algo3.loading_curriculum(1, algo.num_algo, algo.total_loop, root=str(tmp_path))
+    assert torch.equal(algo3.actor_net_wait.flat, algo.actor_net_wait.flat) and torch.equal(algo3.critic_net_wait.flat, algo.critic_net_wait.flat)
+    assert torch.equal(algo3.actor_net_cross.flat, before)
 
 
 def test_training_reaches_published_cross_plateau(mh):
