@@ -105,7 +105,7 @@ MH_HD bool gap_eval(double dx, double vden, double light, double size, double v0
 template <int MC, int NT>
 struct CarSlots {
     double Sc[MC][NT], Vc[MC][NT], brake[MC][NT], rVc[MC][NT];
-    float prevSc[MC][NT], light[MC][NT], pa[MC][NT], es[MC][NT], Ts[MC][NT], rl[MC][NT], wmin[MC][NT];
+    float prevSc[MC][NT], light[MC][NT], pa[MC][NT], es[MC][NT], Ts[MC][NT], rl[MC][NT], wmin[MC][NT], wtmp[MC][NT];
     uint32_t bits[MC][NT];                                      // line | exist << 8
 };
 #define MH_LINE(S, i, t) ((int)((S).bits[i][t] & 255u))
@@ -453,37 +453,22 @@ MH_HD void env_step_thread(const EnvArena &a, const EnvConst &c, const RngKey &k
         const bool left = (p.fl & PF_LEFT) != 0;
         const bool pex = (p.fl & PF_EXIST) != 0;
 
-        // ---- geometry predicates of this pedestrian against every car lane (is_in_front / is_crossing_in_front
-        // evaluated once per pair, reused below), and the observation's running-min gap (pedestrian.get_data
-        // SC:449-460 with delta_l_all SC:508-514 over the cars handed to it: SC:803-806 / C4:796-799)
-        uint32_t inf = 0, cif = 0, behind = 0;    // behind: Sc < Sp_x
-        {
-            uint32_t inf_l = 0, cif_l = 0;        // both predicates depend on the car only through its lane
+        // ---- one pass over the (pedestrian, car) pairs.  The reference touches every pair three times: pedestrian.get_data ->
+        // delta_l_all (SC:449-460, 508-514), detection (SC:176-264) and new_reward_wait_safety (SC:478-506).  All three are
+        // built on the same distance d_raw = |Sc - Sp_x| - Vc^2/2b and the same two lane predicates, so they share one rolled
+        // loop here; what forces an order is kept: `behind` of every car is needed before the first pair (n_wait, SC:206),
+        // and the accident penalty of the wait reward needs the flag after ALL cars' detection (SC:841-846 finish before
+        // SC:849), so the loop leaves the running minimum WITHOUT the penalty per car and a short second loop applies it
+        // (x -> x - penalty is monotonic in fp32, so min and subtraction commute bit for bit).
+        uint32_t inf_l = 0, cif_l = 0, behind = 0;    // lane predicates (they depend on the car only through its lane); behind: Sc < Sp_x
 #pragma unroll 1
-            for (int l = 0; l < c.L; ++l) {
-                inf_l |= (in_front(g, p, l, 0.0) ? 1u : 0u) << l;
-                cif_l |= (crossing_in_front(g, p, l, 0.0) ? 1u : 0u) << l;
-            }
-            double dl = T::far;
-#pragma unroll 1
-            for (int i = 0; i < c.nC; ++i) {
-                const double Sc = S.Sc[i][t];
-                const int line = MH_LINE(S, i, t);
-                const uint32_t f0 = (inf_l >> line) & 1u;
-                inf |= f0 << i;
-                cif |= ((cif_l >> line) & 1u) << i;
-                behind |= ((Sc < p.Spx) ? 1u : 0u) << i;
-                if (((seen >> i) & 1u) && (Sc <= p.Spx) && f0 && !left && (S.light[i][t] >= 0.f))
-                    dl = dmin(dl, (fabs(Sc - p.Spx) - S.brake[i][t]) - 1.0 * S.Vc[i][t]);
-            }
-            if (pex) {
-                const double gate = ((p.fl & PF_CROSSING) && !left) ? 1.0 : 0.0;
-                p.delta = dmin(dl * gate, p.delta);
-            }
+        for (int l = 0; l < c.L; ++l) {
+            inf_l |= (in_front(g, p, l, 0.0) ? 1u : 0u) << l;
+            cif_l |= (crossing_in_front(g, p, l, 0.0) ? 1u : 0u) << l;
         }
+#pragma unroll 1
+        for (int i = 0; i < c.nlead; ++i) behind |= ((S.Sc[i][t] < p.Spx) ? 1u : 0u) << i;
         const double wait_t = (double)p.waitc * c.dt, cross_t = (double)p.crossc * c.dt;
-
-        // ---- detection (SC:176-264); placeholders run it too (SC:842-843)
         const double nwait = (double)__builtin_popcount(lead_green & behind);        // SC:206
         const float ts_new = (float)(T::naif ? (((wait_t + 10.0 * cross_t) - time_braking) + 1.0)
                                              : ((((1.0 + nwait) * wait_t + 2.0 * cross_t) - time_braking) + 1.0));
@@ -494,14 +479,22 @@ MH_HD void env_step_thread(const EnvArena &a, const EnvConst &c, const RngKey &k
         // min(fp32 old, fp32(candidate)) == fp32(min(old, candidate)) bit for bit.
         uint32_t fl = p.fl;
         const bool counts = (p.fl & PF_CROSSING) && (!T::scal || pex);               // SC:844-845
+        const bool guard_p = pex && !left && (p.fl & PF_CROSSING);
+        double dlmin = T::far;                                                       // delta_l_all, SC:508-514
+        float wrun = __builtin_huge_valf();                                          // running min of the wait terms, penalty not yet applied
 #pragma unroll 1
         for (int i = 0; i < c.nlead; ++i) {
-            const double Sc = S.Sc[i][t], Vc = S.Vc[i][t];
+            const double Sc = S.Sc[i][t], Vc = S.Vc[i][t], rVc = S.rVc[i][t];
             const float light = S.light[i][t];
-            const bool gi = ((lead_ok & inf) >> i) & 1u;                             // SC:180
-            const bool bi = (behind >> i) & 1u, ci = (cif >> i) & 1u;
+            const int line = MH_LINE(S, i, t);
+            const bool f0 = (inf_l >> line) & 1u, ci = (cif_l >> line) & 1u;
+            const bool gi = f0 && ((lead_ok >> i) & 1u);                             // SC:180
+            const bool bi = (behind >> i) & 1u;
             const bool ahead = (Sc > p.Spx);
-            const double wdl = (ahead || left) ? T::far : (fabs(Sc - p.Spx) - S.brake[i][t]);   // worst_delta_l SC:522-527
+            const double raw = fabs(Sc - p.Spx) - S.brake[i][t];
+            const double d = raw - 1.0 * Vc;                                         // delta_l SC:516-520
+            if (((seen >> i) & 1u) && (Sc <= p.Spx) && f0 && !left && (light >= 0.f)) dlmin = dmin(dlmin, d);
+            const double wdl = (ahead || left) ? T::far : raw;                       // worst_delta_l SC:522-527
             const bool wneg = wdl < 0.0;
             const bool acc0 = (fl & PF_ACCIDENT) != 0;
             bool wa = (fl & PF_WORST_ACC) != 0;
@@ -512,7 +505,7 @@ MH_HD void env_step_thread(const EnvArena &a, const EnvConst &c, const RngKey &k
             float paf = S.pa[i][t], esf = S.es[i][t], Tsf = S.Ts[i][t];
             {                                                                        // SC:187-201
                 const bool slow = Vc < 0.05;
-                const double dl64 = slow ? T::far : wdl * S.rVc[i][t];
+                const double dl64 = slow ? T::far : wdl * rVc;
                 const float dl = (float)dl64;
                 const bool pos = slow ? (T::far > 0.0) : (wdl > 0.0);
                 // -dl-1 (ST:197, NA:200) cancels near dl = -1: that one difference is formed in fp64
@@ -542,28 +535,38 @@ MH_HD void env_step_thread(const EnvArena &a, const EnvConst &c, const RngKey &k
                 if (T::scal && !((S.bits[i][t] >> 8) & 1u)) r = 0.f;
                 S.rl[i][t] += r;
             }
+            {                                                                        // new_reward_wait_safety SC:478-506, before the penalty
+                const float dlw = (float)(d * rVc);
+                const float soft = fmaxf(-20.0f * exp2f(1.4426950408889634f * (-4.0f * dlw - 4.0f)), -20.0f);
+                const float e0 = (Vc < T::wait_thr) ? 0.0f : ((d >= -Vc) ? soft : 20.0f * dlw);
+                const bool guard = guard_p && (light > 0.f) && bi && f0;
+                wrun = guard ? fminf(wrun, e0) : wrun;
+                S.wtmp[i][t] = wrun;
+            }
         }
         p.fl = fl;
-
-        // ---- wait-reward contribution (SC:855-857 with new_reward_wait_safety SC:478-506); the
-        // reference loops cars outside / pedestrians inside, but worst_dl is per pedestrian and only
-        // sees the cars in ascending order, which this loop preserves.  It needs the accident flag
-        // after ALL cars' detection (the reference finishes SC:841-846 before SC:849), hence a second loop.
+        if (T::four) {                                                               // the followers are handed to get_data too (C4:796-799)
+#pragma unroll 1
+            for (int i = c.nlead; i < c.nC; ++i) {
+                const double Sc = S.Sc[i][t];
+                if (((seen >> i) & 1u) && (Sc <= p.Spx) && ((inf_l >> MH_LINE(S, i, t)) & 1u) && !left && (S.light[i][t] >= 0.f))
+                    dlmin = dmin(dlmin, (fabs(Sc - p.Spx) - S.brake[i][t]) - 1.0 * S.Vc[i][t]);
+            }
+        }
+        if (pex) {                                                                   // pedestrian.get_data SC:449-460
+            const double gate = ((p.fl & PF_CROSSING) && !left) ? 1.0 : 0.0;
+            p.delta = dmin(dlmin * gate, p.delta);
+        }
+        // ---- wait-reward contribution (SC:855-857): the reference loops cars outside / pedestrians inside, but worst_dl is
+        // per pedestrian and only sees the cars in ascending order, which this loop preserves
         {
-            const bool guard_p = pex && !left && (p.fl & PF_CROSSING);
             const float acc_pen = (p.fl & PF_ACCIDENT) ? 20.0f : 0.0f;
-            float pwdl = (float)p.wdl;
+            const float pw0 = (float)p.wdl;
+            float pwdl = pw0;
 #pragma unroll 1
             for (int i = 0; i < c.nlead; ++i) {
-                const double Vc = S.Vc[i][t];
+                pwdl = fminf(pw0, S.wtmp[i][t] - acc_pen);
                 const bool grn = pex && (S.light[i][t] > 0.f);
-                const bool guard = grn && guard_p && (((behind & inf) >> i) & 1u);
-                const double d = (fabs(S.Sc[i][t] - p.Spx) - S.brake[i][t]) - 1.0 * Vc;   // delta_l SC:516-520
-                const float dl = (float)(d * S.rVc[i][t]);
-                const float soft = fmaxf(-20.0f * exp2f(1.4426950408889634f * (-4.0f * dl - 4.0f)), -20.0f);
-                float e = (Vc < T::wait_thr) ? 0.0f : ((d >= -Vc) ? soft : 20.0f * dl);
-                e = e - acc_pen;
-                pwdl = (guard && e < pwdl) ? e : pwdl;
                 const float wm = S.wmin[i][t];
                 S.wmin[i][t] = grn ? ((!any_exist || pwdl < wm) ? pwdl : wm) : wm;
             }
