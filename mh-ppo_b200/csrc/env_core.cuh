@@ -99,11 +99,14 @@ struct EnvConst {
     double brake_den;                // -2 * acc_lo                      (SC:527, 518: Vc^2 / (2b))
     double idm_den;                  // 2 * sqrt(-acc_lo * acc_hi)       (SC:611)
     double time_braking;             // -(10 / (2 * acc_lo)) + 1         (SC:580)
+    double brake_inv;                // 1 / brake_den if brake_den is a power of two (then x * brake_inv == x / brake_den exactly), else 0
 };
 inline void env_const_finish(EnvConst &c) {
     c.brake_den = -2.0 * c.acc_lo;
     c.idm_den = 2.0 * sqrt(-c.acc_lo * c.acc_hi);
     c.time_braking = -(10.0 / (2.0 * c.acc_lo)) + 1.0;
+    int ex = 0;
+    c.brake_inv = (c.brake_den > 0.0 && frexp(c.brake_den, &ex) == 0.5) ? 1.0 / c.brake_den : 0.0;
 }
 
 struct Geo {

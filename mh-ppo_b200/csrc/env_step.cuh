@@ -402,7 +402,8 @@ MH_HD void env_step_thread(const EnvArena &a, const EnvConst &c, const RngKey &k
                 car_move<V>(c, k, (double)ap[(int64_t)i * cs], (double)ap[(int64_t)(half + i) * cs]);
             }
             S.prevSc[i][t] = ka.y; S.Sc[i][t] = k.Sc; S.Vc[i][t] = k.Vc; S.light[i][t] = (float)k.light;
-            S.brake[i][t] = div_pos(k.Vc * k.Vc, c.brake_den);
+            // Vc^2 / (2b): b = 4 in every reference driver, a power of two, where the product with the reciprocal IS the quotient
+            S.brake[i][t] = (c.brake_inv != 0.0) ? (k.Vc * k.Vc) * c.brake_inv : div_pos(k.Vc * k.Vc, c.brake_den);
             // 1/Vc is only read for Vc >= 0.01 (SC:190 `Vc < 0.05`, SC:482 / ST:478 thresholds); below that a
             // finite stand-in keeps a stopped car (Vc = 0) out of the division's slow path
             S.rVc[i][t] = 1.0 / opaque((k.Vc >= 0.01) ? k.Vc : 1.0);
@@ -600,7 +601,9 @@ MH_HD void env_step_thread(const EnvArena &a, const EnvConst &c, const RngKey &k
         for (int i = 0; i < c.nC; ++i) {
             if (i < c.nlead) {
                 const double d = S.Vc[i][t] - 10.0;
-                double r = (-10.0 * (d * d)) / 100.0;                                // SC:657-665
+                // SC:657-665; an fp32 OUTPUT only (never state, never a threshold): the quotient by 100 is taken as a product,
+                // one fp64 ulp away at most and far inside the 1e-5 of an fp32 reward (the exact division is ~35 instructions)
+                double r = (-10.0 * (d * d)) * 0.01;
                 if ((S.light[i][t] > 0.f) && any_exist) r += (double)S.wmin[i][t];
                 if (rp) rp[(int64_t)i * io.rewards.comp_stride] = (float)r;
                 if (lp) lp[(int64_t)i * io.reward_light.comp_stride] = S.rl[i][t];
