@@ -155,8 +155,10 @@ static int policy_act_impl(const mhppo_rollout_cfg *cfg, const float *obs, const
         return ck(cudaGetLastError(), "k_policy_act_tc");
     }
     const dim3 grid((unsigned)((d.N + kFwdBlock - 1) / kFwdBlock), (unsigned)d.C);
-    SET_SMEM(k_policy_act, smem_fwd<16>(2));
-    k_policy_act<<<grid, kFwdBlock, smem_fwd<16>(2), (cudaStream_t)stream>>>(d, net_cross, net_wait, io);
+    if (d.P > kActMaxP) return api_fail(MHPPO_EUNSUPPORTED, "more than 4 pedestrian slots");
+    const size_t sm_act = smem_fwd<16>(2) + sizeof(float) * kFwdBlock * kActMaxP + sizeof(uint16_t) * kFwdBlock * kActMaxP;
+    SET_SMEM(k_policy_act, sm_act);
+    k_policy_act<<<grid, kFwdBlock, sm_act, (cudaStream_t)stream>>>(d, net_cross, net_wait, io);
     api_count_launch();
     return ck(cudaGetLastError(), "k_policy_act");
 }

@@ -154,6 +154,14 @@ struct ActIO {
     const uint32_t *iter_dev;       // if set, the iteration number is read from device memory (replayed CUDA graphs)
 };
 
+// The CTA owns kFwdBlock envs of one car.  Which net a (car, pedestrian) pair runs through differs per env (PY:441-446), and a
+// warp whose lanes read two nets' weights pays two shared-memory wavefronts per load: the kernel was bound by exactly that
+// (shared-memory wavefronts 85 % of peak, FMA pipe 33 %, profiles/round2_policy_act_ncu_metrics.json).  So the EXISTING pairs of
+// the CTA are first compacted into two lists in shared memory (cross from the front, wait from the back; absent pedestrians
+// never enter, PY:440), then thread w evaluates list entry w: every warp reads ONE net (pure broadcast loads) and carries no
+// idle lanes; the means go back through shared memory and the owners finish with the min over pedestrians, the arg-min
+// features, the sample and its log-prob.
+constexpr int kActMaxP = 4;
 __global__ void __launch_bounds__(kFwdBlock, 2) k_policy_act(RolloutDims d, const float *__restrict__ net_cross,
                                                           const float *__restrict__ net_wait, ActIO io) {
     constexpr int KP = 16;
@@ -161,32 +169,77 @@ __global__ void __launch_bounds__(kFwdBlock, 2) k_policy_act(RolloutDims d, cons
     constexpr int NP = (net_params(KP) + 3) & ~3;
     float *sw = smem;
     float *rows = smem + 2 * NP;
+    float *res = rows + (size_t)kFwdBlock * kRowFwd;                       // [kFwdBlock][kActMaxP] means per (env, pedestrian)
+    uint16_t *list = reinterpret_cast<uint16_t *>(res + kFwdBlock * kActMaxP);   // entries: env_local * 4 + pedestrian
+    __shared__ int s_cnt[2];
     stage_net<KP>(sw, net_cross);
     stage_net<KP>(sw + NP, net_wait);
+    const int t = (int)threadIdx.x, lane = t & 31;
+    if (t < 2) s_cnt[t] = 0;
     __syncthreads();
-    const int64_t n = (int64_t)blockIdx.x * kFwdBlock + threadIdx.x;
+    const int64_t n0 = (int64_t)blockIdx.x * kFwdBlock;
+    const int64_t n = n0 + t;
     const int i = blockIdx.y;
-    if (n >= d.N) return;
-    float *row = rows + (size_t)threadIdx.x * kRowFwd;   // one in-place row per sample (odd stride: conflict-free)
-    const ObsView v = obs_view(d, io.obs, n);
-    float mean = d.head.acc_hi;                           // car_b[1,0], PY:436
-    float st[13], x[13];
-    feat_c(v, i, 0, st);                                 // state_c_tensor starts as ped 0's features, PY:437
+    const bool live = n < d.N;
+    const int cap = kFwdBlock * d.P;
+    // ---- 1. owners: which pairs exist, which net they take
+    uint32_t exm = 0;
     for (int p = 0; p < d.P; ++p) {
-        const bool ex = feat_c(v, i, p, x);
-        if (!ex && !d.legacy) continue;                  // PY:440 (the older notebooks visit every slot)
-        const int sel = (io.action_d[(int64_t)(i * d.P + p) * d.N + n] <= 0) ? 0 : 1;   // cross | wait, PY:441-446
-#pragma unroll
-        for (int k = 0; k < 13; ++k) row[k] = x[k];
-        row[13] = row[14] = row[15] = 0.f;
-        const float4 o = mlp_fwd_inplace<KP>(sw + sel * NP, row);
-        const float m = tanhf(o.x) * d.head.std + d.head.mean;   // head type 1, PY:88-90
-        mean = fminf(mean, m);
-        if (m == mean) {                                 // PY:449-450 (ties: the later pedestrian)
-#pragma unroll
-            for (int k = 0; k < 13; ++k) st[k] = x[k];
+        bool ex = false; int sel = 0;
+        if (live) {
+            ex = d.legacy || io.obs[(int64_t)(d.car_w * d.C + d.env_w + 9 * p + 7) * d.N + n] != 0.f;      // PY:440 (the older notebooks visit every slot)
+            sel = (io.action_d[(int64_t)(i * d.P + p) * d.N + n] <= 0) ? 0 : 1;                            // cross | wait, PY:441-446
+        }
+        exm |= (ex ? 1u : 0u) << p;
+        const unsigned mA = __ballot_sync(0xffffffffu, ex && sel == 0), mB = __ballot_sync(0xffffffffu, ex && sel == 1);
+        const unsigned lt = (1u << lane) - 1u;
+        if (mA) {
+            int base = 0;
+            const int leader = __ffs((int)mA) - 1;
+            if (lane == leader) base = atomicAdd(&s_cnt[0], __popc(mA));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (ex && sel == 0) list[base + __popc(mA & lt)] = (uint16_t)(t * 4 + p);
+        }
+        if (mB) {
+            int base = 0;
+            const int leader = __ffs((int)mB) - 1;
+            if (lane == leader) base = atomicAdd(&s_cnt[1], __popc(mB));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (ex && sel == 1) list[cap - 1 - (base + __popc(mB & lt))] = (uint16_t)(t * 4 + p);
         }
     }
+    __syncthreads();
+    // ---- 2. workers: one list entry per thread and pass, one net per warp
+    {
+        const int nA = s_cnt[0], nB = s_cnt[1];
+        float *row = rows + (size_t)t * kRowFwd;         // one in-place row per thread (odd stride: conflict-free)
+        for (int net = 0; net < 2; ++net) {
+            const int cnt = net ? nB : nA;
+            for (int w = t; w < cnt; w += kFwdBlock) {
+                const int ent = net ? list[cap - 1 - w] : list[w];
+                const int e = ent >> 2, p = ent & 3;
+                const ObsView v = obs_view(d, io.obs, n0 + e);
+                feat_c(v, i, p, row);
+                row[13] = row[14] = row[15] = 0.f;
+                const float4 o = mlp_fwd_inplace<KP>(sw + net * NP, row);
+                res[e * kActMaxP + p] = tanhf(o.x) * d.head.std + d.head.mean;      // head type 1, PY:88-90
+            }
+        }
+    }
+    __syncthreads();
+    if (!live) return;
+    // ---- 3. owners: min over the existing pedestrians, the arg-min pedestrian's features, sample, log-prob
+    float mean = d.head.acc_hi;                          // car_b[1,0], PY:436
+    int best = 0;                                        // state_c_tensor starts as ped 0's features, PY:437
+    for (int p = 0; p < d.P; ++p) {
+        if (!((exm >> p) & 1u)) continue;
+        const float m = res[t * kActMaxP + p];
+        mean = fminf(mean, m);
+        if (m == mean) best = p;                         // PY:449-450 (ties: the later pedestrian)
+    }
+    float st[13];
+    const ObsView v = obs_view(d, io.obs, n);
+    feat_c(v, i, best, st);
     const uint32_t iteration = io.iter_dev ? *io.iter_dev : io.iteration;
     const PhiloxBlock b = policy_block(d, n, (uint32_t)(io.t * d.C + i), 1u | (iteration << 8));
     const double z = sqrt(-2.0 * log(1.0 - u53(b.w0, b.w1))) * cos(2.0 * 3.141592653589793 * u53(b.w2, b.w3));
