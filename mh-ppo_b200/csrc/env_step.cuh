@@ -80,19 +80,25 @@ static MH_NOINLINE double cg_exact(double v0y, int gender, int age, double size,
 // a 12-argument call costs more register moves than the body's second copy costs in instruction cache).
 MH_HD bool gap_eval(double dx, double vden, double light, double size, double v0y, int gender, int age,
                                  uint32_t ctr, uint32_t env_lo, uint32_t env_hi, uint32_t k0, uint32_t k1) {
-    const PhiloxBlock b = philox4x32_10(ctr, 0u, env_lo, env_hi, k0, k1);
-    const double u1 = u53(b.w0, b.w1), u2 = u53(b.w2, b.w3);
     const double pden = fabs(v0y + 10e-3);
     // fp32 estimate: CG = size/|v0y+.01| * 10^(0.09 + gender/age terms + 0.09*z)
     const float adj = 0.09f + ((gender == 1) ? 0.0369f : 0.f) + ((age == 0) ? -0.0355f : ((age == 1) ? -0.0221f : -0.1810f));
+    const float base = ((float)size / (float)pden) * exp2f(3.3219280948873623f * adj);            // CG at z = 0
+    const float lhs = fabsf((float)dx / (float)vden) + (float)light;
+    // Level 0, no draw needed: z = sqrt(-2 ln(1 - u1)) cos(2 pi u2) with 1 - u1 >= 2^-53, so |z| <= 8.572 for EVERY block and
+    // CG lies in base * 10^(+-0.7715) = base * [0.1692, 5.909].  A car that stands (lhs ~ dx / 0.01) or is about to pass is
+    // decided here with a 3 % margin for the fp32 evaluation; the caller has consumed the draw either way.
+    if (lhs > base * 6.09f) return false;
+    if (lhs < base * 0.1642f) return true;
+    const PhiloxBlock b = philox4x32_10(ctr, 0u, env_lo, env_hi, k0, k1);
+    const double u1 = u53(b.w0, b.w1), u2 = u53(b.w2, b.w3);
 #ifdef __CUDA_ARCH__
     const float cz = cospif(2.0f * (float)u2);
 #else
     const float cz = cosf(6.2831853f * (float)u2);
 #endif
     const float z = sqrtf(-2.0f * logf((float)(1.0 - u1))) * cz;
-    const float cg = ((float)size / (float)pden) * exp2f(3.3219280948873623f * (adj + 0.09f * z));
-    const float lhs = fabsf((float)dx / (float)vden) + (float)light;
+    const float cg = base * exp2f(3.3219280948873623f * (0.09f * z));
     const float tol = 2e-4f * (fabsf(lhs) + cg) + 1e-30f;
     if (fabsf(lhs - cg) > tol) return lhs < cg;
     return (fabs(dx / vden) + light) < cg_exact(v0y, gender, age, size, u1, u2);
