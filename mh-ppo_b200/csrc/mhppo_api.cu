@@ -18,6 +18,7 @@ static std::atomic<int64_t> g_launches{0};
 
 static int fail(int code, const std::string &msg) { g_err = msg; return code; }
 int api_fail(int code, const std::string &msg) { return fail(code, msg); }   // shared with ppo_api.cu
+void rollout_forget_env(void *env);                                          // ppo_api.cu: drops a CUDA graph captured on this env
 void api_count_launch() { g_launches.fetch_add(1); }
 static int cuda_fail(cudaError_t e, const char *what) {
     g_err = std::string(what) + ": " + cudaGetErrorString(e);
@@ -185,6 +186,7 @@ int mhppo_env_create(const mhppo_env_cfg *cfg, void **handle) {
 int mhppo_env_destroy(void *handle) {
     EnvHandle *h = (EnvHandle *)handle;
     if (!h) return MHPPO_OK;
+    rollout_forget_env(h);
     cudaFree(h->arena_base); cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_rew); cudaFree(h->d_rl);
     cudaFree(h->d_done);
     for (int i = 0; i < kHostStreams; ++i) {

@@ -181,6 +181,16 @@ struct RolloutGraph {
 };
 static RolloutGraph g_rg = {};
 }
+// called by mhppo_env_destroy: a captured graph holds the env's arena pointers by value and must not outlive the handle
+// (a later handle may be allocated at the same address)
+}   // extern "C"
+namespace mhppo { void rollout_forget_env(void *env) {
+    if (g_rg.env == env) {
+        if (g_rg.exec) { cudaGraphExecDestroy(g_rg.exec); g_rg.exec = nullptr; }
+        g_rg.env = nullptr; g_rg.calls = 0;
+    }
+} }
+extern "C" {
 
 int mhppo_rollout_steps(void *env, const mhppo_rollout_cfg *cfg, float *obs, const float *net_cross, const float *net_wait,
                         const int8_t *action_d, const float *light, uint32_t iteration, float *actions, float *obs_c, float *act,
