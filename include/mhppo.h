@@ -65,7 +65,8 @@ typedef struct mhppo_env_dims {
 
 /* A 2-D fp32 view [n_envs, width] with element strides, so callers may keep either the gym layout
  * (env_stride = width, comp_stride = 1) or the coalesced device layout (env_stride = 1,
- * comp_stride = n_envs).  ptr == NULL means "not wanted" for outputs. */
+ * comp_stride = n_envs).  ptr == NULL means "not wanted" for outputs.  The observation views of
+ * mhppo_env_step need 0 <= comp_stride < 2^31 (MHPPO_EINVAL otherwise). */
 typedef struct mhppo_view {
     float *ptr;
     int64_t env_stride;

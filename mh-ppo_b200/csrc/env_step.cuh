@@ -241,6 +241,17 @@ MH_NOINLINE void reset_and_store(const EnvArena &a, const EnvConst &c, int64_t n
 MH_HD float exp_f32(double x) {   // e^x for output-only terms: fp64 argument, fp32 exponential
     return exp2f((float)(x * 1.4426950408889634));
 }
+// 2^x of the reward-shaping terms: the bare MUFU.EX2 (results below 2^-126 flush to zero: an absolute difference of 1e-38 on
+// an fp32 reward term); exp2f() wraps the same instruction in a three-instruction range fix-up, three times per (pedestrian, car) pair
+MH_HD float exp2_shape(float x) {
+#ifdef __CUDA_ARCH__
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+#else
+    return exp2f(x);
+#endif
+}
 
 // ---------------------------------------------------------------------------------------------
 // pedestrian.step, SC:297-417, for the pedestrian currently held in registers
@@ -371,7 +382,7 @@ MH_HD void env_step_thread(const EnvArena &a, const EnvConst &c, const RngKey &k
     const bool will_reset = done && io.autoreset;
     const mhppo_view ov = will_reset ? io.term_obs : io.obs;
     float *const op = ov.ptr ? ov.ptr + n * ov.env_stride : nullptr;
-    const int64_t ocs = ov.comp_stride;
+    const int ocs = (int)ov.comp_stride;                 // the API rejects component strides >= 2^31 (one register instead of two)
 
     // ---- cars: load, act (SC:797-802 / C4:791-795 / C42:807-811 / CO:753-755), observation row
     // (car.get_data SC:652-655) and position/speed store, one slot at a time.  Leaders come before the
@@ -419,11 +430,11 @@ MH_HD void env_step_thread(const EnvArena &a, const EnvConst &c, const RngKey &k
             if (ex) seen |= 1u << i;
             if (i < c.nlead && ex) { lead_ok |= 1u << i; if (k.light > 0.0) lead_green |= 1u << i; }
             if (op) {
-                float *q = op + (int64_t)(T::car_w * i) * ocs;
-                q[0 * ocs] = ex ? (float)k.Ac : 0.f; q[1 * ocs] = ex ? (float)k.Vc : 0.f;
-                q[2 * ocs] = ex ? (float)(10.0 - k.Vc) : 10.f; q[3 * ocs] = ex ? (float)k.Sc : -1000.f;
-                q[4 * ocs] = ex ? (float)k.light : 0.f; q[5 * ocs] = (float)k.line;
-                if (T::scal) q[6 * ocs] = ex ? 1.f : 0.f;
+                float *q = op + (int64_t)(T::car_w * i) * (int64_t)ocs;
+                q[(int64_t)0 * ocs] = ex ? (float)k.Ac : 0.f; q[(int64_t)1 * ocs] = ex ? (float)k.Vc : 0.f;
+                q[(int64_t)2 * ocs] = ex ? (float)(10.0 - k.Vc) : 10.f; q[(int64_t)3 * ocs] = ex ? (float)k.Sc : -1000.f;
+                q[(int64_t)4 * ocs] = ex ? (float)k.light : 0.f; q[(int64_t)5 * ocs] = (float)k.line;
+                if (T::scal) q[(int64_t)6 * ocs] = ex ? 1.f : 0.f;
             }
             if (!will_reset) a.car_a[(int64_t)i * a.N + n] = make_float4((float)k.Vc, (float)k.Sc, (float)k.light, (float)k.Ac);
         }
@@ -432,7 +443,7 @@ MH_HD void env_step_thread(const EnvArena &a, const EnvConst &c, const RngKey &k
     const int env_w = T::scal ? 4 : 3;
     const int ped_o = T::car_w * c.nC + env_w;
     const double time_braking = c.time_braking;                                      // SC:580
-    bool any_exist = false;
+    constexpr uint32_t ANY_EXIST = 1u << 31;             // "a pedestrian exists so far" rides in a spare bit of `lead_green`, whose readers mask it with car bits (no register of its own)
 
     // ---- pedestrians, streamed
 #pragma unroll 1
@@ -500,7 +511,8 @@ MH_HD void env_step_thread(const EnvArena &a, const EnvConst &c, const RngKey &k
             const bool ahead = (Sc > p.Spx);
             const double raw = fabs(Sc - p.Spx) - S.brake[i][t];
             const double d = raw - 1.0 * Vc;                                         // delta_l SC:516-520
-            if (((seen >> i) & 1u) && (Sc <= p.Spx) && f0 && !left && (light >= 0.f)) dlmin = dmin(dlmin, d);
+            const bool dl_ok = (bool)((seen >> i) & 1u) & (Sc <= p.Spx) & f0 & !left & (light >= 0.f);       // one predicate, one select
+            dlmin = dl_ok ? dmin(dlmin, d) : dlmin;
             const double wdl = (ahead || left) ? T::far : raw;                       // worst_delta_l SC:522-527
             const bool wneg = wdl < 0.0;
             const bool acc0 = (fl & PF_ACCIDENT) != 0;
@@ -517,7 +529,7 @@ MH_HD void env_step_thread(const EnvArena &a, const EnvConst &c, const RngKey &k
                 const bool pos = slow ? (T::far > 0.0) : (wdl > 0.0);
                 // -dl-1 (ST:197, NA:200) cancels near dl = -1: that one difference is formed in fp64
                 const float lin = T::neg_dl ? (float)(-1.0 * dl64 - 1.0) : (1.0f * dl - 1.0f);
-                const float pa = pos ? -exp2f(-4.0f * 1.4426950408889634f * dl) : lin;
+                const float pa = pos ? -exp2_shape(-4.0f * 1.4426950408889634f * dl) : lin;
                 paf = (gi && ci) ? fminf(paf, pa) : paf;
             }
             Tsf = (gi && bi) ? fmaxf(ts_new, Tsf) : Tsf;                             // SC:207-208
@@ -528,23 +540,24 @@ MH_HD void env_step_thread(const EnvArena &a, const EnvConst &c, const RngKey &k
                 const bool use_exp = red ? (Tsf < 0.f) : (gap > 0.0);
                 const float arg = red ? (4.0f * Tsf) : (-4.0f * gapf);
                 const float lin = red ? (-1.0f * (1.0f + Tsf)) : (-1.0f - (float)(Sc - p.Spx));
-                const float ne = use_exp ? -exp2f(1.4426950408889634f * arg) : lin;
+                const float ne = use_exp ? -exp2_shape(1.4426950408889634f * arg) : lin;
                 esf = (gi && (red || grn)) ? fminf(ne, esf) : esf;
                 if (!T::naif) fl |= (gi && red && ci && bi) ? PF_NOT_WAITING : 0u;
             }
             S.pa[i][t] = paf; S.es[i][t] = esf; S.Ts[i][t] = Tsf;
-            if (counts) {                                                            // res: SC:250-263
+            {                                                                        // res: SC:250-263 (select, not a branch: lanes disagree)
                 float r = paf + esf;
                 if (T::danger_sign != 0) {
                     const float extra = ((light < 0.f) && (Tsf > 0.f)) ? 0.5f * green : 0.f;
                     r = (T::danger_sign > 0) ? (r + extra) : (r - extra);
                 }
                 if (T::scal && !((S.bits[i][t] >> 8) & 1u)) r = 0.f;
-                S.rl[i][t] += r;
+                const float rl0 = S.rl[i][t];
+                S.rl[i][t] = counts ? rl0 + r : rl0;
             }
             {                                                                        // new_reward_wait_safety SC:478-506, before the penalty
                 const float dlw = (float)(d * rVc);
-                const float soft = fmaxf(-20.0f * exp2f(1.4426950408889634f * (-4.0f * dlw - 4.0f)), -20.0f);
+                const float soft = fmaxf(-20.0f * exp2_shape(1.4426950408889634f * (-4.0f * dlw - 4.0f)), -20.0f);
                 const float e0 = (Vc < T::wait_thr) ? 0.0f : ((d >= -Vc) ? soft : 20.0f * dlw);
                 const bool guard = guard_p && (light > 0.f) && bi && f0;
                 wrun = guard ? fminf(wrun, e0) : wrun;
@@ -575,20 +588,20 @@ MH_HD void env_step_thread(const EnvArena &a, const EnvConst &c, const RngKey &k
                 pwdl = fminf(pw0, S.wtmp[i][t] - acc_pen);
                 const bool grn = pex && (S.light[i][t] > 0.f);
                 const float wm = S.wmin[i][t];
-                S.wmin[i][t] = grn ? ((!any_exist || pwdl < wm) ? pwdl : wm) : wm;
+                S.wmin[i][t] = grn ? ((!(lead_green & ANY_EXIST) || pwdl < wm) ? pwdl : wm) : wm;
             }
             p.wdl = (double)pwdl;
-            any_exist = any_exist || pex;
+            if (pex) lead_green |= ANY_EXIST;
         }
 
         // ---- observation row
         if (op) {
-            float *q = op + (int64_t)(ped_o + 9 * j) * ocs;
-            q[0 * ocs] = pex ? (float)p.Vpx : 0.f; q[1 * ocs] = pex ? (float)p.Vpy : 0.f;
-            q[2 * ocs] = pex ? (float)p.Spx : 0.f; q[3 * ocs] = pex ? (float)p.Spy : 0.f;
-            q[4 * ocs] = pex ? (float)p.delta : 0.f; q[5 * ocs] = (pex && left) ? 1.f : 0.f;
-            q[6 * ocs] = (pex && (p.fl & PF_IN_CROSS)) ? 1.f : 0.f; q[7 * ocs] = pex ? 1.f : 0.f;
-            q[8 * ocs] = pex ? (float)p.dir : 0.f;
+            float *q = op + (int64_t)(ped_o + 9 * j) * (int64_t)ocs;
+            q[(int64_t)0 * ocs] = pex ? (float)p.Vpx : 0.f; q[(int64_t)1 * ocs] = pex ? (float)p.Vpy : 0.f;
+            q[(int64_t)2 * ocs] = pex ? (float)p.Spx : 0.f; q[(int64_t)3 * ocs] = pex ? (float)p.Spy : 0.f;
+            q[(int64_t)4 * ocs] = pex ? (float)p.delta : 0.f; q[(int64_t)5 * ocs] = (pex && left) ? 1.f : 0.f;
+            q[(int64_t)6 * ocs] = (pex && (p.fl & PF_IN_CROSS)) ? 1.f : 0.f; q[(int64_t)7 * ocs] = pex ? 1.f : 0.f;
+            q[(int64_t)8 * ocs] = pex ? (float)p.dir : 0.f;
         }
         // ---- store pedestrian j
         if (!will_reset) {
@@ -610,7 +623,7 @@ MH_HD void env_step_thread(const EnvArena &a, const EnvConst &c, const RngKey &k
                 // SC:657-665; an fp32 OUTPUT only (never state, never a threshold): the quotient by 100 is taken as a product,
                 // one fp64 ulp away at most and far inside the 1e-5 of an fp32 reward (the exact division is ~35 instructions)
                 double r = (-10.0 * (d * d)) * 0.01;
-                if ((S.light[i][t] > 0.f) && any_exist) r += (double)S.wmin[i][t];
+                if ((S.light[i][t] > 0.f) && (lead_green & ANY_EXIST)) r += (double)S.wmin[i][t];
                 if (rp) rp[(int64_t)i * io.rewards.comp_stride] = (float)r;
                 if (lp) lp[(int64_t)i * io.reward_light.comp_stride] = S.rl[i][t];
             }
@@ -620,12 +633,12 @@ MH_HD void env_step_thread(const EnvArena &a, const EnvConst &c, const RngKey &k
     }
     // ---- observation: env row (SC:871)
     if (op) {
-        float *q = op + (int64_t)(T::car_w * c.nC) * ocs;
+        float *q = op + (int64_t)(T::car_w * c.nC) * (int64_t)ocs;
         int o = 0;
-        q[(o++) * ocs] = (float)(cross * (double)c.L / 2.0);
-        q[(o++) * ocs] = (float)ped_traffic;
-        if (T::scal) q[(o++) * ocs] = (float)car_traffic;
-        q[(o++) * ocs] = (float)c.L;
+        q[(int64_t)(o++) * ocs] = (float)(cross * (double)c.L / 2.0);
+        q[(int64_t)(o++) * ocs] = (float)ped_traffic;
+        if (T::scal) q[(int64_t)(o++) * ocs] = (float)car_traffic;
+        q[(int64_t)(o++) * ocs] = (float)c.L;
     }
     step += 1;                                                                       // SC:875
     if (will_reset) {                                                                // in-kernel auto-reset

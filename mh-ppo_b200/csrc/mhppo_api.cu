@@ -255,6 +255,10 @@ int mhppo_env_step(void *handle, mhppo_view actions_dev, mhppo_view obs_dev, mhp
     EnvHandle *h = (EnvHandle *)handle;
     if (!h) return fail(MHPPO_EINVAL, "null handle");
     if (!actions_dev.ptr) return fail(MHPPO_EINVAL, "actions are required");
+    // the step kernel keeps the observation component stride in one 32-bit register (env_step.cuh)
+    if ((obs_dev.ptr && (obs_dev.comp_stride < 0 || obs_dev.comp_stride > INT32_MAX)) ||
+        (term_obs_dev.ptr && (term_obs_dev.comp_stride < 0 || term_obs_dev.comp_stride > INT32_MAX)))
+        return fail(MHPPO_EINVAL, "observation comp_stride must be in [0, 2^31)");
     StepIO io;
     io.actions = actions_dev; io.obs = obs_dev; io.rewards = rewards_dev; io.reward_light = reward_light_dev;
     io.term_obs = term_obs_dev; io.done = done_dev; io.autoreset = autoreset; io.n_begin = 0; io.n_end = h->a.N;

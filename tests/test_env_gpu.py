@@ -238,3 +238,22 @@ def test_state_injection_matches_oracle(oracle_mod, cuda_env_cls, cfg):
     ref = oracle_mod.OracleVecEnv(v, N, c, p, l, seed=7, env_id0=900, store_f32=True)
     got = cuda_env_cls(v, N, c, p, l, seed=7, env_id0=900)
     inject_and_compare(ref, got, v, np.random.default_rng(1))
+
+
+def test_observation_stride_out_of_range_is_rejected():
+    """mhppo_env_step keeps the observation component stride in one 32-bit register: a stride >= 2^31 is MHPPO_EINVAL, not a
+    silent truncation (include/mhppo.h, mhppo_view)."""
+    import mhppo_b200
+    from mhppo_b200 import _lib
+    from mhppo_b200.vec_env import View, _view
+    env = mhppo_b200.VecCrosswalkEnv("coop_scalable", 64, nb_car=4, nb_ped=3, nb_lines=2, seed=1)
+    env.reset()
+    act = torch.zeros(64, env.n_action, device="cuda")
+    good = _view(env._obs, True)
+    bad = View(good.ptr, good.env_stride, 1 << 31)
+    none = View(None, 0, 0)
+    rc = env._L.mhppo_env_step(env._h, _view(act, False), bad, none, none, None, 0, none, env._stream())
+    assert rc != 0 and "comp_stride" in env._L.mhppo_last_error().decode()
+    with pytest.raises(_lib.MhppoError):
+        _lib.check(rc)
+    env.step(act)     # the handle stays usable
