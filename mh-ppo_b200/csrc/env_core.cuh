@@ -147,6 +147,21 @@ MH_HD bool crossing_in_front(const Geo &g, const PedR &p, int line, double pl) {
     return p.Spy > g.Hn + g.cross * ((double)line - pl);
 }
 
+// Both predicates for one lane without the branch on the walking direction (lanes of a warp disagree on it, so the two
+// sides above run one after the other at half occupancy).  With y = -Sp_y for dir == -1 and y = Sp_y otherwise:
+//   in front:          y <= (Hn + cross * a) + 0.001,   a = (dir == -1 ? L - line : line + 1) - 0.5 * nl
+//   crossing in front: y >   Hn + cross * a',           a' = (dir == -1 ? L - line - 1 : line) - pl
+// Bit-identical to the two functions above: Hn = -Hp exactly, negation commutes with rounding ((Hp - b) - 0.001 =
+// -((Hn + b) + 0.001)), and a, a' are small integers or half-integers, exact in either operation order.
+struct LanePred { bool in_front, crossing; };
+MH_HD LanePred lane_pred(const Geo &g, double y, bool neg, int L, int line, double nl, double pl) {
+    const int ai = neg ? (L - line) : (line + 1);
+    LanePred r;
+    r.in_front = y <= (g.Hn + g.cross * ((double)ai - 0.5 * nl)) + 0.001;
+    r.crossing = y > g.Hn + g.cross * ((double)(ai - 1) - pl);
+    return r;
+}
+
 // pedestrian.CG_score, SC:419-428 -- one normal draw, only for crossing pedestrians
 MH_HD double cg_score(const PedR &p, double size, Rng &rng) {
     if (!(p.fl & PF_CROSSING)) return 0.0;

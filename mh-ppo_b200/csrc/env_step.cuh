@@ -142,10 +142,13 @@ MH_HD ChoixPlan choix_plan(const EnvConst &c, const Geo &g, const PedR &p, const
     const int nseen = __builtin_popcount(seen);
     // is_in_front / is_crossing_in_front depend on the car only through its lane: one evaluation per lane
     uint32_t inf1_l = 0, cif_l = 0;
+    const bool neg = p.dir == -1;
+    const double y = neg ? -p.Spy : p.Spy;
 #pragma unroll 1
     for (int l = 0; l < c.L; ++l) {
-        inf1_l |= (in_front(g, p, l, 1.0) ? 1u : 0u) << l;
-        cif_l |= (crossing_in_front(g, p, l, 0.5) ? 1u : 0u) << l;
+        const LanePred lp = lane_pred(g, y, neg, c.L, l, 1.0, 0.5);
+        inf1_l |= (lp.in_front ? 1u : 0u) << l;
+        cif_l |= (lp.crossing ? 1u : 0u) << l;
     }
     uint32_t inf1 = 0, on_cross = 0, behind = 0, blocked = 0;
 #pragma unroll 1
@@ -479,10 +482,15 @@ MH_HD void env_step_thread(const EnvArena &a, const EnvConst &c, const RngKey &k
         // SC:849), so the loop leaves the running minimum WITHOUT the penalty per car and a short second loop applies it
         // (x -> x - penalty is monotonic in fp32, so min and subtraction commute bit for bit).
         uint32_t inf_l = 0, cif_l = 0, behind = 0;    // lane predicates (they depend on the car only through its lane); behind: Sc < Sp_x
+        {
+            const bool neg = p.dir == -1;
+            const double y = neg ? -p.Spy : p.Spy;
 #pragma unroll 1
-        for (int l = 0; l < c.L; ++l) {
-            inf_l |= (in_front(g, p, l, 0.0) ? 1u : 0u) << l;
-            cif_l |= (crossing_in_front(g, p, l, 0.0) ? 1u : 0u) << l;
+            for (int l = 0; l < c.L; ++l) {
+                const LanePred lp = lane_pred(g, y, neg, c.L, l, 0.0, 0.0);
+                inf_l |= (lp.in_front ? 1u : 0u) << l;
+                cif_l |= (lp.crossing ? 1u : 0u) << l;
+            }
         }
 #pragma unroll 1
         for (int i = 0; i < c.nlead; ++i) behind |= ((S.Sc[i][t] < p.Spx) ? 1u : 0u) << i;
