@@ -265,6 +265,14 @@ int mhppo_adam2(float *p0_dev, const float *g0_dev, float *m0_dev, float *v0_dev
 int mhppo_set_mlp_mode(int32_t mode);
 /* 1 if a tensor-core kernel ever timed out waiting for its MMAs (diagnostic; synchronises the device) */
 int mhppo_tc_failures(void);
+/* Self-test of the step kernel's gap-acceptance predicate (`car_time + light < CG`, SC:167-170, 419-428): for n samples
+ * (device arrays) returns the filtered decision the kernel takes (fast), the level that took it (0 = no draw needed,
+ * 1 = fp32 draw, 2 = exact fallback), the exact fp64 decision and the exact critical gap (cg_dev may be NULL).  The normal
+ * draw of sample i is Philox block ctr[i] of stream (env_id, key0, key1).  fast must equal exact for every input. */
+int mhppo_gap_selftest(int64_t n, const double *dx_dev, const double *vden_dev, const double *light_dev, const double *size_dev,
+                       const double *v0y_dev, const int32_t *gender_dev, const int32_t *age_dev, const uint32_t *ctr_dev,
+                       uint64_t env_id, uint32_t key0, uint32_t key1, uint8_t *fast_dev, uint8_t *level_dev, uint8_t *exact_dev,
+                       double *cg_dev, void *stream);
 int mhppo_tc_selftest(const float *A_dev, const float *B_dev, float *D_dev, int32_t N, int32_t K, int32_t mode, void *stream);
 
 #ifdef __cplusplus

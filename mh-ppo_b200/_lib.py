@@ -78,6 +78,7 @@ SYMBOLS = {
     "mhppo_tc_failures": (C.c_int, []),
     "mhppo_set_mlp_mode": (C.c_int, [C.c_int32]),
     "mhppo_set_gaussian_head": (C.c_int, [C.c_float, C.c_float, C.c_float, C.c_float]),
+    "mhppo_gap_selftest": (C.c_int, [C.c_int64] + [C.c_void_p] * 8 + [C.c_uint64, C.c_uint32, C.c_uint32] + [C.c_void_p] * 5),
     "mhppo_tc_selftest": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "mhppo_adam": (C.c_int, [C.c_void_p] * 4 + [C.c_int32] + [C.c_float] * 4 + [C.c_int32, C.c_float, C.c_void_p]),
 }

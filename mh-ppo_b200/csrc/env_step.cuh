@@ -78,29 +78,52 @@ static MH_NOINLINE double cg_exact(double v0y, int gender, int age, double size,
 // both sides in fp64 exactly as the reference does.  `ctr` is the Philox block of this decision's
 // normal draw (one block per CG_score call).  Inlined at its two call sites (3 % faster than one out-of-line copy:
 // a 12-argument call costs more register moves than the body's second copy costs in instruction cache).
+//
+// Three levels, each sound on its own (mhppo_gap_selftest compares all of them with the exact decision on adversarial inputs):
+//  0. no draw: z = sqrt(-2 ln(1 - u1)) cos(2 pi u2) with 1 - u1 >= 2^-53, so |z| <= 8.572 for EVERY block and CG lies in
+//     base * 10^(+-0.7715) = base * [0.1692, 5.909].  A car that stands (lhs ~ dx / 0.01) or is about to pass is decided
+//     here with a 3 % margin for the fp32 evaluation; the caller has consumed the draw either way;
+//  1. fp32 draw from the top 24 bits of the two uniforms with the SFU intrinsics (device build).  Error budget of z:
+//     1 - u1 truncated to 24 bits is exact in fp32 (a multiple of 2^-24 in (0, 1]) and off by < 2^-24; __logf is within
+//     2^-21.4 absolute on [0.5, 2] (3 ulp elsewhere), so |d ln| <= 4.8e-7 and |d sqrt(-2 ln)| <= sqrt(2 * 4.8e-7) = 9.8e-4
+//     (the worst case, 1 - u1 ~ 1; for 1 - u1 < 0.5 the error is <= 2^-24 / (1 - u1) / r <= 6e-5 down to the cut-off
+//     1 - u1 >= 2^-12, below which this level is skipped); the cosine adds 1.1e-6 * r.  CG = base * 10^(0.09 z), so
+//     |d CG| / CG <= 0.2072 * 9.8e-4 + 3e-6 = 2.06e-4 against the 5e-4 of `tol`;
+//  2. exact: both sides in fp64 in the reference's operation order.
 MH_HD bool gap_eval(double dx, double vden, double light, double size, double v0y, int gender, int age,
-                                 uint32_t ctr, uint32_t env_lo, uint32_t env_hi, uint32_t k0, uint32_t k1) {
+                                 uint32_t ctr, uint32_t env_lo, uint32_t env_hi, uint32_t k0, uint32_t k1, int *level = nullptr) {
     const double pden = fabs(v0y + 10e-3);
     // fp32 estimate: CG = size/|v0y+.01| * 10^(0.09 + gender/age terms + 0.09*z)
     const float adj = 0.09f + ((gender == 1) ? 0.0369f : 0.f) + ((age == 0) ? -0.0355f : ((age == 1) ? -0.0221f : -0.1810f));
     const float base = ((float)size / (float)pden) * exp2f(3.3219280948873623f * adj);            // CG at z = 0
     const float lhs = fabsf((float)dx / (float)vden) + (float)light;
-    // Level 0, no draw needed: z = sqrt(-2 ln(1 - u1)) cos(2 pi u2) with 1 - u1 >= 2^-53, so |z| <= 8.572 for EVERY block and
-    // CG lies in base * 10^(+-0.7715) = base * [0.1692, 5.909].  A car that stands (lhs ~ dx / 0.01) or is about to pass is
-    // decided here with a 3 % margin for the fp32 evaluation; the caller has consumed the draw either way.
+    if (level) *level = 0;
     if (lhs > base * 6.09f) return false;
     if (lhs < base * 0.1642f) return true;
     const PhiloxBlock b = philox4x32_10(ctr, 0u, env_lo, env_hi, k0, k1);
-    const double u1 = u53(b.w0, b.w1), u2 = u53(b.w2, b.w3);
+    if (level) *level = 1;
 #ifdef __CUDA_ARCH__
-    const float cz = cospif(2.0f * (float)u2);
+    const float wf = 1.0f - (float)(b.w0 >> 8) * 5.9604644775390625e-8f;                          // 1 - u1 from the top 24 bits: exact in fp32
+    if (wf >= 2.44140625e-4f) {
+        const float u2f = (float)(b.w2 >> 8) * 5.9604644775390625e-8f;
+        const float cz = -__cosf(6.2831853f * (u2f - 0.5f));                                      // cos(2 pi u2), argument in [-pi, pi)
+        float r;
+        asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-2.0f * __logf(wf)));
+        const float cg = base * exp2f(3.3219280948873623f * (0.09f * (r * cz)));
+        const float tol = 5e-4f * (fabsf(lhs) + cg) + 1e-30f;
+        if (fabsf(lhs - cg) > tol) return lhs < cg;
+    }
+    const double u1 = u53(b.w0, b.w1), u2 = u53(b.w2, b.w3);
 #else
-    const float cz = cosf(6.2831853f * (float)u2);
+    const double u1 = u53(b.w0, b.w1), u2 = u53(b.w2, b.w3);
+    {
+        const float z = sqrtf(-2.0f * logf((float)(1.0 - u1))) * cosf(6.2831853f * (float)u2);
+        const float cg = base * exp2f(3.3219280948873623f * (0.09f * z));
+        const float tol = 2e-4f * (fabsf(lhs) + cg) + 1e-30f;
+        if (fabsf(lhs - cg) > tol) return lhs < cg;
+    }
 #endif
-    const float z = sqrtf(-2.0f * logf((float)(1.0 - u1))) * cz;
-    const float cg = base * exp2f(3.3219280948873623f * (0.09f * z));
-    const float tol = 2e-4f * (fabsf(lhs) + cg) + 1e-30f;
-    if (fabsf(lhs - cg) > tol) return lhs < cg;
+    if (level) *level = 2;
     return (fabs(dx / vden) + light) < cg_exact(v0y, gender, age, size, u1, u2);
 }
 

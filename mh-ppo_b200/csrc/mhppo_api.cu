@@ -83,6 +83,23 @@ static const EnvKernelEntry *find_kernel(int variant, int C, int P) {
 
 static unsigned grid_for(int64_t n) { return (unsigned)((n + kEnvBlock - 1) / kEnvBlock); }
 
+
+// Self-test of the gap-acceptance predicate (env_step.cuh gap_eval): the filtered decision, the level that took it and the
+// exact fp64 decision with its critical gap, one thread per sample.
+__global__ void k_gap_selftest(int64_t n, const double *dx, const double *vden, const double *light, const double *size,
+                               const double *v0y, const int32_t *gender, const int32_t *age, const uint32_t *ctr,
+                               uint32_t env_lo, uint32_t env_hi, uint32_t k0, uint32_t k1,
+                               uint8_t *fast, uint8_t *level, uint8_t *exact, double *cg) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int lv = 0;
+    fast[i] = gap_eval(dx[i], vden[i], light[i], size[i], v0y[i], gender[i], age[i], ctr[i], env_lo, env_hi, k0, k1, &lv) ? 1 : 0;
+    level[i] = (uint8_t)lv;
+    const PhiloxBlock b = philox4x32_10(ctr[i], 0u, env_lo, env_hi, k0, k1);
+    const double g = cg_exact(v0y[i], gender[i], age[i], size[i], u53(b.w0, b.w1), u53(b.w2, b.w3));
+    exact[i] = ((fabs(dx[i] / vden[i]) + light[i]) < g) ? 1 : 0;
+    if (cg) cg[i] = g;
+}
 }  // namespace mhppo
 
 using namespace mhppo;
@@ -346,6 +363,21 @@ int mhppo_env_import_state(void *handle, const float *car_f, const int32_t *car_
     DumpPtrs d{(float *)car_f, (int32_t *)car_i, (float *)ped_f, (int32_t *)ped_i, (double *)env_f, (int64_t *)env_i};
     k_env_import<<<grid_for(h->a.N), kEnvBlock, 0, (cudaStream_t)stream>>>(h->a, h->c, d);
     g_launches.fetch_add(1);
+    CK(cudaGetLastError());
+    return MHPPO_OK;
+}
+
+int mhppo_gap_selftest(int64_t n, const double *dx_dev, const double *vden_dev, const double *light_dev, const double *size_dev,
+                       const double *v0y_dev, const int32_t *gender_dev, const int32_t *age_dev, const uint32_t *ctr_dev,
+                       uint64_t env_id, uint32_t key0, uint32_t key1, uint8_t *fast_dev, uint8_t *level_dev, uint8_t *exact_dev,
+                       double *cg_dev, void *stream) {
+    if (n <= 0 || !dx_dev || !vden_dev || !light_dev || !size_dev || !v0y_dev || !gender_dev || !age_dev || !ctr_dev || !fast_dev ||
+        !level_dev || !exact_dev)
+        return fail(MHPPO_EINVAL, "null argument");
+    k_gap_selftest<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n, dx_dev, vden_dev, light_dev, size_dev, v0y_dev,
+                                                                              gender_dev, age_dev, ctr_dev, (uint32_t)env_id,
+                                                                              (uint32_t)(env_id >> 32), key0, key1, fast_dev,
+                                                                              level_dev, exact_dev, cg_dev);
     CK(cudaGetLastError());
     return MHPPO_OK;
 }
