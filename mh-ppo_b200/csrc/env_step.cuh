@@ -319,12 +319,18 @@ MH_HD void ped_step_stream(const EnvConst &c, const Geo &g, PedR &p, const CarSl
         }
         if (p.tstop != 0) {                                                          // SC:335-339
             p.Vpx = 0.0; p.Vpy = 0.0; p.tstop -= 1; p.t0c += 1;
+        } else if (!choose) {
+            // a refused kerb decision (every step of a waiting pedestrian): the uniform of SC:346 and the randint of SC:406 are
+            // drawn, but `u < 0.98 and choice` is False whatever u is and SC:410 overwrites t_stop -- the two blocks are
+            // consumed without being computed
+            rng.skip(2);
+            p.fl &= ~PF_DECISION; p.tstop = 0; p.waitc += 1;                         // SC:408-411
+            p.Vpx = 0.0; p.Vpy = 0.0; p.t0c += 1;
         } else {
-            const double u = rng.random();                                           // SC:346: always drawn
-            if ((u < 0.98) && choose) walk_try = true;
+            const double u = rng.random();                                           // SC:346
+            if (u < 0.98) walk_try = true;
             else {                                                                   // SC:405-413
                 p.tstop = rng.randint(T::rs_lo, T::rs_hi);
-                if (!choose) { p.fl &= ~PF_DECISION; p.tstop = 0; p.waitc += 1; }
                 p.Vpx = 0.0; p.Vpy = 0.0; p.t0c += 1;
             }
         }
