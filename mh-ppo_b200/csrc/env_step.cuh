@@ -301,38 +301,43 @@ MH_HD void ped_step_stream(const EnvConst &c, const Geo &g, PedR &p, const CarSl
     const double dy = (double)p.dir * p.Spy;
     if (!(p.fl & PF_CROSSING)) return;                                               // SC:308
 
-    bool choose = true;
     const bool first_decision = !(p.fl & PF_DECISION) && (p.fl & PF_AT_CROSSING);    // SC:311
     // kerb arrival is evaluated after the decision block in the reference; it cannot fire in a step
     // that took the decision block (decision is then True), so it is decided up front
     const bool arrive = !first_decision && (dy < g.Hn) && (pp_y * (double)p.dir > g.Hn) && !(p.fl & PF_DECISION);  // SC:320
     const bool in_walk_block = !arrive && (first_decision || (fabs(p.Spy) <= g.Hp) || (p.fl & PF_DECISION));      // SC:331
 
-    // phase A: decide whether this step needs the walking model / a gap-acceptance decision
+    // phase A: decide whether this step needs the walking model / a gap-acceptance decision.  The bookkeeping of the three
+    // cheap outcomes (decision taken, standing still, decision refused) is written as selects: with branches the lanes that
+    // took the kerb decision and the lanes already walking reached the uniform draw and the walking model below as two
+    // groups, and both ran twice per warp.
+    const bool accept = first_decision && kerb_choice;                               // SC:311-318 (first_decision implies in_walk_block)
+    const bool stopped = in_walk_block && (p.tstop != 0);                            // SC:335-339
+    // a refused kerb decision (every step of a waiting pedestrian): the uniform of SC:346 and the randint of SC:406 are
+    // drawn, but `u < 0.98 and choice` is False whatever u is and SC:410 overwrites t_stop -- the two blocks are
+    // consumed without being computed
+    const bool refuse = first_decision && !kerb_choice && !stopped;
+    const bool draw = in_walk_block && !stopped && !refuse;
+    {
+        const bool still = stopped || refuse;
+        uint32_t fl = p.fl;
+        fl = accept ? (fl & ~PF_AT_CROSSING) : fl;
+        fl = (first_decision && !refuse) ? (fl | PF_DECISION) : fl;                  // SC:317, undone by SC:408 when refused
+        p.fl = fl;
+        p.lpos = accept ? ((p.dir < 0) ? (c.L - 1) : 0) : p.lpos;
+        p.t0c = (first_decision ? step : p.t0c) + (still ? 1 : 0);
+        p.tstop -= stopped ? 1 : 0;
+        p.waitc += refuse ? 1 : 0;                                                   // SC:408-411 (t_stop is already 0)
+        if (refuse) rng.skip(2);
+        p.Vpx = still ? 0.0 : p.Vpx; p.Vpy = still ? 0.0 : p.Vpy;
+    }
     bool walk_try = false;
-    if (in_walk_block) {
-        if (first_decision) {
-            choose = kerb_choice;
-            if (choose) { p.lpos = (p.dir < 0) ? (c.L - 1) : 0; p.fl &= ~PF_AT_CROSSING; }
-            p.fl |= PF_DECISION;
-            p.t0c = step;
-        }
-        if (p.tstop != 0) {                                                          // SC:335-339
-            p.Vpx = 0.0; p.Vpy = 0.0; p.tstop -= 1; p.t0c += 1;
-        } else if (!choose) {
-            // a refused kerb decision (every step of a waiting pedestrian): the uniform of SC:346 and the randint of SC:406 are
-            // drawn, but `u < 0.98 and choice` is False whatever u is and SC:410 overwrites t_stop -- the two blocks are
-            // consumed without being computed
-            rng.skip(2);
-            p.fl &= ~PF_DECISION; p.tstop = 0; p.waitc += 1;                         // SC:408-411
+    if (draw) {
+        const double u = rng.random();                                               // SC:346
+        if (u < 0.98) walk_try = true;
+        else {                                                                       // SC:405-413
+            p.tstop = rng.randint(T::rs_lo, T::rs_hi);
             p.Vpx = 0.0; p.Vpy = 0.0; p.t0c += 1;
-        } else {
-            const double u = rng.random();                                           // SC:346
-            if (u < 0.98) walk_try = true;
-            else {                                                                   // SC:405-413
-                p.tstop = rng.randint(T::rs_lo, T::rs_hi);
-                p.Vpx = 0.0; p.Vpy = 0.0; p.t0c += 1;
-            }
         }
     }
     if (walk_try) {                                                                  // SC:347-402
@@ -365,10 +370,9 @@ MH_HD void ped_step_stream(const EnvConst &c, const Geo &g, PedR &p, const CarSl
             p.Spx = p.Spx + p.Vpy * ratio * dt;
             p.Vpx = p.Vpy * ratio;
             p.crossc += 1;
-            if (change_line) {                                                       // apply_change_line SC:288-294
-                if (fabs(ny) >= g.Hp) p.lpos = (p.dir < 0) ? c.L : ((p.dir > 0) ? -1 : 0);
-                else p.lpos = (int)floor((ny + g.Hp) / g.cross);
-            }
+            // apply_change_line SC:288-294: change_line implies |ny| < Hp here, so its kerb branch is dead.  (Carrying the
+            // quotient of will_change_line down here instead of dividing again costs a register the kernel does not have: it spilled.)
+            if (change_line) p.lpos = (int)floor((ny + g.Hp) / g.cross);
         } else {                                                                     // SC:389-397
             p.fl |= PF_STOP;
             const double d = fabs(((double)p.dir * (g.W - dtc) - (double)p.dir * g.W / 2.0) - p.Spy);
