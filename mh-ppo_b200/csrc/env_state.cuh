@@ -136,11 +136,10 @@ MH_HD void load_env(const EnvArena &a, const EnvConst &c, int64_t n, EnvR<MC, MP
 
 // tag of a pedestrian whose fp32 Sp_y equals the fp32 rounding of a snapped position
 MH_HD uint32_t sym_tag(const Geo &g, const PedR &p, float spy32) {
-    if (spy32 == (float)sym_kerb(g, p)) return PB_Y_KERB;
-    if (spy32 == (float)sym_lane(g, p)) return PB_Y_LANE;
-    return 0u;
+    // both candidates are a handful of operations: selects, so that the lanes of a warp do not split here
+    const bool kerb = spy32 == (float)sym_kerb(g, p), lane = spy32 == (float)sym_lane(g, p);
+    return kerb ? PB_Y_KERB : (lane ? PB_Y_LANE : 0u);
 }
-
 template <int MC, int MP>
 MH_HD void store_env(const EnvArena &a, const EnvConst &c, int64_t n, const EnvR<MC, MP> &e) {
     uint32_t clo, chi;

@@ -614,9 +614,10 @@ MH_HD void env_step_thread(const EnvArena &a, const EnvConst &c, const RngKey &k
                     dlmin = dmin(dlmin, (fabs(Sc - p.Spx) - S.brake[i][t]) - 1.0 * S.Vc[i][t]);
             }
         }
-        if (pex) {                                                                   // pedestrian.get_data SC:449-460
+        {                                                                            // pedestrian.get_data SC:449-460 (a select: lanes disagree on pex)
             const double gate = ((p.fl & PF_CROSSING) && !left) ? 1.0 : 0.0;
-            p.delta = dmin(dlmin * gate, p.delta);
+            const double dnew = dmin(dlmin * gate, p.delta);
+            p.delta = pex ? dnew : p.delta;
         }
         // ---- wait-reward contribution (SC:855-857): the reference loops cars outside / pedestrians inside, but worst_dl is
         // per pedestrian and only sees the cars in ascending order, which this loop preserves
