@@ -625,7 +625,7 @@ MH_HD void env_step_thread(const EnvArena &a, const EnvConst &c, const RngKey &k
             const float acc_pen = (p.fl & PF_ACCIDENT) ? 20.0f : 0.0f;
             const float pw0 = (float)p.wdl;
             float pwdl = pw0;
-#pragma unroll 1
+#pragma unroll 4
             for (int i = 0; i < c.nlead; ++i) {
                 pwdl = fminf(pw0, S.wtmp[i][t] - acc_pen);
                 const bool grn = pex && (S.light[i][t] > 0.f);
