@@ -58,7 +58,7 @@ _lib = None
 def lib():
     global _lib
     if _lib is None:
-        L = C.CDLL(_build.build())
+        L = C.CDLL(_build.build_sanitized() if os.environ.get("HOSTSIM_SANITIZE") else _build.build())   # HOSTSIM_SANITIZE: tests/test_hostsim_sanitizers.py
         L.hs_create.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(EnvConst), C.c_int64, C.c_uint64, C.c_int64,
                                 C.POINTER(C.c_void_p)]
         L.hs_destroy.argtypes = [C.c_void_p]
