@@ -230,7 +230,8 @@ MH_HD WalkOut walk_sin(double W, double v0y, double Spy, double dt, int step, in
     const double av = fabs(v0y);
     const double T = W / (av + 10e-3);
     const bool check = ((av * PI_) / 2.0 <= Vm);
-    const double A = check ? (PI_ * av / 2.0 + 0.0) : (0.0 + (Vm - av) / (1.0 - (2.0 / PI_)));
+    constexpr double kAd = 1.0 - (2.0 / 3.141592653589793);
+    const double A = check ? (PI_ * av / 2.0 + 0.0) : (0.0 + div_rcp(Vm - av, kAd, 1.0 / kAd));
     const double B = check ? 0.0 : (Vm - A);
     const double w = PI_ / T;
     const double t = (double)step * dt + dt, t0 = (double)t0c * dt;
@@ -377,16 +378,16 @@ MH_HD void ped_step_stream(const EnvConst &c, const Geo &g, PedR &p, const CarSl
             p.fl |= PF_STOP;
             const double d = fabs(((double)p.dir * (g.W - dtc) - (double)p.dir * g.W / 2.0) - p.Spy);
             const double px = p.Vpx * d / fabs(p.Vpy + 10e-3);
-            p.Vpx = px / dt;
+            p.Vpx = div_rcp(px, dt, c.rdt);
             p.Spx = p.Spx + px;
-            p.Vpy = (double)p.dir * d / dt;
+            p.Vpy = div_rcp((double)p.dir * d, dt, c.rdt);
             p.Spy = (double)p.dir * ((g.W - dtc) - g.W / 2.0);
         }
     } else if (arrive) {                                                             // SC:320-328
         const double px = (p.Vpx * dt) * (fabs(g.Hn - dy) / fabs(p.Vpy * dt + 10e-3));
-        p.Vpx = px / dt;
+        p.Vpx = div_rcp(px, dt, c.rdt);
         p.Spx = p.Spx + px;
-        p.Vpy = (double)p.dir * fabs(-dy - g.Hp) / dt;
+        p.Vpy = div_rcp((double)p.dir * fabs(-dy - g.Hp), dt, c.rdt);
         p.Spy = (double)(-p.dir) * g.W / 2.0;
         p.tstop = 0;
         p.fl |= PF_AT_CROSSING;

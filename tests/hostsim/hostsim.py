@@ -19,7 +19,8 @@ class EnvConst(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("nC", "nP", "L", "nb_car", "nlead", "nA", "nobs", "done_idx", "sin_model")] + \
                [("dt", C.c_double), ("acc_lo", C.c_double), ("acc_hi", C.c_double), ("pb", C.c_double * 8),
                 ("cross_lo", C.c_double), ("cross_hi", C.c_double),
-                ("brake_den", C.c_double), ("idm_den", C.c_double), ("time_braking", C.c_double), ("brake_inv", C.c_double)]  # filled by hs_create
+                ("brake_den", C.c_double), ("idm_den", C.c_double), ("time_braking", C.c_double), ("brake_inv", C.c_double),
+                ("idm_rden", C.c_double), ("rdt", C.c_double)]  # filled by hs_create
 
 
 class View(C.Structure):
