@@ -38,6 +38,9 @@ struct RngKey { uint32_t k0, k1; int64_t env_id0; };
 // every iteration exposes a full HBM round trip (30 % of the warp stall samples sat on the first use of
 // those loads, profiles/round2_env_step_notes.md); fetching group i+1 into L2 while group i is computed
 // took 7 % off the step (L1 as the target measured the same; prefetching everything at kernel entry added nothing).
+#ifndef MH_ENTRY_PF
+#define MH_ENTRY_PF 1
+#endif
 #ifndef MH_PREFETCH
 #define MH_PREFETCH 2
 #endif
@@ -402,6 +405,13 @@ template <int V, int MC, int MP, int NT>
 MH_HD void env_step_thread(const EnvArena &a, const EnvConst &c, const RngKey &key, const StepIO &io, int64_t n,
                            CarSlots<MC, NT> &S, int t) {
     typedef VT<V> T;
+#if MH_ENTRY_PF
+    // the first car's rows and action words start their trip together with the env word (they do not depend on it): 2 % of the
+    // step (prefetching the first pedestrian or the second car here as well measured the same)
+    prefetch_next(&a.car_a[n]); prefetch_next(&a.car_b[n]);
+    prefetch_next(io.actions.ptr + n * io.actions.env_stride);
+    prefetch_next(io.actions.ptr + n * io.actions.env_stride + (int64_t)(c.nA / 2) * io.actions.comp_stride);
+#endif
     // ---- env word
     const float4 ee = a.env_e[n];
     const double cross = words_to_double(f2u(ee.x), f2u(ee.y));
