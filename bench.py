@@ -361,6 +361,7 @@ def main():
     ap.add_argument("--envs", type=int, default=0, help="override envs per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
+    ap.add_argument("--per-step", action="store_true", help="add the device time of every timed step to the JSON line (profile of an episode)")
     ap.add_argument("--ppo-envs", type=int, default=131072, help="envs per GPU of the PPO samples/s section (0 = skip)")
     ap.add_argument("--ppo-iters", type=int, default=2)
     ap.add_argument("--row-major-actions", action="store_true", help="device-resident actions as a contiguous [N, A] tensor (gym layout)")
@@ -434,7 +435,8 @@ def main():
     barrier()
     wall = time.perf_counter() - wall0
     launches = mhppo_b200.launch_count() - n0
-    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    dev_ms = sum(step_ms)
 
     # ---- end-to-end region: host buffers through the reference-facing call -------------------------
     Ke = max(8, min(K, 40))
@@ -486,7 +488,7 @@ def main():
             "config": workload_config(variant, nb_car, nb_ped, nb_lines, n_envs, state_bytes, flushed),
             "env_steps_per_s": env_steps, "slot_agent_steps_per_s": env_steps * (C + nb_ped),
             "active_agents_per_env": active, "wall_s_timed_region": wall, "gpu_launches": int(launches),
-            "clocks": clocks,
+            "clocks": clocks, **({"per_step_ms": [round(x, 5) for x in step_ms]} if args.per_step else {}),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": recorded_traffic(n_envs)[0] if args.workload == "scalable_432" else None,
                          "traffic_source": recorded_traffic(n_envs)[1] if args.workload == "scalable_432" else None,
