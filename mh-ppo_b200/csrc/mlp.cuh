@@ -98,4 +98,31 @@ __device__ __forceinline__ void stage_net(float *sw, const float *__restrict__ g
     for (int i = threadIdx.x; i < net_params(KP); i += blockDim.x) sw[i] = g[i];
 }
 
+// The same staging as ONE bulk asynchronous copy per net (TMA, `cp.async.bulk`): a single thread issues it, the bytes land
+// while the CTA does other work, completion is counted on an mbarrier.  Needs 16-byte aligned source / destination and a
+// size that is a multiple of 16 (net_params(16) * 4 = 19 472).
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bulk_bar_init(uint64_t *bar) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(bar)) : "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_expect(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)), "l"(src),
+                 "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (uint32_t polls = 0; !done; ++polls) {
+        if (polls == (1u << 26)) __trap();          // a lost copy is an error, not a hang
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done)
+                     : "r"(smem_addr(bar)), "r"(parity)
+                     : "memory");
+    }
+}
+
 }  // namespace mhppo

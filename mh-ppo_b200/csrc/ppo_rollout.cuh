@@ -172,11 +172,22 @@ __global__ void __launch_bounds__(kFwdBlock, 2) k_policy_act(RolloutDims d, cons
     float *res = rows + (size_t)kFwdBlock * kRowFwd;                       // [kFwdBlock][kActMaxP] means per (env, pedestrian)
     uint16_t *list = reinterpret_cast<uint16_t *>(res + kFwdBlock * kActMaxP);   // entries: env_local * 4 + pedestrian
     __shared__ int s_cnt[2];
-    stage_net<KP>(sw, net_cross);
-    stage_net<KP>(sw + NP, net_wait);
+    __shared__ __align__(8) uint64_t wbar;
     const int t = (int)threadIdx.x, lane = t & 31;
+    // the two nets (2 x 19 KB) travel as two bulk asynchronous copies (TMA) while the owners classify their pairs; the workers
+    // wait on the mbarrier before their first weight load.  (Unaligned caller buffers take the plain staging loop.)
+    constexpr uint32_t kNetBytes = (uint32_t)(net_params(KP) * sizeof(float));
+    static_assert(kNetBytes % 16 == 0 && (NP * sizeof(float)) % 16 == 0, "bulk copy granularity");
+    const bool bulk = (((reinterpret_cast<uintptr_t>(net_cross) | reinterpret_cast<uintptr_t>(net_wait)) & 15u) == 0);
+    if (bulk) { if (t == 0) bulk_bar_init(&wbar); }
+    else { stage_net<KP>(sw, net_cross); stage_net<KP>(sw + NP, net_wait); }
     if (t < 2) s_cnt[t] = 0;
     __syncthreads();
+    if (bulk && t == 0) {
+        bulk_expect(&wbar, 2 * kNetBytes);
+        bulk_g2s(sw, net_cross, kNetBytes, &wbar);
+        bulk_g2s(sw + NP, net_wait, kNetBytes, &wbar);
+    }
     const int64_t n0 = (int64_t)blockIdx.x * kFwdBlock;
     const int64_t n = n0 + t;
     const int i = blockIdx.y;
@@ -209,6 +220,7 @@ __global__ void __launch_bounds__(kFwdBlock, 2) k_policy_act(RolloutDims d, cons
         }
     }
     __syncthreads();
+    if (bulk) bulk_wait(&wbar, 0);
     // ---- 2. workers: one list entry per thread and pass, one net per warp
     {
         const int nA = s_cnt[0], nB = s_cnt[1];
