@@ -233,7 +233,7 @@ def bind_to_gpu_numa_node(torch, local):
         return {"numa_node": None, "note": type(e).__name__}
 
 
-def run_ppo(mh, torch, dist, world, rank, dev, n_envs, iters, warm=1, wl=("coop_scalable", 4, 3, 2)):
+def run_ppo(mh, torch, dist, world, rank, dev, n_envs, iters, warm=2, wl=("coop_scalable", 4, 3, 2)):
     """PPO samples/s (BASELINE.json metric, second half): one iteration = one 80-step episode in every env
     (Env_rollout.iterations_rand) + reward-to-go + 10 x (cross, wait) + 10 x choice update epochs (Algo_PPO.train)."""
     variant, nb_car, nb_ped, nb_lines = wl
@@ -244,7 +244,7 @@ def run_ppo(mh, torch, dist, world, rank, dev, n_envs, iters, warm=1, wl=("coop_
     algo = mh.Algo_PPO(mh.Model_PPO, env, num_states_c=13, num_states_d=D, num_actions=1, mean=-1.0, std=3.0, nb_cars=nb_car, dt=0.3)
     r = algo.rollout
     ev = lambda: torch.cuda.Event(enable_timing=True)
-    for _ in range(warm):
+    for _ in range(warm):      # (the second identical rollout call captures and instantiates the CUDA graph the later ones replay)
         r.iterations_rand(algo.actor_net_cross, algo.actor_net_wait, algo.actor_net_choice)
         algo.update()
     torch.cuda.synchronize()
