@@ -239,8 +239,6 @@ __global__ void __launch_bounds__(kTcGradBlock, 1) k_ppo_grad_tc(SampleSet ss, c
                 if (sel) ppo_loss<HEAD>(la, s, lcur, make_float4(o0, 0.f, 0.f, 0.f), d4, acc);
                 st4(row + WG::D4, make_float4(d4[0], 0.f, 0.f, 0.f));
                 bar_arrive(BAR_R4, NT);                       // a3 and dz are in the rows: dW4 on W
-                // the next tile's features travel from HBM while the backward chain runs
-                if (base + tstep < ss.Q) fetch(base + tstep, xn, seln, sn);
 #pragma unroll
                 for (int k4 = 0; k4 < H3 / 4; ++k4) {                                                 // delta3 = relu'(a3) * dz0 * W4[:, 0]
                     const float4 wk = ld4(w4c + 4 * k4);
@@ -251,6 +249,11 @@ __global__ void __launch_bounds__(kTcGradBlock, 1) k_ppo_grad_tc(SampleSet ss, c
             put_tmem<32>(ahi, alo, v);
             sync_for_mma();
             if (tid == 0) issue_layer_ts<H3, H2>(tmem + C3, Ahi, Alo, bw.w3h, bw.w3l, &sh.bar);
+            // The next tile's features travel from HBM while the backward chain runs.  Issued HERE, in front of two waits (the F4
+            // barrier and the MMA), not right after the loss: ptxas reuses the loads' address registers for the next shared-memory
+            // loads and guards them with the loads' completion scoreboard, so whatever follows the fetch waits out the whole
+            // global-memory latency (13 % of the epilogue warps' time sat on that one LDS, profiles/round2 ncu source page).
+            if (base + tstep < ss.Q) fetch(base + tstep, xn, seln, sn);
             bar_sync(BAR_F4, NT);                             // a3 has been read
 #pragma unroll
             for (int j = 0; j < 32; j += 4) st4(row + WG::A3 + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
