@@ -3,10 +3,13 @@
 // Replaces Crosswalk_hybrid_multi_*.step (SC:789-878 and siblings) + in-kernel auto-reset.
 //
 // Shape of the computation (chosen for the SM, not copied from the Python control flow):
-//  * the kernel is bound by instruction issue, not by HBM: ~8k mostly-fp64 instructions per env
-//    step against 976 bytes.  What limits the issue rate is (a) how many warps an SM can hold
-//    (registers) and (b) how much SASS a warp walks per step (instruction-cache misses were the
-//    second-largest stall of the unrolled versions, profiles/round1_env_step_r1d_summary.txt).
+//  * the kernel is bound by latency, not by HBM and not by issue slots: a warp walks ~8k warp-level
+//    instructions per step (976 bytes of state per env), an SM holds 20 warps (registers), and every
+//    instruction costs ~7 cycles of its warp's life whether 3 or 32 lanes are active
+//    (profiles/round2_env_step_notes.md).  What counts is (a) how many warps an SM can hold, (b) how
+//    much SASS a warp walks per step -- instruction-cache misses were the second-largest stall of the
+//    unrolled versions (profiles/round1_env_step_r1d_summary.txt) -- and (c) that lanes which take the
+//    same rare path take it TOGETHER (one reconvergence point in front of every expensive block).
 //    So the CARS of a CTA live in shared memory ([field][slot][thread], conflict-free) and every
 //    loop over cars is ROLLED: one copy of each (pedestrian, car) body in SASS, few live
 //    registers, 5 CTAs per SM instead of 3;
