@@ -70,7 +70,8 @@ __device__ __forceinline__ void issue_layer_ts(uint32_t d_tmem, uint32_t a_hi, u
 
 constexpr int kTcGradRow = 16 + H1 + H2 + H3 + OP;       // 148 floats: 16-byte aligned rows, stride = 20 (mod 32) words -> conflict-free 128-bit accesses
 constexpr int kTcGradNetFloats = (tcm::NetTiles<16>::FLOATS + 255) & ~255;
-constexpr size_t kTcGradSmemFloats = (size_t)kTcGradNetFloats + BwdTiles::FLOATS + (size_t)2 * 128 * kTcGradRow;      // two row buffers
+constexpr int kTcGradStageExtra = 256;             // the part of the fetch staging area that does not fit the unused layer-4 tiles
+constexpr size_t kTcGradSmemFloats = (size_t)kTcGradNetFloats + BwdTiles::FLOATS + (size_t)2 * 128 * kTcGradRow + kTcGradStageExtra;      // two row buffers
 
 // Warp-specialised CTA: warps 0-3 ("E", thread = sample = TMEM lane) issue the MMAs and run the epilogues; warps 4-7 ("W")
 // only accumulate the weight gradient.  The two groups hand the row buffer back and forth through named barriers:
@@ -104,6 +105,13 @@ __global__ void __launch_bounds__(kTcGradBlock, 1) k_ppo_grad_tc(SampleSet ss, c
     constexpr int RBUF = 128 * kTcGradRow;
     w.stage(net);
     bw.stage<KP>(net);
+    // Landing area of the asynchronous fetch of the NEXT tile (cp.async: no destination registers, nothing for later
+    // instructions to wait on), [array][thread]: the layer-4 operand tiles of both tile sets are never read by this kernel (the
+    // output layer runs on the CUDA cores), 2 x 1024 floats, plus 256 floats of its own.
+    float *stA = w.w4h;                                             // features 0..7
+    float *stB = bw.w4h;                                            // features 8..12, rtg, V, old log-prob
+    float *stC = rows0 + 2 * RBUF;                                  // action, compacted-column index of the tile after next
+    static_assert(tcm::NetTiles<KP>::W4 == 512 && BwdTiles::W4 == 512, "staging area = the two unused layer-4 tile pairs");
     static_assert(HEAD == 0 || HEAD == 1, "single-output heads only: the categorical choice nets use k_ppo_grad");
     for (int i = threadIdx.x; i <= H3; i += blockDim.x) w4c[i] = (i < H3) ? net[off_w4(KP) + i * OP] : net[off_b4(KP)];
     // TMEM: forward accumulators in columns 0-63; each backward layer has its own columns, so a delta can be read a second time
@@ -152,23 +160,65 @@ __global__ void __launch_bounds__(kTcGradBlock, 1) k_ppo_grad_tc(SampleSet ss, c
         auto wait_mma = [&]() { ok &= tc::mbar_wait(&sh.bar, phase); phase ^= 1; tc::fence_after(); };
         LossIn lin;
         lin.rtg = lin.V = lin.act = lin.logp = 0.f;
-        auto fetch = [&](int64_t base, float (&x)[KP], bool &sel, int64_t &s) {      // features and loss inputs of a tile, ahead of use
+        // ---- asynchronous fetch.  issue(base, idx): the features and loss inputs of work item base + tid start their trip into
+        // this thread's slots of the staging area; collect(): they are read back one tile later.  The compacted-column index a
+        // tile needs for its addresses is itself fetched one tile earlier (slot stC[128 + tid]), so no address waits for a load.
+        auto cp4 = [](float *dst, const void *src) {
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(tc::smem_u32(dst)), "l"(src) : "memory");
+        };
+        auto issue = [&](int64_t base, int32_t col, bool &sel, int64_t &s) {      // col: ss.idx[k] of this item (ignored without a list)
+            const int64_t q = base + tid;
+            sel = q < ss.Q;
             s = 0;
-            sel = map_sample(ss, base + tid, s);
+            if (sel) {
+                const int64_t tt = q / ss.K, k = q - tt * ss.K;
+                s = tt * ss.CN + (ss.idx ? (int64_t)col : k);
 #pragma unroll
-            for (int k = 0; k < KP; ++k) x[k] = (sel && k < ss.D) ? ss.x[(int64_t)k * ss.S + s] : 0.f;
-            if (sel) lin = load_loss_in<HEAD>(la, s);
+                for (int f = 0; f < 13; ++f)
+                    if (f < ss.D) cp4((f < 8 ? stA + f * 128 : stB + (f - 8) * 128) + tid, ss.x + (int64_t)f * ss.S + s);
+                cp4(stB + 5 * 128 + tid, la.rtg + s);
+                if (HEAD != 0) { cp4(stB + 6 * 128 + tid, la.V + s); cp4(stB + 7 * 128 + tid, la.logp_old + s); }
+                if (HEAD == 1) cp4(stC + tid, la.act + s);
+            }
+        };
+        auto issue_col = [&](int64_t base) {                                       // the column index of work item base + tid
+            const int64_t q = base + tid;
+            if (ss.idx && q < ss.Q) cp4(stC + 128 + tid, ss.idx + (q % ss.K));
+        };
+        auto commit_wait = [&]() { asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory"); };
+        auto collect = [&](bool sel, float (&x)[KP]) {
+#pragma unroll
+            for (int f = 0; f < KP; ++f) x[f] = (sel && f < ss.D && f < 13) ? (f < 8 ? stA[f * 128 + tid] : stB[(f - 8) * 128 + tid]) : 0.f;
+            if (sel) {
+                lin.rtg = stB[5 * 128 + tid];
+                if (HEAD != 0) { lin.V = stB[6 * 128 + tid]; lin.logp = stB[7 * 128 + tid]; }
+                if (HEAD == 1) lin.act = stC[tid];
+            }
         };
         float xn[KP];
         bool seln = false;
         int64_t sn = 0;
-        if (tile0 < ss.Q) fetch(tile0, xn, seln, sn);
+        {   // prologue: the first tile's column index with a plain load, then its data and the second tile's index in flight
+            const int64_t q = tile0 + tid;
+            const int32_t col0 = (ss.idx && q < ss.Q) ? ss.idx[q % ss.K] : 0;
+            issue(tile0, col0, seln, sn);
+            issue_col(tile0 + tstep);
+        }
         int t = 0;
         for (int64_t base = tile0; base < ss.Q; base += tstep, ++t) {
             float *row = rows0 + (t & 1) * RBUF + (size_t)tid * ROW;
+            // this tile's data (issued one tile ago) and the next tile's column index have landed; the next tile's data and the
+            // index of the tile after it start their trip now and travel during the whole tile
+            commit_wait();
             const bool sel = seln;
             const int64_t s = sn;
+            collect(sel, xn);
             const LossIn lcur = lin;
+            {
+                const int32_t col1 = __float_as_int(stC[128 + tid]);
+                issue(base + tstep, col1, seln, sn);
+                issue_col(base + 2 * tstep);
+            }
             float v[32];
             uint32_t m1 = 0, m2a = 0, m2b = 0, m3 = 0;                // ReLU masks of the three hidden layers
             // ---- forward.  This tile's row buffer still belongs to W (layer 1 + biases of the tile before the previous one) until its F1;
@@ -249,11 +299,6 @@ __global__ void __launch_bounds__(kTcGradBlock, 1) k_ppo_grad_tc(SampleSet ss, c
             put_tmem<32>(ahi, alo, v);
             sync_for_mma();
             if (tid == 0) issue_layer_ts<H3, H2>(tmem + C3, Ahi, Alo, bw.w3h, bw.w3l, &sh.bar);
-            // The next tile's features travel from HBM while the backward chain runs.  Issued HERE, in front of two waits (the F4
-            // barrier and the MMA), not right after the loss: ptxas reuses the loads' address registers for the next shared-memory
-            // loads and guards them with the loads' completion scoreboard, so whatever follows the fetch waits out the whole
-            // global-memory latency (13 % of the epilogue warps' time sat on that one LDS, profiles/round2 ncu source page).
-            if (base + tstep < ss.Q) fetch(base + tstep, xn, seln, sn);
             bar_sync(BAR_F4, NT);                             // a3 has been read
 #pragma unroll
             for (int j = 0; j < 32; j += 4) st4(row + WG::A3 + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
@@ -292,6 +337,7 @@ __global__ void __launch_bounds__(kTcGradBlock, 1) k_ppo_grad_tc(SampleSet ss, c
             for (int j = 0; j < 32; j += 4) st4(row + WG::A1 + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
             bar_arrive(BAR_R1, NT);                           // delta1 is in the rows: layer 1 and the biases
         }
+        asm volatile("cp.async.wait_all;" ::: "memory");     // (nothing is in flight past the last tile; belt and braces before the area is reused)
         // the last two tiles' rows have been read (one F1 arrival of W is still unmatched per buffer in use)
         if (t >= 2) bar_sync((t & 1) ? BAR_F1B : BAR_F1, NT);
         if (t >= 1) bar_sync(((t - 1) & 1) ? BAR_F1B : BAR_F1, NT);
