@@ -11,6 +11,7 @@
 //                 the reduction runs over samples, which a tf32 MMA could only read from 128B-swizzled MN-major tiles
 //                 (tc.cuh); it runs on four dedicated warps CONCURRENTLY with the chain of backward-data MMAs and their
 //                 epilogues (ReLU masks kept in registers from the forward pass) on the other four.
+// The next tile's features / loss inputs / column index are fetched with cp.async into the unused layer-4 tile space.
 // Every epilogue writes its row twice: fp32 into the row buffer (weight gradient) and hi/lo into the next A operand tile.
 #pragma once
 #include "ppo_update.cuh"
