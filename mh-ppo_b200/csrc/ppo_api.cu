@@ -109,7 +109,8 @@ static int launch_grad_tc(int head, const SampleSet &ss, const float *net, const
 
 template <int KP>
 static int launch_grad(int head, const SampleSet &ss, const float *net, const LossArgs &la, const Workspace &w, cudaStream_t s) {
-    if (KP == 16 && head != 2 && use_tc(false)) return launch_grad_tc(head, ss, net, la, w, s);
+    // (the tensor-core kernel stages exactly the 13 features of the cross / wait nets; a wider 16-padded input takes the FFMA kernel)
+    if (KP == 16 && ss.D <= 13 && head != 2 && use_tc(false)) return launch_grad_tc(head, ss, net, la, w, s);
     const size_t sm = smem_grad<KP>();
     if (head == 0) { SET_SMEM((k_ppo_grad<KP, 0>), sm); k_ppo_grad<KP, 0><<<kGradGrid, kMlpBlock, sm, s>>>(ss, net, la, w.gpartial, w.lpartial); }
     else if (head == 1) { SET_SMEM((k_ppo_grad<KP, 1>), sm); k_ppo_grad<KP, 1><<<kGradGrid, kMlpBlock, sm, s>>>(ss, net, la, w.gpartial, w.lpartial); }
